@@ -1,0 +1,161 @@
+/* pero_b200.h — C ABI of the B200-native quantize-and-predict path of DCGM/pero-pretraining.
+ *
+ * The reference has no FFI layer: its boundary for this path is a set of torch.nn.Module methods
+ * (SURVEY.md §8b).  Every entry point below replaces the body of one of those methods (or a
+ * group of torch ops inside it) and cites it as  file:line  relative to the reference root.
+ * The Python host side (pero_pretraining_b200/) keeps the reference's module signatures and calls
+ * these functions through ctypes; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless stated; sizes are int64_t; no torch types.
+ *   - The caller owns every buffer including workspaces; the library allocates nothing persistent,
+ *     keeps no state between calls and is re-entrant.  All work is enqueued on `stream`; no call
+ *     synchronises, so sequences of calls are CUDA-graph capturable.
+ *   - Return 0 on success; negative = PERO_ERR_* below; positive = a cudaError_t.  Never throws, never
+ *     prints.  pero_strerror() names any code.
+ *   - "frames" are the rows the path works on: N = n_lines * frames_per_line feature vectors of
+ *     dimension D (one per 8-px column of a 40-px text line); "codebook" is K codewords x D.
+ */
+#ifndef PERO_B200_H_
+#define PERO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pero_stream_t;
+
+#define PERO_OK 0
+#define PERO_ERR_BAD_SHAPE (-1)
+#define PERO_ERR_BAD_ALIGN (-2)
+#define PERO_ERR_WORKSPACE (-3)
+#define PERO_ERR_ARCH (-4)
+#define PERO_ERR_NULL (-5)
+#define PERO_ERR_DRIVER (-6)
+#define PERO_ERR_UNSUPPORTED (-7)
+
+int pero_version(void);
+const char* pero_strerror(int code);
+/* 0 when the current device is sm_100 (B200); PERO_ERR_ARCH otherwise. */
+int pero_check_device(void);
+
+/* ------------------------------------------------------------------ nearest-codeword assignment
+ * Replaces  models/autoencoders.py:212-217  (distances + argmin of VectorQuantizer.forward) and
+ *           scripts/produce_kmeans_labels.py:72-76 (cdist + argmin of the FQ / PQ-AE labeller).
+ *
+ * pero_vq_codebook_prepare: fp32 codebook [K, D] -> opaque device blob holding the bf16 operand
+ *   (rows padded to a multiple of 64 columns) and |c|^2 in fp32 computed from the fp32 weights.
+ *   Re-run whenever the codebook changes (pero_vq_ema_apply refreshes it itself).
+ */
+size_t pero_vq_codebook_bytes(int64_t K, int64_t D);
+int pero_vq_codebook_prepare(const float* weight, int64_t K, int64_t D, void* codebook, size_t codebook_bytes,
+                             pero_stream_t stream);
+
+/* pero_vq_assign: for every frame, the index of the nearest codeword (lowest index on exact ties).
+ *   x               fp32 frames; channels_first = 1: [n_lines, D, frames_per_line] (the NCHW tensor the
+ *                   quantizer receives, H*W collapsed; autoencoders.py:205-209 permutes it),
+ *                   channels_first = 0: [n_lines * frames_per_line, D] rows (kmeans labeller).
+ *   index_offset    added to every index (codebook shard k0 when the codebook is sharded).
+ *   idx   [N] int64 or NULL, dmin [N] fp32 or NULL (|c|^2 - 2<x,c> of the winner, i.e. the squared
+ *                   distance minus |x|^2), written only when `packed_io` is NULL.
+ *   packed_io [N] u64 or NULL: when given, results are min-merged into it as
+ *                   (order_key(dmin) << 32 | index) and idx/dmin are left untouched — the caller
+ *                   all-reduces it with MIN over codebook shards and calls pero_vq_unpack.  Must be
+ *                   pre-set to all ones (pero_vq_packed_init).
+ *   x_rows [N, D] fp32 or NULL: row-major copy of the frames for the gather / EMA stages.
+ */
+size_t pero_vq_assign_workspace_bytes(int64_t N, int64_t K, int64_t D);
+int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int channels_first, int64_t K,
+                   int64_t D, const void* codebook, int64_t index_offset, int64_t* idx, float* dmin,
+                   uint64_t* packed_io, float* x_rows, void* workspace, size_t workspace_bytes,
+                   pero_stream_t stream);
+int pero_vq_packed_init(uint64_t* packed, int64_t N, pero_stream_t stream);
+int pero_vq_unpack(const uint64_t* packed, int64_t N, int64_t* idx, float* dmin, pero_stream_t stream);
+
+/* ------------------------------------------------------------------ quantize + straight-through
+ * Replaces  models/autoencoders.py:218-222, 239-241  (one-hot, encodings @ weight, straight-through,
+ * permute back).  out = x + (weight[idx] - x), evaluated in fp32 exactly as the reference does,
+ * written channels-first [n_lines, D, frames_per_line] (or as rows when channels_first = 0).
+ */
+int pero_vq_gather_st(const float* x_rows, const int64_t* idx, const float* weight, int64_t n_lines,
+                      int64_t frames_per_line, int channels_first, int64_t K, int64_t D, float* out,
+                      pero_stream_t stream);
+
+/* ------------------------------------------------------------------ EMA codebook update
+ * Replaces  models/autoencoders.py:225-237.
+ * pero_vq_ema_accumulate: deterministic sort-based segmented sum:
+ *     sums[k, :] = sum of x_rows[n, :] over frames with idx[n] == k (ascending n),  counts[k] = #frames.
+ *   `sums_counts` is ONE contiguous fp32 buffer [K*D + K] (sums then counts) so that data-parallel
+ *   ranks all-reduce it with a single SUM before pero_vq_ema_apply.
+ * pero_vq_ema_apply:
+ *     cs <- cs*decay + (1-decay)*counts;  n = sum(cs);  cs <- (cs + eps) / (n + K*eps) * n
+ *     ema_w <- ema_w*decay + (1-decay)*sums;  weight <- ema_w / cs[:, None]
+ *   and, when `codebook` is not NULL, refreshes the prepared blob for the next assign.
+ */
+size_t pero_vq_ema_workspace_bytes(int64_t N, int64_t K, int64_t D);
+int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, int64_t K, int64_t D,
+                           float* sums_counts, void* workspace, size_t workspace_bytes, pero_stream_t stream);
+int pero_vq_ema_apply(const float* sums_counts, int64_t K, int64_t D, float decay, float epsilon, float* ema_w,
+                      float* ema_cluster_size, float* weight, void* codebook, size_t codebook_bytes,
+                      void* workspace, size_t workspace_bytes, pero_stream_t stream);
+/* counts[k] = #frames with idx == k as int64 (models/autoencoders.py:165, torch.bincount). */
+int pero_vq_counts(const int64_t* idx, int64_t N, int64_t K, int64_t* counts, pero_stream_t stream);
+
+/* ------------------------------------------------------------------ commitment / latent loss
+ * Replaces  models/autoencoders.py:193-202  (VectorQuantizer.calculate_loss = mse_loss terms).
+ * pero_mse_fwd: out[0] = scale * mean((a - b)^2), deterministic two-stage reduction.
+ * pero_mse_bwd: g_b = coef * grad_out[0] * (b - a), and g_a = -g_b when g_a != NULL
+ *               (coef = 2 * weight / numel).
+ */
+size_t pero_mse_workspace_bytes(int64_t numel);
+int pero_mse_fwd(const float* a, const float* b, int64_t numel, float scale, float* out, void* workspace,
+                 size_t workspace_bytes, pero_stream_t stream);
+int pero_mse_bwd(const float* a, const float* b, int64_t numel, float coef, const float* grad_out, float* g_a,
+                 float* g_b, pero_stream_t stream);
+
+/* ------------------------------------------------------------------ masked-label cross-entropy
+ * Replaces  masked_pretraining/model.py:104-105 (LinearHead) + :78-82 (MaskedCrossEntropyLoss):
+ * gather the masked frames, logits = h @ W^T + b over them only, mean cross-entropy with an online
+ * log-sum-exp; the [M, V] logits never reach HBM in the forward.
+ *
+ * pero_head_prepare: fp32 head [V, Dh] (+ bias [V]) -> opaque blob with bf16 W, bf16 W^T and the bias.
+ * pero_masked_ce_fwd:
+ *   h        hidden states [N, Dh], fp32 (h_is_bf16 = 0) or bf16 (1)
+ *   rows     [M] int32 frame indices of the masked frames, ascending (mask == 1 order)
+ *   labels   [N] int64 (only labels[rows[m]] are read; must lie in [0, V))
+ *   loss_sum [1] fp32: sum over masked frames of (lse - logit[label]);  lse [M] fp32 saved for backward
+ * pero_masked_ce_bwd: gradients of  loss = grad_scale[0] * inv_count * loss_sum:
+ *   d_h [N, Dh] (same dtype as h, zero on unmasked frames), d_W [V, Dh] fp32, d_b [V] fp32.
+ */
+size_t pero_head_bytes(int64_t V, int64_t Dh);
+int pero_head_prepare(const float* W, const float* bias, int64_t V, int64_t Dh, void* head, size_t head_bytes,
+                      pero_stream_t stream);
+size_t pero_masked_ce_workspace_bytes(int64_t N, int64_t M, int64_t V, int64_t Dh);
+int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+                       const int64_t* labels, const void* head, int64_t V, float* loss_sum, float* lse,
+                       void* workspace, size_t workspace_bytes, pero_stream_t stream);
+int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+                       const int64_t* labels, const void* head, int64_t V, const float* lse,
+                       const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
+                       void* workspace, size_t workspace_bytes, pero_stream_t stream);
+/* Ordered compaction of a {0,1} mask without a host sync: rows[0..count) = indices with mask != 0
+ * (optionally also requiring labels[i] >= 0), count[0] = their number.  mask_dtype: 0 int64, 1 int32,
+ * 2 uint8/bool. */
+size_t pero_mask_compact_workspace_bytes(int64_t N);
+int pero_mask_compact(const void* mask, int mask_dtype, int want_value, const int64_t* labels_or_null, int64_t N,
+                      int32_t* rows, int32_t* count, void* workspace, size_t workspace_bytes,
+                      pero_stream_t stream);
+
+/* ------------------------------------------------------------------ test hook
+ * C[rows_a, rows_b] = A @ B^T through the same tcgen05 core (bf16 operands with row pitch `kd`,
+ * fp32 out).  variant: bit0 = CTA pairs (cta_group::2), bit1 = resident A.  Used by tests only. */
+int pero_debug_gemm_tn(const void* a_bf16, int64_t rows_a, const void* b_bf16, int64_t rows_b, int64_t kd,
+                       int variant, int num_splits, float* out, pero_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERO_B200_H_ */

@@ -1,0 +1,120 @@
+// Host side of gemm_core.cuh: TMA tensor-map construction (driver entry point fetched through the
+// runtime, so the library does not link libcuda) and the launch helper that sizes shared memory,
+// the stage ring and the grid.
+#pragma once
+#include "gemm_core.cuh"
+#include "errors.h"
+
+namespace pero {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Row-major bf16 matrix [rows, cols] with row pitch `pitch_elems` (multiple of 8 elements), tiled in
+// boxes of {64 columns, box_rows rows}, SWIZZLE_128B, out-of-bounds elements read as zero.
+inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                          uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return PERO_ERR_DRIVER;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems & 7u) || box_rows == 0 || box_rows > 256)
+        return PERO_ERR_BAD_ALIGN;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PERO_OK : PERO_ERR_DRIVER;
+}
+
+inline int device_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+constexpr size_t kSmemBudget = 227 * 1024;
+constexpr size_t kSmemFloor = 120 * 1024;   // > half an SM: never two TMEM-hungry CTAs on one SM
+
+// Picks the deepest ring that fits; returns 0 when even 2 stages do not fit.
+inline int pick_stages(int cta_group, bool a_resident, int num_kb) {
+    for (int s = kMaxStages; s >= 2; --s)
+        if (gemm_smem_bytes(cta_group, a_resident, num_kb, s) <= kSmemBudget) return s;
+    return 0;
+}
+
+// A: [rows_a, kd] bf16, pitch_a elements; B: [rows_b, kd] bf16, pitch_b elements; kd % 64 == 0.
+// `workers` = number of CTAs (kCtaGroup == 1) or CTA pairs (== 2); 0 = fill the machine.
+template <int kCtaGroup, bool kAResident, class Epi>
+int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int rows_b, int pitch_b, int kd,
+                   int num_ks, int split_mode, int fixed_s, int workers, const typename Epi::Params& ep,
+                   cudaStream_t stream) {
+    if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
+    GemmShape sh;
+    sh.rows_a = rows_a; sh.rows_b = rows_b;
+    sh.num_kb = kd / kBlockK;
+    sh.num_rb = (rows_a + kBlockM * kCtaGroup - 1) / (kBlockM * kCtaGroup);
+    sh.num_ct = (rows_b + kBlockN - 1) / kBlockN;
+    sh.num_ks = num_ks < 1 ? 1 : num_ks;
+    sh.kb_per_split = (sh.num_kb + sh.num_ks - 1) / sh.num_ks;
+    sh.num_ks = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;   // no empty splits
+    sh.split_mode = split_mode; sh.fixed_s = fixed_s < 1 ? 1 : fixed_s;
+    if (kAResident && (sh.num_ks != 1 || sh.num_kb > kMaxAKb)) return PERO_ERR_BAD_SHAPE;
+    sh.num_stages = pick_stages(kCtaGroup, kAResident, sh.num_kb);
+    if (sh.num_stages < 2) return PERO_ERR_BAD_SHAPE;
+
+    CUtensorMap ta, tb;
+    int rc = make_tmap_bf16(&ta, a, (uint64_t)rows_a, (uint64_t)kd, (uint64_t)pitch_a, kBlockM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tb, b, (uint64_t)rows_b, (uint64_t)kd, (uint64_t)pitch_b, kBlockN / kCtaGroup);
+    if (rc) return rc;
+
+    const long long units = (long long)sh.num_rb * sh.num_ct * sh.num_ks;
+    const int max_workers = device_sm_count() / kCtaGroup;
+    if (split_mode == 1) workers = sh.num_rb * sh.fixed_s;
+    else if (workers <= 0 || workers > max_workers) workers = max_workers;
+    if (split_mode == 0 && workers > units) workers = (int)units;
+
+    size_t smem = gemm_smem_bytes(kCtaGroup, kAResident, sh.num_kb, sh.num_stages);
+    if (smem < kSmemFloor) smem = kSmemFloor;
+    auto kern = gemm_tn_kernel<kCtaGroup, kAResident, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(workers * kCtaGroup));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtaGroup; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, sh, ep);
+    return e == cudaSuccess ? PERO_OK : (int)e;
+}
+
+}  // namespace pero
