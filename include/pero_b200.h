@@ -61,19 +61,19 @@ int pero_vq_codebook_prepare(const float* weight, int64_t K, int64_t D, void* co
  *   index_offset    added to every index (codebook shard k0 when the codebook is sharded).
  *   idx   [N] int64 or NULL, dmin [N] fp32 or NULL (|c|^2 - 2<x,c> of the winner, i.e. the squared
  *                   distance minus |x|^2), written only when `packed_io` is NULL.
- *   packed_io [N] u64 or NULL: when given, results are min-merged into it as
+ *   packed_io [N] int64 or NULL: when given, results are min-merged into it as the SIGNED word
  *                   (order_key(dmin) << 32 | index) and idx/dmin are left untouched — the caller
- *                   all-reduces it with MIN over codebook shards and calls pero_vq_unpack.  Must be
- *                   pre-set to all ones (pero_vq_packed_init).
+ *                   all-reduces it with a plain int64 MIN over codebook shards and calls
+ *                   pero_vq_unpack.  Must be pre-set to INT64_MAX (pero_vq_packed_init).
  *   x_rows [N, D] fp32 or NULL: row-major copy of the frames for the gather / EMA stages.
  */
 size_t pero_vq_assign_workspace_bytes(int64_t N, int64_t K, int64_t D);
 int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int channels_first, int64_t K,
                    int64_t D, const void* codebook, int64_t index_offset, int64_t* idx, float* dmin,
-                   uint64_t* packed_io, float* x_rows, void* workspace, size_t workspace_bytes,
+                   int64_t* packed_io, float* x_rows, void* workspace, size_t workspace_bytes,
                    pero_stream_t stream);
-int pero_vq_packed_init(uint64_t* packed, int64_t N, pero_stream_t stream);
-int pero_vq_unpack(const uint64_t* packed, int64_t N, int64_t* idx, float* dmin, pero_stream_t stream);
+int pero_vq_packed_init(int64_t* packed, int64_t N, pero_stream_t stream);
+int pero_vq_unpack(const int64_t* packed, int64_t N, int64_t* idx, float* dmin, pero_stream_t stream);
 
 /* ------------------------------------------------------------------ quantize + straight-through
  * Replaces  models/autoencoders.py:218-222, 239-241  (one-hot, encodings @ weight, straight-through,
@@ -98,7 +98,7 @@ int pero_vq_gather_st(const float* x_rows, const int64_t* idx, const float* weig
 size_t pero_vq_ema_workspace_bytes(int64_t N, int64_t K, int64_t D);
 int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, int64_t K, int64_t D,
                            float* sums_counts, void* workspace, size_t workspace_bytes, pero_stream_t stream);
-int pero_vq_ema_apply(const float* sums_counts, int64_t K, int64_t D, float decay, float epsilon, float* ema_w,
+int pero_vq_ema_apply(const float* sums_counts, int64_t K, int64_t D, double decay, double epsilon, float* ema_w,
                       float* ema_cluster_size, float* weight, void* codebook, size_t codebook_bytes,
                       void* workspace, size_t workspace_bytes, pero_stream_t stream);
 /* counts[k] = #frames with idx == k as int64 (models/autoencoders.py:165, torch.bincount). */
@@ -106,13 +106,14 @@ int pero_vq_counts(const int64_t* idx, int64_t N, int64_t K, int64_t* counts, pe
 
 /* ------------------------------------------------------------------ commitment / latent loss
  * Replaces  models/autoencoders.py:193-202  (VectorQuantizer.calculate_loss = mse_loss terms).
- * pero_mse_fwd: out[0] = scale * mean((a - b)^2), deterministic two-stage reduction.
+ * pero_mse_fwd: m = mean((a - b)^2); out[0] = scale_a * m + scale_b * m (each product rounded to fp32,
+ *               like q_latent_loss + commitment_cost * e_latent_loss); deterministic two-stage reduction.
  * pero_mse_bwd: g_b = coef * grad_out[0] * (b - a), and g_a = -g_b when g_a != NULL
  *               (coef = 2 * weight / numel).
  */
 size_t pero_mse_workspace_bytes(int64_t numel);
-int pero_mse_fwd(const float* a, const float* b, int64_t numel, float scale, float* out, void* workspace,
-                 size_t workspace_bytes, pero_stream_t stream);
+int pero_mse_fwd(const float* a, const float* b, int64_t numel, float scale_a, float scale_b, float* out,
+                 void* workspace, size_t workspace_bytes, pero_stream_t stream);
 int pero_mse_bwd(const float* a, const float* b, int64_t numel, float coef, const float* grad_out, float* g_a,
                  float* g_b, pero_stream_t stream);
 
@@ -141,6 +142,16 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
                        const int64_t* labels, const void* head, int64_t V, const float* lse,
                        const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
                        void* workspace, size_t workspace_bytes, pero_stream_t stream);
+/* Logits-in variant for callers that already hold logits [N, V] (fp32 or bf16):
+ * MaskedCrossEntropyLoss.forward(output, labels, mask), masked_pretraining/model.py:78-82.
+ * workspace: >= 4*M bytes rounded up to 256.  d_logits has the dtype of logits; zero_init != 0 clears it
+ * first (rows not listed get zero gradient). */
+int pero_ce_logits_fwd(const void* logits, int is_bf16, int64_t N, int64_t V, const int32_t* rows, int64_t M,
+                       const int64_t* labels, float* loss_sum, float* lse, void* workspace, size_t workspace_bytes,
+                       pero_stream_t stream);
+int pero_ce_logits_bwd(const void* logits, int is_bf16, int64_t N, int64_t V, const int32_t* rows, int64_t M,
+                       const int64_t* labels, const float* lse, const float* grad_scale, float inv_count, int zero_init,
+                       void* d_logits, pero_stream_t stream);
 /* Ordered compaction of a {0,1} mask without a host sync: rows[0..count) = indices with mask != 0
  * (optionally also requiring labels[i] >= 0), count[0] = their number.  mask_dtype: 0 int64, 1 int32,
  * 2 uint8/bool. */

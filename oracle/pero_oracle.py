@@ -41,15 +41,18 @@ def vq_assign_fp32(flat, weight):
     return torch.argmin(vq_distances(flat, weight), dim=1)
 
 
-def vq_forward(inputs, weight, ema_w=None, ema_cluster_size=None, decay=0.99, epsilon=1e-5, training=True):
+def vq_forward(inputs, weight, ema_w=None, ema_cluster_size=None, decay=0.99, epsilon=1e-5, training=True,
+               indices_override=None):
     """VectorQuantizer.forward restated as a pure function.  models/autoencoders.py:204-241.
 
     Returns dict(quantized [Nl,D,H,W] (forward value of the straight-through expression), indices [N] int64,
     and -- when decay > 0 and training -- the NEW weight / ema_w / ema_cluster_size; the quantized output of
-    this call uses the OLD weight, exactly as the reference (the update takes effect next step)."""
+    this call uses the OLD weight, exactly as the reference (the update takes effect next step).
+    `indices_override` replaces the arg-min result (tests use it to check everything downstream of the
+    assignment independently of bf16 near-tie flips)."""
     flat, nhwc_shape = flatten_frames(inputs)
     K = weight.shape[0]
-    idx = vq_assign_fp32(flat, weight)
+    idx = vq_assign_fp32(flat, weight) if indices_override is None else indices_override
     # :218-222 one-hot @ weight  ==  gather (each output row has exactly one non-zero product)
     encodings = torch.zeros(idx.shape[0], K, dtype=flat.dtype)
     encodings.scatter_(1, idx.unsqueeze(1), 1)

@@ -16,6 +16,7 @@ c_sz = ctypes.c_size_t
 c_vp = ctypes.c_void_p
 c_int = ctypes.c_int
 c_f32 = ctypes.c_float
+c_f64 = ctypes.c_double
 
 # name -> (restype, argtypes); mirrors include/pero_b200.h one to one.
 SIGNATURES = {
@@ -32,11 +33,11 @@ SIGNATURES = {
     "pero_vq_gather_st": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_vp]),
     "pero_vq_ema_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pero_vq_ema_accumulate": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
-    "pero_vq_ema_apply": (c_int, [c_vp, c_i64, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_sz,
+    "pero_vq_ema_apply": (c_int, [c_vp, c_i64, c_i64, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_sz,
                                   c_vp]),
     "pero_vq_counts": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "pero_mse_workspace_bytes": (c_sz, [c_i64]),
-    "pero_mse_fwd": (c_int, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_sz, c_vp]),
+    "pero_mse_fwd": (c_int, [c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_sz, c_vp]),
     "pero_mse_bwd": (c_int, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "pero_head_bytes": (c_sz, [c_i64, c_i64]),
     "pero_head_prepare": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
@@ -45,6 +46,8 @@ SIGNATURES = {
                                    c_sz, c_vp]),
     "pero_masked_ce_bwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32,
                                    c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pero_ce_logits_fwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pero_ce_logits_bwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_int, c_vp, c_vp]),
     "pero_mask_compact_workspace_bytes": (c_sz, [c_i64]),
     "pero_mask_compact": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pero_debug_gemm_tn": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),

@@ -1,0 +1,187 @@
+"""Drop-in quantizer modules: same names, constructor arguments, attributes, state_dict keys and return
+values as the reference's ``pero_pretraining/models/autoencoders.py`` (VectorQuantizer :170-241,
+VQVAE :108-167), with the quantize path running in libpero_b200.so.
+
+Differences that are observable only through object identity (documented in DESIGN.md):
+  * the EMA step updates ``embedding.weight`` / ``ema_w`` / ``ema_cluster_size`` IN PLACE; the reference
+    re-wraps fresh ``torch.nn.Parameter`` objects every step (autoencoders.py:235-237), which silently
+    detaches them from any optimizer.  Values and state_dict contents are the same.
+  * distances use bf16 operands with fp32 accumulation, so an index may differ from the fp32 reference
+    where the two nearest codewords are closer than the epsilon stated in tests/ (near-tie rule).
+"""
+import torch
+
+from . import ops
+
+
+class _QuantizeST(torch.autograd.Function):
+    """assign -> gather -> straight-through (+ EMA side effect).  Backward is the identity on the inputs
+    (autoencoders.py:239: inputs + (quantized - inputs).detach()); nothing flows to the codebook."""
+
+    @staticmethod
+    def forward(ctx, inputs, vq):
+        n_lines, D = inputs.shape[0], inputs.shape[1]
+        frames = 1
+        for s in inputs.shape[2:]:
+            frames *= s
+        x = inputs.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        cb = vq._prepared_codebook()
+        update = vq.decay > 0.0 and vq.training
+        idx, _, x_rows = ops.vq_assign(x, cb, n_lines, frames, channels_first=True, want_rows=True)
+        weight = vq.embedding.weight.data
+        out = ops.vq_gather_st(x_rows, idx, weight, n_lines, frames, channels_first=True)
+        if update and idx.numel() > 0:
+            sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings)
+            if vq._dp_group is not None:
+                torch.distributed.all_reduce(sums_counts, group=vq._dp_group)   # [K, D+1] SUM over ranks
+            ops.vq_ema_apply(sums_counts, vq.ema_w.data, vq.ema_cluster_size, weight, vq.decay, vq.epsilon, cb)
+            vq._codebook_tag = vq._weight_tag()
+        ctx.mark_non_differentiable(idx)
+        return out.view(inputs.shape), idx
+
+    @staticmethod
+    def backward(ctx, g_out, _g_idx):
+        return g_out, None
+
+
+class _WeightedMse(torch.autograd.Function):
+    """w * mse(tokens, features) with gradient to `features` only (w_features) and/or `tokens` (w_tokens)."""
+
+    @staticmethod
+    def forward(ctx, tokens, features, w_tokens, w_features):
+        t = tokens.detach().float().contiguous()
+        f = features.detach().float().contiguous()
+        ctx.save_for_backward(t, f)
+        ctx.w = (float(w_tokens), float(w_features))
+        ctx.dtypes = (tokens.dtype, features.dtype)
+        # q_latent_loss + commitment_cost * e_latent_loss, each term rounded as the reference does (:200)
+        return ops.mse_fwd(t, f, float(w_tokens), float(w_features))
+
+    @staticmethod
+    def backward(ctx, g):
+        t, f = ctx.saved_tensors
+        w_t, w_f = ctx.w
+        g = g.detach().float().contiguous()
+        numel = t.numel()
+        g_t = g_f = None
+        if ctx.needs_input_grad[0] and w_t != 0.0:
+            g_t, _ = ops.mse_bwd(t, f, -2.0 * w_t / numel, g, want_a=False, want_b=True)   # w_t*2/n*(t - f)
+            g_t = g_t.to(ctx.dtypes[0])
+        if ctx.needs_input_grad[1] and w_f != 0.0:
+            _, g_f = ops.mse_bwd(t, f, 2.0 * w_f / numel, g, want_a=False, want_b=True)    # w_f*2/n*(f - t)
+            g_f = g_f.to(ctx.dtypes[1])
+        return g_t, g_f, None, None
+
+
+class VectorQuantizer(torch.nn.Module):
+    """models/autoencoders.py:170-241."""
+
+    def __init__(self, num_embeddings, embeddings_dim, commitment_cost, decay, epsilon=1e-5):
+        super().__init__()
+        self.embeddings_dim = embeddings_dim
+        self.num_embeddings = num_embeddings
+        self.embedding = torch.nn.Embedding(self.num_embeddings, self.embeddings_dim)
+        if decay > 0.0:
+            self.embedding.weight.data.normal_()
+            self.register_buffer('ema_cluster_size', torch.zeros(num_embeddings))
+            self.ema_w = torch.nn.Parameter(torch.Tensor(num_embeddings, self.embeddings_dim))
+            self.ema_w.data.normal_()
+        else:
+            self.embedding.weight.data.uniform_(-1 / self.num_embeddings, 1 / self.num_embeddings)
+        self.commitment_cost = commitment_cost
+        self.decay = decay
+        self.epsilon = epsilon
+        self._codebook = None         # derived cache (bf16 operand, |c|^2): non-persistent, rebuilt on demand
+        self._codebook_tag = None
+        self._dp_group = None
+
+    # -- data parallel: batch-sharded frames, replicated codebook, EMA sums/counts all-reduced
+    def enable_data_parallel(self, group=None):
+        if not torch.distributed.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dp_group = group if group is not None else torch.distributed.group.WORLD
+        return self
+
+    def _weight_tag(self):
+        w = self.embedding.weight
+        return (w.data_ptr(), w._version, w.device)
+
+    def _prepared_codebook(self):
+        w = self.embedding.weight
+        if not w.is_cuda:
+            raise ops._lib.PeroError("VectorQuantizer runs on a CUDA (B200) device only; there is no CPU path")
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            raise TypeError("embedding.weight must be contiguous float32")
+        tag = self._weight_tag()
+        if self._codebook is None or self._codebook.blob.device != w.device:
+            self._codebook = ops.PreparedCodebook(self.num_embeddings, self.embeddings_dim, w.device)
+            self._codebook_tag = None
+        if self._codebook_tag != tag:
+            self._codebook.prepare(w.data)
+            self._codebook_tag = tag
+        return self._codebook
+
+    def calculate_loss(self, tokens, features):
+        """autoencoders.py:193-202.  Accepts any two same-shape tensors (VQVAE passes tensors from either
+        side of its 1x1 projections, :155-159)."""
+        w_tokens = 0.0 if self.decay > 0.0 else 1.0
+        return _WeightedMse.apply(tokens, features, w_tokens, self.commitment_cost)
+
+    def forward(self, inputs):
+        """inputs [Nl, D, H, W] -> (quantized [Nl, D, H, W] with straight-through grad, indices [Nl*H*W] int64)."""
+        if inputs.dim() != 4 or inputs.shape[1] != self.embeddings_dim:
+            raise ValueError(f"expected [N, {self.embeddings_dim}, H, W], got {tuple(inputs.shape)}")
+        return _QuantizeST.apply(inputs, self)
+
+
+class VQVAE(torch.nn.Module):
+    """models/autoencoders.py:108-167; encoder/decoder are the caller's modules (conv stacks are out of scope)."""
+
+    def __init__(self, encoder, decoder, num_embeddings, embeddings_dim, commitment_cost=0.25, decay=0.99,
+                 reconstruction_loss='mse'):
+        super().__init__()
+        self.encoder = encoder
+        self.decoder = decoder
+        self.encoder_projection_layer = torch.nn.Conv2d(encoder.out_channels, embeddings_dim, 1)
+        self.decoder_projection_layer = torch.nn.Conv2d(embeddings_dim, decoder.base_channels, 1)
+        self.num_embeddings = num_embeddings
+        self.embeddings_dim = embeddings_dim
+        self.reconstruction_loss = reconstruction_loss
+        self.vq = VectorQuantizer(self.num_embeddings, self.embeddings_dim, commitment_cost, decay)
+
+    def calculate_loss(self, images, reconstructions, features, tokens):
+        kind = self.reconstruction_loss.lower()
+        if kind in ('l2', 'mse'):
+            recon_loss = torch.nn.functional.mse_loss(images, reconstructions)
+        elif kind in ('l1', 'mae'):
+            recon_loss = torch.nn.functional.l1_loss(images, reconstructions)
+        else:
+            raise ValueError(f'Unknown reconstruction loss: {self.reconstruction_loss}')
+        return self.vq.calculate_loss(tokens, features) + recon_loss
+
+    def encode(self, x):
+        return self.encoder(x)
+
+    def decode(self, x):
+        return self.decoder(x)
+
+    def quantize(self, x):
+        x = self.encoder_projection_layer(x)
+        tokens, labels = self.vq(x)
+        return self.decoder_projection_layer(tokens), labels
+
+    def forward(self, images):
+        features = self.encode(images)
+        tokens, labels = self.quantize(features)
+        reconstructions = self.decode(tokens)
+        loss = self.calculate_loss(images, reconstructions, features, tokens)
+        return {
+            'tokens': tokens,
+            'labels': labels,
+            'loss': loss,
+            'reconstructions': reconstructions,
+            'counts': ops.vq_counts(labels, self.num_embeddings),     # torch.bincount(labels, minlength=K), :165
+        }

@@ -11,11 +11,11 @@ namespace pero {
 // row and cannot change the arg-min; reference: models/autoencoders.py:212-217).  The running
 // (min, argmin) stays in registers across the column sweep; strict '<' in ascending column order keeps
 // torch.argmin's first-index-on-ties rule.  Results of different workers on the same row are merged
-// with one 64-bit atomicMin on (order_key(d) << 32 | index): min distance first, then lowest index.
+// with one signed 64-bit atomicMin on (order_key(d) << 32 | index): min distance first, then lowest index.
 struct ArgminEpi {
     struct Params {
         const float* cnorm;            // [num_ct * 256] |c|^2 in fp32, +inf beyond the last codeword
-        unsigned long long* packed;    // [rows] pre-set to ~0
+        long long* packed;             // [rows] pre-set to kPackedEmpty
         int rows;
         int index_offset;              // global index of this shard's codeword 0
     };
@@ -49,9 +49,7 @@ struct ArgminEpi {
     }
     static __device__ __forceinline__ void end_rb(State& st, const Params& ep, const TileCtx& cx) {
         if (cx.row < ep.rows) {
-            const unsigned long long key =
-                ((unsigned long long)float_order_key(st.best) << 32) | (unsigned)(st.besti + ep.index_offset);
-            atomicMin(ep.packed + cx.row, key);
+            atomicMin(ep.packed + cx.row, pack_dist_index(st.best, st.besti + ep.index_offset));
         }
     }
 };

@@ -1,0 +1,622 @@
+// Masked-label cross-entropy over codebook logits:
+//   LinearHead                masked_pretraining/model.py:104-105
+//   MaskedCrossEntropyLoss    masked_pretraining/model.py:78-82 (+ :84-93 by a second call)
+// Only the M masked frames go through the head: gather -> logits GEMM (tcgen05) -> online log-sum-exp in
+// the GEMM epilogue.  The backward recomputes the logits tile by tile, turns them into
+// dlogits = (softmax - onehot) * scale in the epilogue (bf16, both orientations) and runs two more
+// tcgen05 GEMMs for d_W = dlogits^T @ h and d_h = dlogits @ W (split over the label axis, fixed-order
+// reduction), then scatters d_h back to the frame positions.  No atomics anywhere: deterministic.
+#include <cub/device/device_select.cuh>
+#include <cuda_bf16.h>
+#include <thrust/iterator/counting_iterator.h>
+#include "../../include/pero_b200.h"
+#include "epilogues.cuh"
+#include "gemm_host.cuh"
+#include "layout.h"
+
+namespace pero {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// Prepared head: bf16 W [V, Dhp] | bf16 W^T [Dh, Vp] | bias fp32 [Vt] (-inf beyond V so padded label
+// columns vanish from the log-sum-exp).  Dhp, Vp: rounded up to 64; Vt: rounded up to 256.
+struct HeadLayout { int64_t Dhp, Vp, Vt; size_t w_off, wt_off, bias_off, total; };
+inline HeadLayout head_layout(int64_t V, int64_t Dh) {
+    HeadLayout l;
+    l.Dhp = round_up(Dh, 64); l.Vp = round_up(V, 64); l.Vt = round_up(V, 256);
+    l.w_off = 0;
+    l.wt_off = align256((size_t)V * l.Dhp * 2);
+    l.bias_off = l.wt_off + align256((size_t)Dh * l.Vp * 2);
+    l.total = l.bias_off + align256((size_t)l.Vt * 4);
+    return l;
+}
+
+constexpr int kMaxLseSplits = 64;
+
+struct CeWsLayout {
+    int64_t Dhp, Vp, Mp64, Mpad, S, KS;
+    size_t a_off, at_off, lab_off, inv_off, p_off, pt_off, pm_off, ps_off, zlab_off, planes_off, total;
+};
+inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
+    CeWsLayout l;
+    l.Dhp = round_up(Dh, 64); l.Vp = round_up(V, 64); l.Mp64 = round_up(M, 64); l.Mpad = round_up(M, 128);
+    const int64_t num_rb = l.Mpad / 128, num_ct = (V + 255) / 256, num_ct_dh = (Dh + 255) / 256;
+    int64_t S = 148 / num_rb;
+    if (S < 1) S = 1;
+    if (S > num_ct) S = num_ct;
+    if (S > kMaxLseSplits) S = kMaxLseSplits;
+    l.S = S;
+    int64_t KS = 148 / (num_rb * num_ct_dh);
+    if (KS < 1) KS = 1;
+    if (KS > l.Vp / 64) KS = l.Vp / 64;
+    if (KS > 16) KS = 16;
+    l.KS = KS;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    l.a_off = take((size_t)M * l.Dhp * 2);
+    l.at_off = take((size_t)Dh * l.Mp64 * 2);
+    l.lab_off = take((size_t)l.Mpad * 4);
+    l.inv_off = take((size_t)N * 4);
+    l.p_off = take((size_t)M * l.Vp * 2);
+    l.pt_off = take((size_t)V * l.Mp64 * 2);
+    l.pm_off = take((size_t)S * l.Mpad * 4);
+    l.ps_off = take((size_t)S * l.Mpad * 4);
+    l.zlab_off = take((size_t)l.Mpad * 4);
+    l.planes_off = take((size_t)KS * M * Dh * 4);
+    l.total = off;
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------ prep
+__global__ void __launch_bounds__(256)
+head_prepare_kernel(const float* __restrict__ W, const float* __restrict__ bias, int V, int Dh, int Dhp, int Vp, int Vt,
+                    __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wbt, float* __restrict__ bias_out) {
+    // 32 x 32 tiles of W: coalesced read along Dh, bf16 copy, transposed bf16 copy through shared memory.
+    __shared__ float tile[32][33];
+    const int v0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int v = v0 + ty + i * 8, d = d0 + tx;
+        const float x = (v < V && d < Dh) ? __ldg(W + (size_t)v * Dh + d) : 0.f;
+        tile[ty + i * 8][tx] = x;
+        if (v < V && d < Dhp) wb[(size_t)v * Dhp + d] = __float2bfloat16_rn(x);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int d = d0 + ty + i * 8, v = v0 + tx;
+        if (d < Dh && v < Vp) wbt[(size_t)d * Vp + v] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+    }
+    if (blockIdx.y == 0) {
+        const int v = v0 + (int)threadIdx.x;
+        if (threadIdx.x < 32 && v < Vt) bias_out[v] = v < V ? (bias ? __ldg(bias + v) : 0.f) : -CUDART_INF_F;
+    }
+}
+
+__global__ void ce_inv_init_kernel(int* __restrict__ inv, long long N) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) inv[i] = -1;
+}
+
+// Gather the masked frames into the GEMM operand A [M, Dhp] bf16 (+ A^T [Dh, Mp64] for d_W), their labels,
+// and the inverse frame -> masked-row map.  Tiles of 32 masked rows x 32 channels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const long long* __restrict__ labels, int M, int Dh,
+                 int Dhp, int Mp64, int Mpad, __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ at,
+                 int* __restrict__ lab, int* __restrict__ inv) {
+    __shared__ float tile[32][33];
+    const int m0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty + i * 8, d = d0 + tx;
+        float x = 0.f;
+        if (m < M && d < Dh) x = (float)h[(size_t)__ldg(rows + m) * Dh + d];
+        tile[ty + i * 8][tx] = x;
+        if (m < M && d < Dhp) a[(size_t)m * Dhp + d] = __float2bfloat16_rn(x);
+    }
+    if (at) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int d = d0 + ty + i * 8, m = m0 + tx;
+            if (d < Dh && m < Mp64) at[(size_t)d * Mp64 + m] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+        }
+    }
+    if (blockIdx.y == 0 && threadIdx.x < 32) {
+        const int m = m0 + (int)threadIdx.x;
+        if (m < Mpad) {
+            int l = -1;
+            if (m < M) {
+                const int r = __ldg(rows + m);
+                l = (int)__ldg(labels + r);
+                if (inv) inv[r] = m;
+            }
+            lab[m] = l;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ epilogues
+// Online log-sum-exp over the label axis; one partial (max, sum) per row and column split.
+struct LseEpi {
+    struct Params {
+        const float* bias;    // [Vt], -inf beyond V
+        const int* lab;       // [Mpad]
+        float* pm; float* ps; // [S, Mpad] partial max / sum(exp(z - max))
+        float* zlab;          // [Mpad] logit at the label
+        int M, Mpad, S;
+    };
+    struct State { float m, s, zl; int label; bool has; };
+    static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
+        st.m = -CUDART_INF_F; st.s = 0.f; st.zl = 0.f; st.has = false;
+        st.label = cx.row < ep.M ? __ldg(ep.lab + cx.row) : -1;
+    }
+    static __device__ __forceinline__ void tile(State& st, const Params& ep, const TileCtx& cx, uint32_t taddr) {
+#pragma unroll 1
+        for (int c = 0; c < kBlockN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            const int col = cx.col0 + c * 32;
+            const float4* bp = reinterpret_cast<const float4*>(ep.bias + col);
+            float4 b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b[i] = __ldg(bp + i);
+            tmem_ld_wait();
+            float z[32];
+            float cmax = -CUDART_INF_F;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                z[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b[i].x;
+                z[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b[i].y;
+                z[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b[i].z;
+                z[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b[i].w;
+                cmax = fmaxf(cmax, fmaxf(fmaxf(z[4 * i], z[4 * i + 1]), fmaxf(z[4 * i + 2], z[4 * i + 3])));
+            }
+            const unsigned rel = (unsigned)(st.label - col);
+            if (rel < 32u) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (rel == (unsigned)j) st.zl = z[j];
+                st.has = true;
+            }
+            if (cmax > -CUDART_INF_F) {
+                const float mn = fmaxf(st.m, cmax);
+                const float mn2 = mn * kLog2e;
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(z[j], kLog2e, -mn2));
+                st.s = st.s * exp2f((st.m - mn) * kLog2e) + acc;
+                st.m = mn;
+            }
+        }
+    }
+    static __device__ __forceinline__ void end_rb(State& st, const Params& ep, const TileCtx& cx) {
+        const int slot = cx.worker % ep.S;
+        ep.pm[(size_t)slot * ep.Mpad + cx.row] = st.m;
+        ep.ps[(size_t)slot * ep.Mpad + cx.row] = st.s;
+        if (st.has) ep.zlab[cx.row] = st.zl;
+    }
+};
+
+// dlogits tile = (exp(z - lse) - [col == label]) * scale, written bf16 as P [M, Vp] and P^T [V, Mp64].
+struct DlogitsEpi {
+    struct Params {
+        const float* bias; const int* lab; const float* lse; const float* grad_scale;
+        float inv_count;
+        __nv_bfloat16* p; __nv_bfloat16* pt;
+        int M, V, Vp, Mp64;
+    };
+    struct State { float lse2, scale; int label; bool ok; };
+    static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
+        const bool ok = cx.row < ep.M;
+        st.ok = ok;
+        st.label = ok ? __ldg(ep.lab + cx.row) : -1;
+        st.lse2 = ok ? __ldg(ep.lse + cx.row) * kLog2e : 0.f;
+        st.scale = ok ? ep.inv_count * (ep.grad_scale ? __ldg(ep.grad_scale) : 1.0f) : 0.f;
+    }
+    static __device__ __forceinline__ void tile(State& st, const Params& ep, const TileCtx& cx, uint32_t taddr) {
+#pragma unroll 1
+        for (int c = 0; c < kBlockN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            const int col = cx.col0 + c * 32;
+            const float4* bp = reinterpret_cast<const float4*>(ep.bias + col);
+            float4 b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b[i] = __ldg(bp + i);
+            tmem_ld_wait();
+            if (col >= ep.Vp) continue;
+            const unsigned rel = (unsigned)(st.label - col);
+            __nv_bfloat162 o[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float bb[4] = {b[i].x, b[i].y, b[i].z, b[i].w};
+                float g[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * i + e;
+                    const float z = __uint_as_float(r[j]) + bb[e];
+                    float pz = exp2f(fmaf(z, kLog2e, -st.lse2));      // exp(-inf) = 0 on padded label columns
+                    if (rel == (unsigned)j) pz -= 1.0f;
+                    g[e] = st.ok ? pz * st.scale : 0.f;      // rows in [M, Mp64) are zero padding of P^T
+                }
+                o[2 * i] = __floats2bfloat162_rn(g[0], g[1]);
+                o[2 * i + 1] = __floats2bfloat162_rn(g[2], g[3]);
+            }
+            if (cx.row < ep.M) {
+                // Vp is a multiple of 64, so a 32-column chunk is either fully inside the pitch or skipped above
+                uint4* dst = reinterpret_cast<uint4*>(ep.p + (size_t)cx.row * ep.Vp + col);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = *reinterpret_cast<uint4*>(&o[4 * i]);
+            }
+            if (cx.row < ep.Mp64) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (col + j < ep.V) {
+                        const __nv_bfloat162 v2 = o[j >> 1];
+                        ep.pt[(size_t)(col + j) * ep.Mp64 + cx.row] = (j & 1) ? v2.y : v2.x;
+                    }
+                }
+            }
+        }
+    }
+    static __device__ __forceinline__ void end_rb(State&, const Params&, const TileCtx&) {}
+};
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// lse[m] = log-sum-exp combined over the S column splits; loss_sum = sum_m (lse[m] - z[label]) in a
+// fixed order (single CTA).
+__global__ void __launch_bounds__(1024)
+ce_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ zlab, int M, int Mpad,
+                   int S, float* __restrict__ lse, float* __restrict__ loss_sum) {
+    __shared__ float sh[32];
+    float part = 0.f;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        float mx = -CUDART_INF_F;
+        for (int s = 0; s < S; ++s) mx = fmaxf(mx, pm[(size_t)s * Mpad + m]);
+        float sum = 0.f;
+        for (int s = 0; s < S; ++s) sum += ps[(size_t)s * Mpad + m] * exp2f((pm[(size_t)s * Mpad + m] - mx) * kLog2e);
+        const float l = mx + log2f(sum) * kLn2;
+        lse[m] = l;
+        part += l - zlab[m];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = sh[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) loss_sum[0] = t;
+    }
+}
+
+// d_b[v] = sum_m P^T[v, m]: one warp per label, fixed lane-strided order.
+__global__ void __launch_bounds__(256)
+ce_db_kernel(const __nv_bfloat16* __restrict__ pt, int V, int M, int Mp64, float* __restrict__ db) {
+    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (v >= V) return;
+    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(pt + (size_t)v * Mp64);
+    float s = 0.f;
+    for (int i = lane; i < Mp64 / 2; i += 32) {      // columns >= M are zero by construction
+        const float2 f = __bfloat1622float2(row[i]);
+        s += f.x + f.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) db[v] = s;
+    (void)M;
+}
+
+// d_h[n, :] = sum over split planes of row inv[n] (zero when the frame is not masked).
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ inv, long long N, int M, int Dh, int KS,
+                     T* __restrict__ dh) {
+    const long long total = N * Dh;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long n = i / Dh;
+        const int d = (int)(i - n * Dh);
+        const int m = __ldg(inv + n);
+        float s = 0.f;
+        if (m >= 0)
+            for (int k = 0; k < KS; ++k) s += __ldg(planes + ((size_t)k * M + m) * Dh + d);
+        dh[i] = (T)s;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ logits-in CE
+// MaskedCrossEntropyLoss.forward(output, labels, mask) for callers that already hold the logits
+// (masked_pretraining/model.py:78-82): one warp per selected row, online log-sum-exp, 16-byte loads.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_logits_fwd_kernel(const T* __restrict__ logits, const int* __restrict__ rows, const long long* __restrict__ labels, int M, int V,
+                     float* __restrict__ lse, float* __restrict__ rowloss) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const int r = __ldg(rows + m);
+    const T* z = logits + (size_t)r * V;
+    float mx = -CUDART_INF_F, s = 0.f;
+    for (int v = lane; v < V; v += 32) {
+        const float x = (float)z[v];
+        if (x > mx) { s = s * exp2f((mx - x) * kLog2e); mx = x; }
+        s += exp2f((x - mx) * kLog2e);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+        const float nm = fmaxf(mx, om);
+        s = (nm == -CUDART_INF_F) ? 0.f : s * exp2f((mx - nm) * kLog2e) + os * exp2f((om - nm) * kLog2e);
+        mx = nm;
+    }
+    if (lane == 0) {
+        const float l = mx + log2f(s) * kLn2;
+        lse[m] = l;
+        rowloss[m] = l - (float)z[__ldg(labels + r)];
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+ce_sum_kernel(const float* __restrict__ v, int M, float* __restrict__ out) {
+    __shared__ float sh[32];
+    float part = 0.f;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) part += v[m];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = sh[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) out[0] = t;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_logits_bwd_kernel(const T* __restrict__ logits, const int* __restrict__ rows, const long long* __restrict__ labels,
+                     const float* __restrict__ lse, const float* __restrict__ grad_scale, float inv_count, int M, int V,
+                     T* __restrict__ d_logits) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const int r = __ldg(rows + m);
+    const int label = (int)__ldg(labels + r);
+    const float l2 = __ldg(lse + m) * kLog2e;
+    const float scale = inv_count * (grad_scale ? __ldg(grad_scale) : 1.0f);
+    const T* z = logits + (size_t)r * V;
+    T* d = d_logits + (size_t)r * V;
+    for (int v = lane; v < V; v += 32) {
+        float p = exp2f(fmaf((float)z[v], kLog2e, -l2));
+        if (v == label) p -= 1.0f;
+        d[v] = (T)(p * scale);
+    }
+}
+
+struct MaskPred {
+    const void* mask; int dtype; int want; const long long* labels;
+    __device__ __forceinline__ bool operator()(int i) const {
+        long long v;
+        if (dtype == 0) v = static_cast<const long long*>(mask)[i];
+        else if (dtype == 1) v = static_cast<const int*>(mask)[i];
+        else v = static_cast<const unsigned char*>(mask)[i];
+        return v == want && (labels == nullptr || labels[i] >= 0);
+    }
+};
+
+template <typename T>
+int launch_ce_gather(const void* h, const int32_t* rows, const int64_t* labels, int M, int Dh, const CeWsLayout& l, char* ws,
+                     bool with_t, bool with_inv, cudaStream_t stream) {
+    dim3 grid((unsigned)((l.Mpad + 31) / 32), (unsigned)(l.Dhp / 32));
+    ce_gather_kernel<T><<<grid, 256, 0, stream>>>(
+        static_cast<const T*>(h), rows, reinterpret_cast<const long long*>(labels), M, Dh, (int)l.Dhp, (int)l.Mp64, (int)l.Mpad,
+        reinterpret_cast<__nv_bfloat16*>(ws + l.a_off), with_t ? reinterpret_cast<__nv_bfloat16*>(ws + l.at_off) : nullptr,
+        reinterpret_cast<int*>(ws + l.lab_off), with_inv ? reinterpret_cast<int*>(ws + l.inv_off) : nullptr);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pero
+
+using namespace pero;
+
+extern "C" {
+
+size_t pero_head_bytes(int64_t V, int64_t Dh) {
+    if (V <= 0 || Dh <= 0) return 0;
+    return head_layout(V, Dh).total;
+}
+
+int pero_head_prepare(const float* W, const float* bias, int64_t V, int64_t Dh, void* head, size_t head_bytes,
+                      pero_stream_t stream) {
+    if (!W || !head) return PERO_ERR_NULL;
+    if (V <= 0 || Dh <= 0 || V > (1ll << 24) || Dh > 65536) return PERO_ERR_BAD_SHAPE;
+    const HeadLayout l = head_layout(V, Dh);
+    if (head_bytes < l.total) return PERO_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(head) & 255) return PERO_ERR_BAD_ALIGN;
+    char* base = static_cast<char*>(head);
+    dim3 grid((unsigned)(l.Vt / 32), (unsigned)(l.Dhp / 32));
+    head_prepare_kernel<<<grid, 256, 0, stream>>>(W, bias, (int)V, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.Vt,
+                                                  reinterpret_cast<__nv_bfloat16*>(base + l.w_off),
+                                                  reinterpret_cast<__nv_bfloat16*>(base + l.wt_off),
+                                                  reinterpret_cast<float*>(base + l.bias_off));
+    return (int)cudaGetLastError();
+}
+
+size_t pero_masked_ce_workspace_bytes(int64_t N, int64_t M, int64_t V, int64_t Dh) {
+    if (N <= 0 || M <= 0 || V <= 0 || Dh <= 0) return 0;
+    return ce_ws_layout(N, M, V, Dh).total;
+}
+
+static int ce_check(const void* h, int64_t N, int64_t Dh, const int32_t* rows, int64_t M, const int64_t* labels,
+                    const void* head, int64_t V, void* workspace, size_t workspace_bytes) {
+    if (!h || !rows || !labels || !head || !workspace) return PERO_ERR_NULL;
+    if (N <= 0 || M <= 0 || M > N || V <= 0 || Dh <= 0 || N > (1ll << 31) - 256 || V > (1ll << 24) || Dh > 512)
+        return PERO_ERR_BAD_SHAPE;   // Dh <= 512: the masked rows stay resident in shared memory for the sweep
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(head) & 255)) return PERO_ERR_BAD_ALIGN;
+    if (workspace_bytes < ce_ws_layout(N, M, V, Dh).total) return PERO_ERR_WORKSPACE;
+    return PERO_OK;
+}
+
+int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+                       const int64_t* labels, const void* head, int64_t V, float* loss_sum, float* lse,
+                       void* workspace, size_t workspace_bytes, pero_stream_t stream) {
+    if (M == 0) return PERO_ERR_BAD_SHAPE;   // the reference returns NaN on an empty mask; the host wrapper handles it
+    int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (!loss_sum || !lse) return PERO_ERR_NULL;
+    const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
+    const HeadLayout hl = head_layout(V, Dh);
+    char* ws = static_cast<char*>(workspace);
+    const char* hb = static_cast<const char*>(head);
+    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, (int)M, (int)Dh, l, ws, false, false, stream)
+                   : launch_ce_gather<float>(h, rows, labels, (int)M, (int)Dh, l, ws, false, false, stream);
+    if (rc) return rc;
+    LseEpi::Params ep;
+    ep.bias = reinterpret_cast<const float*>(hb + hl.bias_off);
+    ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
+    ep.pm = reinterpret_cast<float*>(ws + l.pm_off);
+    ep.ps = reinterpret_cast<float*>(ws + l.ps_off);
+    ep.zlab = reinterpret_cast<float*>(ws + l.zlab_off);
+    ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S;
+    rc = launch_gemm_tn<1, true, LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
+                                         /*split_mode=*/1, (int)l.S, 0, ep, stream);
+    if (rc) return rc;
+    ce_finalize_kernel<<<1, 1024, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, (int)l.S, lse, loss_sum);
+    return (int)cudaGetLastError();
+}
+
+int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+                       const int64_t* labels, const void* head, int64_t V, const float* lse,
+                       const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
+                       void* workspace, size_t workspace_bytes, pero_stream_t stream) {
+    if (M == 0) return PERO_ERR_BAD_SHAPE;
+    int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (!lse || !d_W || !d_b) return PERO_ERR_NULL;
+    if (Dh % 4 != 0) return PERO_ERR_BAD_SHAPE;
+    const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
+    const HeadLayout hl = head_layout(V, Dh);
+    char* ws = static_cast<char*>(workspace);
+    const char* hb = static_cast<const char*>(head);
+    int* inv = reinterpret_cast<int*>(ws + l.inv_off);
+    if (d_h) ce_inv_init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(inv, N);
+    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, (int)M, (int)Dh, l, ws, true, d_h != nullptr, stream)
+                   : launch_ce_gather<float>(h, rows, labels, (int)M, (int)Dh, l, ws, true, d_h != nullptr, stream);
+    if (rc) return rc;
+
+    __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + l.p_off);
+    __nv_bfloat16* PT = reinterpret_cast<__nv_bfloat16*>(ws + l.pt_off);
+    DlogitsEpi::Params ep;
+    ep.bias = reinterpret_cast<const float*>(hb + hl.bias_off);
+    ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
+    ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
+    ep.p = P; ep.pt = PT; ep.M = (int)M; ep.V = (int)V; ep.Vp = (int)l.Vp; ep.Mp64 = (int)l.Mp64;
+    rc = launch_gemm_tn<1, true, DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
+                                             0, 1, 0, ep, stream);
+    if (rc) return rc;
+
+    // d_W [V, Dh] = P^T [V, Mp64] @ A^T [Dh, Mp64]^T
+    StoreEpi::Params sw;
+    sw.out = d_W; sw.ld = Dh; sw.split_stride = 0; sw.rows = (int)V; sw.cols = (int)Dh;
+    rc = launch_gemm_tn<1, false, StoreEpi>(PT, (int)V, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1, 0, 1, 0,
+                                            sw, stream);
+    if (rc) return rc;
+    ce_db_kernel<<<(unsigned)((V + 7) / 8), 256, 0, stream>>>(PT, (int)V, (int)M, (int)l.Mp64, d_b);
+
+    if (d_h) {
+        // planes[ks] [M, Dh] = P [M, Vp] @ W^T [Dh, Vp]^T over the ks-th slice of the label axis
+        float* planes = reinterpret_cast<float*>(ws + l.planes_off);
+        StoreEpi::Params sh;
+        sh.out = planes; sh.ld = Dh; sh.split_stride = (long long)M * Dh; sh.rows = (int)M; sh.cols = (int)Dh;
+        rc = launch_gemm_tn<1, false, StoreEpi>(P, (int)M, (int)l.Vp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0, 1,
+                                                0, sh, stream);
+        if (rc) return rc;
+        const long long total = N * Dh;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        // the number of planes actually produced is recomputed exactly as launch_gemm_tn does
+        const int num_kb = (int)(l.Vp / 64);
+        const int kb_per = (num_kb + (int)l.KS - 1) / (int)l.KS;
+        const int ks_eff = (num_kb + kb_per - 1) / kb_per;
+        if (h_is_bf16)
+            ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
+                                                                                     static_cast<__nv_bfloat16*>(d_h));
+        else
+            ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
+                                                                             static_cast<float*>(d_h));
+    }
+    return (int)cudaGetLastError();
+}
+
+int pero_ce_logits_fwd(const void* logits, int is_bf16, int64_t N, int64_t V, const int32_t* rows, int64_t M,
+                       const int64_t* labels, float* loss_sum, float* lse, void* workspace, size_t workspace_bytes,
+                       pero_stream_t stream) {
+    if (!logits || !rows || !labels || !loss_sum || !lse || !workspace) return PERO_ERR_NULL;
+    if (N <= 0 || M <= 0 || M > N || V <= 0 || V > (1ll << 30)) return PERO_ERR_BAD_SHAPE;
+    if (workspace_bytes < align256((size_t)M * 4)) return PERO_ERR_WORKSPACE;
+    float* rowloss = static_cast<float*>(workspace);
+    const unsigned grid = (unsigned)((M + 7) / 8);
+    if (is_bf16)
+        ce_logits_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), rows,
+                                                                      reinterpret_cast<const long long*>(labels), (int)M, (int)V, lse, rowloss);
+    else
+        ce_logits_fwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(logits), rows,
+                                                              reinterpret_cast<const long long*>(labels), (int)M, (int)V, lse, rowloss);
+    ce_sum_kernel<<<1, 1024, 0, stream>>>(rowloss, (int)M, loss_sum);
+    return (int)cudaGetLastError();
+}
+
+int pero_ce_logits_bwd(const void* logits, int is_bf16, int64_t N, int64_t V, const int32_t* rows, int64_t M,
+                       const int64_t* labels, const float* lse, const float* grad_scale, float inv_count, int zero_init,
+                       void* d_logits, pero_stream_t stream) {
+    if (!logits || !rows || !labels || !lse || !d_logits) return PERO_ERR_NULL;
+    if (N <= 0 || M <= 0 || M > N || V <= 0 || V > (1ll << 30)) return PERO_ERR_BAD_SHAPE;
+    if (zero_init) {
+        cudaError_t e = cudaMemsetAsync(d_logits, 0, (size_t)N * V * (is_bf16 ? 2 : 4), stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const unsigned grid = (unsigned)((M + 7) / 8);
+    if (is_bf16)
+        ce_logits_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), rows,
+            reinterpret_cast<const long long*>(labels), lse, grad_scale, inv_count, (int)M, (int)V, static_cast<__nv_bfloat16*>(d_logits));
+    else
+        ce_logits_bwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(logits), rows,
+            reinterpret_cast<const long long*>(labels), lse, grad_scale, inv_count, (int)M, (int)V, static_cast<float*>(d_logits));
+    return (int)cudaGetLastError();
+}
+
+size_t pero_mask_compact_workspace_bytes(int64_t N) {
+    if (N <= 0) return 0;
+    size_t bytes = 0;
+    MaskPred pred{nullptr, 0, 1, nullptr};
+    cudaError_t e = cub::DeviceSelect::If(nullptr, bytes, thrust::counting_iterator<int>(0), (int32_t*)nullptr,
+                                          (int32_t*)nullptr, (int)N, pred);
+    if (e != cudaSuccess || bytes == 0) {      // no device to query (CPU-only host): conservative bound
+        (void)cudaGetLastError();
+        bytes = (size_t)N + (1u << 20);
+    }
+    return align256(bytes);
+}
+
+int pero_mask_compact(const void* mask, int mask_dtype, int want_value, const int64_t* labels_or_null, int64_t N,
+                      int32_t* rows, int32_t* count, void* workspace, size_t workspace_bytes,
+                      pero_stream_t stream) {
+    if (!mask || !rows || !count || !workspace) return PERO_ERR_NULL;
+    if (N <= 0 || N > (1ll << 31) - 256 || mask_dtype < 0 || mask_dtype > 2) return PERO_ERR_BAD_SHAPE;
+    size_t bytes = workspace_bytes;
+    MaskPred pred{mask, mask_dtype, want_value, reinterpret_cast<const long long*>(labels_or_null)};
+    if (workspace_bytes < pero_mask_compact_workspace_bytes(N)) return PERO_ERR_WORKSPACE;
+    cudaError_t e = cub::DeviceSelect::If(workspace, bytes, thrust::counting_iterator<int>(0), rows, count, (int)N, pred, stream);
+    return (int)e;
+}
+
+}  // extern "C"

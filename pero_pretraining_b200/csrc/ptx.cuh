@@ -163,23 +163,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
 }
 
 // ---------------------------------------------------------------- misc
-// Order-preserving map float -> uint32 (smaller float <=> smaller key); used to pack
-// (distance, index) into one u64 so that min() picks the nearest codeword, lowest index on ties.
-__host__ __device__ __forceinline__ uint32_t float_order_key(float f) {
+// Order-preserving map float -> int32 (smaller float <=> smaller SIGNED key).  (distance, index) pairs
+// are packed as (key << 32 | index) into one signed 64-bit word, so a plain MIN -- atomicMin on the
+// device, an int64 MIN all-reduce across codebook shards -- picks the nearest codeword and, on exactly
+// equal distances, the lowest index.  "Empty" is INT64_MAX.
+__host__ __device__ __forceinline__ int32_t float_order_key(float f) {
 #ifdef __CUDA_ARCH__
-    uint32_t b = __float_as_uint(f);
+    int32_t b = __float_as_int(f);
 #else
-    uint32_t b; memcpy(&b, &f, 4);
+    int32_t b; memcpy(&b, &f, 4);
 #endif
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return b ^ ((b >> 31) & 0x7FFFFFFF);
 }
-__host__ __device__ __forceinline__ float float_from_order_key(uint32_t k) {
-    uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+__host__ __device__ __forceinline__ float float_from_order_key(int32_t k) {
+    int32_t b = k ^ ((k >> 31) & 0x7FFFFFFF);
 #ifdef __CUDA_ARCH__
-    return __uint_as_float(b);
+    return __int_as_float(b);
 #else
     float f; memcpy(&f, &b, 4); return f;
 #endif
 }
+__host__ __device__ __forceinline__ long long pack_dist_index(float d, int index) {
+    return (long long)(((unsigned long long)(uint32_t)float_order_key(d) << 32) | (uint32_t)index);
+}
+constexpr long long kPackedEmpty = 0x7FFFFFFFFFFFFFFFll;
 
 }  // namespace pero

@@ -36,7 +36,7 @@ __global__ void codebook_prepare_kernel(const float* __restrict__ w, int K, int 
 // bf16 GEMM operand [N, Dp] and, optionally, the fp32 rows the gather/EMA stages read coalesced.
 __global__ void __launch_bounds__(256)
 frames_prepare_cf_kernel(const float* __restrict__ x, int D, int Dp, int HW, long long N,
-                         __nv_bfloat16* __restrict__ xb, float* __restrict__ xr, unsigned long long* __restrict__ packed) {
+                         __nv_bfloat16* __restrict__ xb, float* __restrict__ xr, long long* __restrict__ packed) {
     __shared__ float tile[64][33];
     const int nl = blockIdx.z, hw0 = blockIdx.x * 32, d0 = blockIdx.y * 64;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -62,14 +62,14 @@ frames_prepare_cf_kernel(const float* __restrict__ x, int D, int Dp, int HW, lon
     }
     if (packed) {
         const long long lin = ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
-        if (lin < N) packed[lin] = ~0ull;
+        if (lin < N) packed[lin] = kPackedEmpty;
     }
 }
 
 // Frames already stored as rows [N, D] (the kmeans labeller flattens before cdist).
 __global__ void __launch_bounds__(256)
 frames_prepare_rows_kernel(const float* __restrict__ x, int D, int Dp, long long N,
-                           __nv_bfloat16* __restrict__ xb, float* __restrict__ xr, unsigned long long* __restrict__ packed) {
+                           __nv_bfloat16* __restrict__ xb, float* __restrict__ xr, long long* __restrict__ packed) {
     const long long pairs = N * (Dp / 2);
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,21 +84,21 @@ frames_prepare_rows_kernel(const float* __restrict__ x, int D, int Dp, long long
             if (d + 1 < D) xr[n * D + d + 1] = b;
         }
     }
-    if (packed) for (long long n = t0; n < N; n += stride) packed[n] = ~0ull;
+    if (packed) for (long long n = t0; n < N; n += stride) packed[n] = kPackedEmpty;
 }
 
-__global__ void packed_init_kernel(unsigned long long* packed, long long N) {
+__global__ void packed_init_kernel(long long* packed, long long N) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) packed[i] = ~0ull;
+    if (i < N) packed[i] = kPackedEmpty;
 }
 
-__global__ void unpack_kernel(const unsigned long long* __restrict__ packed, long long N,
+__global__ void unpack_kernel(const long long* __restrict__ packed, long long N,
                               long long* __restrict__ idx, float* __restrict__ dmin) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const unsigned long long p = packed[i];
-    if (idx) idx[i] = (long long)(p & 0xffffffffull);
-    if (dmin) dmin[i] = float_from_order_key((uint32_t)(p >> 32));
+    const long long p = packed[i];
+    if (idx) idx[i] = (long long)((unsigned long long)p & 0xffffffffull);
+    if (dmin) dmin[i] = float_from_order_key((int32_t)(p >> 32));
 }
 
 // bit0: CTA pairs (cta_group::2); bit1: resident A row block.  PERO_ASSIGN_VARIANT overrides.
@@ -111,7 +111,7 @@ int assign_variant_default(int num_kb) {
 }
 
 int run_assign_gemm(const __nv_bfloat16* xb, long long N, int Dp, const CodebookLayout& cl, const void* codebook,
-                    long long K, int index_offset, unsigned long long* packed, cudaStream_t stream) {
+                    long long K, int index_offset, long long* packed, cudaStream_t stream) {
     ArgminEpi::Params ep;
     ep.cnorm = reinterpret_cast<const float*>(static_cast<const char*>(codebook) + cl.cnorm_off);
     ep.packed = packed; ep.rows = (int)N; ep.index_offset = index_offset;
@@ -156,24 +156,24 @@ size_t pero_vq_assign_workspace_bytes(int64_t N, int64_t K, int64_t D) {
     return assign_ws_layout(N, D).total;
 }
 
-int pero_vq_packed_init(uint64_t* packed, int64_t N, pero_stream_t stream) {
+int pero_vq_packed_init(int64_t* packed, int64_t N, pero_stream_t stream) {
     if (!packed) return PERO_ERR_NULL;
     if (N <= 0) return N == 0 ? PERO_OK : PERO_ERR_BAD_SHAPE;
-    packed_init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(packed), N);
+    packed_init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(reinterpret_cast<long long*>(packed), N);
     return (int)cudaGetLastError();
 }
 
-int pero_vq_unpack(const uint64_t* packed, int64_t N, int64_t* idx, float* dmin, pero_stream_t stream) {
+int pero_vq_unpack(const int64_t* packed, int64_t N, int64_t* idx, float* dmin, pero_stream_t stream) {
     if (!packed) return PERO_ERR_NULL;
     if (N <= 0) return N == 0 ? PERO_OK : PERO_ERR_BAD_SHAPE;
     unpack_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(
-        reinterpret_cast<const unsigned long long*>(packed), N, reinterpret_cast<long long*>(idx), dmin);
+        reinterpret_cast<const long long*>(packed), N, reinterpret_cast<long long*>(idx), dmin);
     return (int)cudaGetLastError();
 }
 
 int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int channels_first, int64_t K,
                    int64_t D, const void* codebook, int64_t index_offset, int64_t* idx, float* dmin,
-                   uint64_t* packed_io, float* x_rows, void* workspace, size_t workspace_bytes,
+                   int64_t* packed_io, float* x_rows, void* workspace, size_t workspace_bytes,
                    pero_stream_t stream) {
     if (n_lines < 0 || frames_per_line < 0) return PERO_ERR_BAD_SHAPE;
     const int64_t N = n_lines * frames_per_line;
@@ -188,8 +188,8 @@ int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int
     const CodebookLayout cl = codebook_layout(K, D);
     char* ws = static_cast<char*>(workspace);
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + wl.xb_off);
-    unsigned long long* packed_ws = reinterpret_cast<unsigned long long*>(ws + wl.packed_off);
-    unsigned long long* packed = packed_io ? reinterpret_cast<unsigned long long*>(packed_io) : packed_ws;
+    long long* packed_ws = reinterpret_cast<long long*>(ws + wl.packed_off);
+    long long* packed = packed_io ? reinterpret_cast<long long*>(packed_io) : packed_ws;
     const int Dp = (int)cl.Dp;
 
     if (channels_first) {

@@ -1,0 +1,195 @@
+"""Drop-in head / loss / model glue of the masked-label-prediction task: same class names, constructor
+arguments, attributes and state_dict keys as the reference's ``pero_pretraining/masked_pretraining/model.py``
+(LinearHead :98-105, MaskedCrossEntropyLoss :72-95, MaskedTransformerEncoder :33-69).
+
+The training path is fused: only the masked frames are pushed through the head, and the [M, V] logits never
+reach HBM (C ABI: pero_masked_ce_fwd / pero_masked_ce_bwd).  Full logits for every frame -- which the
+reference's evaluation reads from ``result['output']`` (tester.py:70-93, visualizer.py:32) -- are produced
+only in eval mode or on request.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _rows_from_mask(mask, labels, want, require_label, device):
+    """Ordered int32 frame indices with mask == want.  A numpy mask (what BatchOperator._create_mask
+    returns, batch_operator.py:27-32) is compacted on the host: M is known without a device sync.  A tensor
+    mask is compacted on the device and M is read back once (the reference's boolean indexing syncs too)."""
+    if isinstance(mask, np.ndarray):
+        sel = mask.reshape(-1) == want
+        if require_label:
+            lab = labels.detach().cpu().numpy().reshape(-1) if isinstance(labels, torch.Tensor) else np.asarray(labels).reshape(-1)
+            sel = sel & (lab >= 0)
+        rows = np.flatnonzero(sel).astype(np.int32)
+        return torch.from_numpy(rows).to(device, non_blocking=True), int(rows.size)
+    mask = mask.to(device)
+    rows, count = ops.mask_compact(mask, labels if require_label else None, want)
+    m = int(count.item())
+    return rows[:m], m
+
+
+class _FusedHeadCE(torch.autograd.Function):
+    """sum-of-terms masked CE of Linear(h) against labels; each term = (rows, weight)."""
+
+    @staticmethod
+    def forward(ctx, h, W, b, labels, head_prep, terms, dp_group):
+        # terms: list of (rows int32 tensor, M_local int, weight float)
+        n_frames = h.shape[0] * h.shape[1] if h.dim() == 3 else h.shape[0]
+        h2 = h.detach().reshape(n_frames, h.shape[-1])
+        if h2.dtype not in (torch.float32, torch.bfloat16):
+            h2 = h2.float()
+        h2 = h2.contiguous()
+        lab = labels.detach().reshape(-1)
+        if lab.dtype != torch.int64:
+            lab = lab.long()
+        lab = lab.contiguous()
+        saved, loss = [], None
+        for rows, m_local, weight in terms:
+            if dp_group is not None:
+                cnt = torch.tensor([float(m_local)], device=h2.device)
+                torch.distributed.all_reduce(cnt, group=dp_group)
+                m_global = float(cnt.item())
+            else:
+                m_global = float(m_local)
+            if m_local > 0:
+                loss_sum, lse, _ = ops.masked_ce_fwd(h2, rows, lab, head_prep)
+            else:
+                loss_sum, lse = torch.zeros(1, device=h2.device), None
+            if dp_group is not None:
+                loss_sum = loss_sum.clone()
+                torch.distributed.all_reduce(loss_sum, group=dp_group)
+            # mean over the GLOBAL number of selected frames; an empty selection gives NaN like F.cross_entropy
+            term = loss_sum[0] / m_global if m_global > 0 else loss_sum[0] * float('nan')
+            term = term * weight if weight != 1.0 else term
+            loss = term if loss is None else loss + term
+            saved.append((rows, m_local, weight, m_global, lse))
+        ctx.saved = saved
+        ctx.h2, ctx.lab, ctx.head_prep, ctx.dp_group = h2, lab, head_prep, dp_group
+        ctx.h_shape, ctx.h_dtype, ctx.has_bias = h.shape, h.dtype, b is not None
+        ctx.w_dtype = W.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        h2, lab, head = ctx.h2, ctx.lab, ctx.head_prep
+        g = g.detach().float().reshape(1).contiguous()
+        want_dh = ctx.needs_input_grad[0]
+        d_h = d_W = d_b = None
+        for rows, m_local, weight, m_global, lse in ctx.saved:
+            if m_local == 0 or m_global == 0:
+                continue
+            dh_t, dW_t, db_t = ops.masked_ce_bwd(h2, rows, lab, head, lse, g, weight / m_global, want_dh=want_dh)
+            d_h = dh_t if d_h is None else (d_h + dh_t if dh_t is not None else d_h)
+            d_W = dW_t if d_W is None else d_W + dW_t
+            d_b = db_t if d_b is None else d_b + db_t
+        if d_W is None:
+            d_W = torch.zeros(head.V, head.Dh, device=h2.device)
+            d_b = torch.zeros(head.V, device=h2.device)
+            if want_dh:
+                d_h = torch.zeros_like(h2)
+        if ctx.dp_group is not None:
+            # every rank ends with the gradient of the single-process loss on the concatenated batch
+            torch.distributed.all_reduce(d_W, group=ctx.dp_group)
+            torch.distributed.all_reduce(d_b, group=ctx.dp_group)
+        if d_h is not None:
+            d_h = d_h.reshape(ctx.h_shape).to(ctx.h_dtype)
+        return d_h, d_W.to(ctx.w_dtype), (d_b if ctx.has_bias else None), None, None, None, None
+
+
+class LinearHead(torch.nn.Module):
+    """masked_pretraining/model.py:98-105.  ``forward`` returns logits for every frame (a plain library GEMM,
+    used by evaluation); training goes through ``masked_loss`` instead."""
+
+    def __init__(self, in_features=512, out_features=4096):
+        super().__init__()
+        self.linear = torch.nn.Linear(in_features, out_features)
+        self._prep = None
+        self._prep_tag = None
+
+    def forward(self, x):
+        return self.linear(x)
+
+    def _prepared(self):
+        W, b = self.linear.weight, self.linear.bias
+        if not W.is_cuda:
+            raise ops._lib.PeroError("LinearHead.masked_loss runs on a CUDA (B200) device only; there is no CPU path")
+        tag = (W.data_ptr(), W._version, None if b is None else (b.data_ptr(), b._version), W.device)
+        if self._prep is None or self._prep.blob.device != W.device:
+            self._prep = ops.PreparedHead(W.shape[0], W.shape[1], W.device)
+            self._prep_tag = None
+        if self._prep_tag != tag:
+            self._prep.prepare(W.detach().float(), None if b is None else b.detach().float())
+            self._prep_tag = tag
+        return self._prep
+
+    def masked_loss(self, hidden, labels, mask, unmasked_weight=None, dp_group=None):
+        """Fused LinearHead + MaskedCrossEntropyLoss on hidden states [Nl, T, Dh] (or [N, Dh])."""
+        dev = hidden.device
+        rows, m = _rows_from_mask(mask, labels, 1, False, dev)
+        terms = [(rows, m, 1.0)]
+        if unmasked_weight is not None:
+            rows0, m0 = _rows_from_mask(mask, labels, 0, True, dev)     # model.py:85-90
+            terms.append((rows0, m0, float(unmasked_weight)))
+        return _FusedHeadCE.apply(hidden, self.linear.weight, self.linear.bias, labels, self._prepared(), terms, dp_group)
+
+
+class MaskedCrossEntropyLoss(torch.nn.Module):
+    """masked_pretraining/model.py:72-95: logits-in interface kept for callers that already hold logits."""
+
+    def __init__(self, unmasked_weight=None):
+        super().__init__()
+        self.unmasked_weight = unmasked_weight
+
+    def forward(self, output, labels, mask):
+        from .logits_ce import masked_ce_from_logits
+        return masked_ce_from_logits(output, labels, mask, self.unmasked_weight)
+
+
+class MaskedTransformerEncoder(torch.nn.Module):
+    """masked_pretraining/model.py:33-69.  `backbone(images, mask=mask)` -> [n, c, w] is the caller's module."""
+
+    def __init__(self, backbone, head, loss=None, output='auto'):
+        super().__init__()
+        self.backbone = backbone
+        self.head = head
+        self.loss = MaskedCrossEntropyLoss() if loss is None else loss
+        self.output_mode = output      # 'auto': logits for every frame only in eval mode; True / False to force
+        self._dp_group = None
+
+    def enable_data_parallel(self, group=None):
+        if not torch.distributed.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dp_group = group if group is not None else torch.distributed.group.WORLD
+        return self
+
+    def hidden(self, images, mask=None):
+        x = self.backbone(images, mask=mask)
+        return x.permute(0, 2, 1)          # 'n c w -> n w c' (model.py:60)
+
+    def encode(self, images, mask=None):
+        return self.head(self.hidden(images, mask))
+
+    def forward(self, x, labels=None, mask=None):
+        hidden = self.hidden(x, mask)
+        want_output = (not self.training) if self.output_mode == 'auto' else bool(self.output_mode)
+        output = self.head(hidden) if want_output else None
+        loss = None
+        if mask is not None and labels is not None:
+            fused = isinstance(self.head, LinearHead) and isinstance(self.loss, MaskedCrossEntropyLoss)
+            if fused:
+                loss = self.head.masked_loss(hidden.contiguous(), labels, mask, self.loss.unmasked_weight, self._dp_group)
+            else:
+                if output is None:
+                    output = self.head(hidden)
+                if not isinstance(mask, torch.Tensor):
+                    mask = torch.from_numpy(mask).to(output.device)
+                loss = self.loss(output, labels, mask)
+        return {'output': output, 'loss': loss}
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path))

@@ -1,0 +1,250 @@
+"""Tensor-level wrappers over the C ABI (include/pero_b200.h).
+
+Each function takes/returns torch CUDA tensors, passes raw device pointers + sizes + the current CUDA
+stream to libpero_b200.so and raises on any non-zero return code.  PyTorch is used for device memory and
+streams only; no torch op computes anything on the path here.
+"""
+import torch
+
+from . import _lib
+from ._lib import check
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError(f"{name} must be a CUDA float32 tensor, got {t.dtype} on {t.device}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes, device):
+    # 256-byte aligned scratch from torch's caching allocator (its blocks are 512-byte aligned)
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def require_device():
+    """Fail loudly unless a B200 (sm_100) is current and the library is loadable."""
+    L = _lib.lib()
+    if not torch.cuda.is_available():
+        raise _lib.PeroError("pero_pretraining_b200 needs a CUDA device (B200); there is no CPU fallback")
+    check(L.pero_check_device(), "pero_check_device")
+
+
+# ------------------------------------------------------------------------------------------ codebook / assign
+class PreparedCodebook:
+    """Device blob with the bf16 GEMM operand and |c|^2 of a [K, D] fp32 codebook."""
+
+    def __init__(self, K, D, device):
+        self.K, self.D = int(K), int(D)
+        self.nbytes = _lib.lib().pero_vq_codebook_bytes(self.K, self.D)
+        self.blob = _ws(self.nbytes, device)
+
+    def prepare(self, weight):
+        w = _f32c(weight, "weight")
+        assert tuple(w.shape) == (self.K, self.D)
+        check(_lib.lib().pero_vq_codebook_prepare(w.data_ptr(), self.K, self.D, self.blob.data_ptr(), self.nbytes,
+                                                  _stream()), "pero_vq_codebook_prepare")
+        return self
+
+
+def vq_assign(x, codebook, n_lines, frames_per_line, channels_first, want_dmin=False, want_rows=False,
+              index_offset=0, packed=None):
+    """Nearest-codeword indices.  x: [n_lines, D, frames] (channels_first) or [N, D].
+    Returns (idx int64 [N] or None, dmin or None, x_rows or None)."""
+    L = _lib.lib()
+    x = _f32c(x, "x")
+    N = int(n_lines) * int(frames_per_line)
+    K, D = codebook.K, codebook.D
+    dev = x.device
+    idx = torch.empty(N, dtype=torch.int64, device=dev) if packed is None else None
+    dmin = torch.empty(N, dtype=torch.float32, device=dev) if (want_dmin and packed is None) else None
+    x_rows = torch.empty(N, D, dtype=torch.float32, device=dev) if want_rows else None
+    if N == 0:
+        return idx, dmin, x_rows
+    wsb = L.pero_vq_assign_workspace_bytes(N, K, D)
+    ws = _ws(wsb, dev)
+    check(L.pero_vq_assign(x.data_ptr(), int(n_lines), int(frames_per_line), 1 if channels_first else 0, K, D,
+                           codebook.blob.data_ptr(), int(index_offset), _p(idx), _p(dmin), _p(packed), _p(x_rows),
+                           ws.data_ptr(), wsb, _stream()), "pero_vq_assign")
+    return idx, dmin, x_rows
+
+
+def vq_packed_init(N, device):
+    packed = torch.empty(int(N), dtype=torch.int64, device=device)
+    check(_lib.lib().pero_vq_packed_init(packed.data_ptr(), int(N), _stream()), "pero_vq_packed_init")
+    return packed
+
+
+def vq_unpack(packed, want_dmin=False):
+    N = packed.numel()
+    idx = torch.empty(N, dtype=torch.int64, device=packed.device)
+    dmin = torch.empty(N, dtype=torch.float32, device=packed.device) if want_dmin else None
+    check(_lib.lib().pero_vq_unpack(packed.data_ptr(), N, idx.data_ptr(), _p(dmin), _stream()), "pero_vq_unpack")
+    return idx, dmin
+
+
+def vq_gather_st(x_rows, idx, weight, n_lines, frames_per_line, channels_first):
+    """out = x + (weight[idx] - x), channels-first [n_lines, D, frames] or rows [N, D]."""
+    w = _f32c(weight, "weight")
+    K, D = w.shape
+    shape = (int(n_lines), D, int(frames_per_line)) if channels_first else (int(n_lines) * int(frames_per_line), D)
+    out = torch.empty(shape, dtype=torch.float32, device=w.device)
+    check(_lib.lib().pero_vq_gather_st(x_rows.data_ptr(), idx.data_ptr(), w.data_ptr(), int(n_lines),
+                                       int(frames_per_line), 1 if channels_first else 0, K, D, out.data_ptr(),
+                                       _stream()), "pero_vq_gather_st")
+    return out
+
+
+def vq_ema_accumulate(x_rows, idx, K):
+    """Deterministic per-codeword sums and counts: one fp32 buffer [K*D + K]."""
+    L = _lib.lib()
+    N, D = x_rows.shape
+    out = torch.empty(K * D + K, dtype=torch.float32, device=x_rows.device)
+    wsb = L.pero_vq_ema_workspace_bytes(N, K, D)
+    ws = _ws(wsb, x_rows.device)
+    check(L.pero_vq_ema_accumulate(x_rows.data_ptr(), idx.data_ptr(), N, K, D, out.data_ptr(), ws.data_ptr(), wsb,
+                                   _stream()), "pero_vq_ema_accumulate")
+    return out
+
+
+def vq_ema_apply(sums_counts, ema_w, ema_cluster_size, weight, decay, epsilon, codebook=None):
+    """In-place EMA update of ema_w / ema_cluster_size / weight (+ refresh of the prepared codebook)."""
+    K, D = weight.shape
+    for t, n in ((ema_w, "ema_w"), (ema_cluster_size, "ema_cluster_size"), (weight, "weight")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError(f"{n} must be a contiguous CUDA float32 tensor")
+    check(_lib.lib().pero_vq_ema_apply(sums_counts.data_ptr(), K, D, float(decay), float(epsilon), ema_w.data_ptr(),
+                                       ema_cluster_size.data_ptr(), weight.data_ptr(),
+                                       None if codebook is None else codebook.blob.data_ptr(),
+                                       0 if codebook is None else codebook.nbytes, None, 0, _stream()),
+          "pero_vq_ema_apply")
+
+
+def vq_counts(idx, K):
+    counts = torch.empty(int(K), dtype=torch.int64, device=idx.device)
+    check(_lib.lib().pero_vq_counts(idx.data_ptr(), idx.numel(), int(K), counts.data_ptr(), _stream()), "pero_vq_counts")
+    return counts
+
+
+# ------------------------------------------------------------------------------------------ MSE
+def mse_fwd(a, b, scale_a=1.0, scale_b=0.0):
+    """m = mean((a-b)^2); returns the 0-dim tensor scale_a*m + scale_b*m."""
+    L = _lib.lib()
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    if a.shape != b.shape:
+        raise ValueError(f"mse: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    wsb = L.pero_mse_workspace_bytes(a.numel())
+    ws = _ws(wsb, a.device)
+    check(L.pero_mse_fwd(a.data_ptr(), b.data_ptr(), a.numel(), float(scale_a), float(scale_b), out.data_ptr(), ws.data_ptr(), wsb,
+                         _stream()), "pero_mse_fwd")
+    return out
+
+
+def mse_bwd(a, b, coef, grad_out, want_a, want_b):
+    """g_b = coef * grad_out * (b - a); g_a = -g_b."""
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    g_a = torch.empty_like(a) if want_a else None
+    g_b = torch.empty_like(b) if want_b else None
+    go = None if grad_out is None else _f32c(grad_out, "grad_out")
+    check(_lib.lib().pero_mse_bwd(a.data_ptr(), b.data_ptr(), a.numel(), float(coef), _p(go), _p(g_a), _p(g_b),
+                                  _stream()), "pero_mse_bwd")
+    return g_a, g_b
+
+
+# ------------------------------------------------------------------------------------------ masked CE
+class PreparedHead:
+    """Device blob with bf16 W, bf16 W^T and the bias of a Linear(Dh -> V) head."""
+
+    def __init__(self, V, Dh, device):
+        self.V, self.Dh = int(V), int(Dh)
+        self.nbytes = _lib.lib().pero_head_bytes(self.V, self.Dh)
+        self.blob = _ws(self.nbytes, device)
+
+    def prepare(self, W, bias):
+        W = _f32c(W, "W")
+        b = None if bias is None else _f32c(bias, "bias")
+        check(_lib.lib().pero_head_prepare(W.data_ptr(), _p(b), self.V, self.Dh, self.blob.data_ptr(), self.nbytes,
+                                           _stream()), "pero_head_prepare")
+        return self
+
+
+def _check_h(h):
+    if not h.is_cuda or h.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"hidden states must be CUDA float32 or bfloat16, got {h.dtype}")
+    return h if h.is_contiguous() else h.contiguous()
+
+
+def masked_ce_fwd(h, rows, labels, head):
+    """h [N, Dh]; rows int32 [M]; labels int64 [N].  Returns (loss_sum [1], lse [M], workspace)."""
+    L = _lib.lib()
+    h = _check_h(h)
+    N, Dh = h.shape
+    M = rows.numel()
+    loss_sum = torch.empty(1, dtype=torch.float32, device=h.device)
+    lse = torch.empty(M, dtype=torch.float32, device=h.device)
+    wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
+    ws = _ws(wsb, h.device)
+    check(L.pero_masked_ce_fwd(h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M,
+                               labels.data_ptr(), head.blob.data_ptr(), head.V, loss_sum.data_ptr(), lse.data_ptr(),
+                               ws.data_ptr(), wsb, _stream()), "pero_masked_ce_fwd")
+    return loss_sum, lse, ws
+
+
+def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None):
+    """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32)."""
+    L = _lib.lib()
+    h = _check_h(h)
+    N, Dh = h.shape
+    M = rows.numel()
+    d_h = torch.empty_like(h) if want_dh else None
+    d_W = torch.empty(head.V, Dh, dtype=torch.float32, device=h.device)
+    d_b = torch.empty(head.V, dtype=torch.float32, device=h.device)
+    wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
+    if ws is None or ws.numel() < wsb:
+        ws = _ws(wsb, h.device)
+    gs = None if grad_scale is None else _f32c(grad_scale, "grad_scale")
+    check(L.pero_masked_ce_bwd(h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M,
+                               labels.data_ptr(), head.blob.data_ptr(), head.V, lse.data_ptr(), _p(gs),
+                               float(inv_count), _p(d_h), d_W.data_ptr(), d_b.data_ptr(), ws.data_ptr(), wsb,
+                               _stream()), "pero_masked_ce_bwd")
+    return d_h, d_W, d_b
+
+
+_MASK_DTYPES = {torch.int64: 0, torch.int32: 1, torch.uint8: 2, torch.bool: 2}
+
+
+def mask_compact(mask, labels=None, want=1):
+    """Ordered indices of frames with mask == want (and labels >= 0 when given), no host sync.
+    Returns (rows int32 [N] (first `count` valid), count int32 [1])."""
+    L = _lib.lib()
+    m = mask.reshape(-1)
+    if not m.is_contiguous():
+        m = m.contiguous()
+    if m.dtype not in _MASK_DTYPES:
+        raise TypeError(f"mask dtype {m.dtype} not supported")
+    N = m.numel()
+    rows = torch.empty(N, dtype=torch.int32, device=m.device)
+    count = torch.zeros(1, dtype=torch.int32, device=m.device)
+    wsb = L.pero_mask_compact_workspace_bytes(N)
+    ws = _ws(wsb, m.device)
+    lab = None if labels is None else labels.reshape(-1).contiguous()
+    check(L.pero_mask_compact(m.data_ptr(), _MASK_DTYPES[m.dtype], int(want), _p(lab), N, rows.data_ptr(),
+                              count.data_ptr(), ws.data_ptr(), wsb, _stream()), "pero_mask_compact")
+    return rows, count
+
+
+def debug_gemm_tn(a_bf16, b_bf16, variant=0, splits=1):
+    ra, kd = a_bf16.shape
+    rb = b_bf16.shape[0]
+    out = torch.zeros(max(splits, 1), ra, rb, dtype=torch.float32, device=a_bf16.device)
+    check(_lib.lib().pero_debug_gemm_tn(a_bf16.data_ptr(), ra, b_bf16.data_ptr(), rb, kd, int(variant), int(splits),
+                                        out.data_ptr(), _stream()), "pero_debug_gemm_tn")
+    return out

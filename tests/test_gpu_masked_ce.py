@@ -1,0 +1,164 @@
+"""GPU parity of the fused LinearHead + MaskedCrossEntropyLoss path (and the logits-in loss) against the
+golden fixture produced by the reference and against the oracle.
+
+Stated tolerances (north_star: "losses and gradients agree within a stated bf16/tf32 relative tolerance"):
+the fused path multiplies bf16-rounded hidden states and weights with fp32 accumulation, and its backward
+rounds dlogits to bf16 before the d_W / d_h GEMMs, so
+    loss:       |got - ref| <= 3e-3 * |ref|
+    gradients:  max|got - ref| <= 2e-2 * max|ref|   (per tensor)
+The logits-in loss is fp32 end to end: rtol 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import pero_oracle as O
+
+pytestmark = pytest.mark.gpu
+LOSS_RTOL = 3e-3
+GRAD_RTOL = 2e-2
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _close_grad(got, ref, what):
+    got, ref = got.detach().double().cpu(), ref.double()
+    err = (got - ref).abs().max().item()
+    assert err <= GRAD_RTOL * max(ref.abs().max().item(), 1e-12), f"{what}: max err {err:.3e} vs max|ref| {ref.abs().max().item():.3e}"
+
+
+def _run_fused(dev, h, W, b, labels, mask, uw, h_dtype=torch.float32):
+    from pero_pretraining_b200 import LinearHead
+    head = LinearHead(W.shape[1], W.shape[0]).to(dev)
+    with torch.no_grad():
+        head.linear.weight.copy_(W)
+        head.linear.bias.copy_(b)
+    hh = h.to(dev).to(h_dtype).requires_grad_(True)
+    loss = head.masked_loss(hh, labels.to(dev), mask, uw)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss, hh.grad, head.linear.weight.grad, head.linear.bias.grad
+
+
+def test_fused_head_ce_golden(cuda_dev):
+    g = load_golden("masked_ce")
+    h, W, b, labels = T(g["h"]), T(g["W"]), T(g["b"]), T(g["labels"])
+    for tag, uw in (("plain", None), ("unmasked", float(g["unmasked_weight"]))):
+        for mask in (g["mask"], T(g["mask"])):        # numpy mask (host compaction) and tensor mask (device compaction)
+            loss, gh, gW, gb = _run_fused(cuda_dev, h, W, b, labels, mask, uw)
+            assert abs(loss.item() - float(g[f"{tag}_loss"])) <= LOSS_RTOL * abs(float(g[f"{tag}_loss"]))
+            _close_grad(gh, T(g[f"{tag}_g_h"]), "d_h")
+            _close_grad(gW, T(g[f"{tag}_g_W"]), "d_W")
+            _close_grad(gb, T(g[f"{tag}_g_b"]), "d_b")
+            pad = (T(g["labels"]) < 0).to(gh.device)
+            assert float(gh[pad].abs().max()) == 0.0            # padding frames get no gradient
+
+
+@pytest.mark.parametrize("Nl,T_,Dh,V,p,dtype", [
+    (8, 128, 512, 4096, 0.15, torch.float32),      # config c1
+    (8, 128, 512, 4096, 0.15, torch.bfloat16),     # --bfloat16 autocast hands the head bf16 hidden states
+    (5, 37, 96, 1000, 0.5, torch.float32),         # ragged: V, Dh, M not multiples of any tile
+    (2, 9, 64, 300, 1.0, torch.float32),           # every frame masked
+    (3, 50, 512, 257, 0.02, torch.float32),        # a handful of masked frames
+])
+def test_fused_head_ce_vs_oracle(cuda_dev, Nl, T_, Dh, V, p, dtype):
+    rng = np.random.default_rng(Nl * 1000 + V)
+    g = torch.Generator(device="cpu").manual_seed(V + Dh)
+    h = torch.randn(Nl, T_, Dh, generator=g)
+    bound = 1.0 / np.sqrt(Dh)
+    W = (torch.rand(V, Dh, generator=g) * 2 - 1) * bound
+    b = (torch.rand(V, generator=g) * 2 - 1) * bound
+    labels = torch.from_numpy(rng.integers(0, V, size=(Nl, T_))).long()
+    if T_ > 8:
+        labels[:, -4:] = -1
+    mask = O.create_mask(labels.numpy(), p, rng)
+    if mask.sum() == 0:
+        mask[0, 0] = 1
+    if dtype == torch.bfloat16:
+        h = h.bfloat16().float()           # the oracle sees the same (bf16-representable) hidden states
+    ref_loss, ref_dh, ref_dW, ref_db = O.head_masked_ce(h, W, b, labels, T(mask))
+    loss, gh, gW, gb = _run_fused(cuda_dev, h, W, b, labels, mask, None, dtype)
+    assert abs(loss.item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item())
+    assert gh.dtype == dtype
+    _close_grad(gh.float(), ref_dh, "d_h")
+    _close_grad(gW, ref_dW, "d_W")
+    _close_grad(gb, ref_db, "d_b")
+
+
+def test_fused_head_ce_is_deterministic(cuda_dev):
+    g = torch.Generator(device="cpu").manual_seed(77)
+    h, W, b = torch.randn(4, 64, 512, generator=g), torch.randn(2048, 512, generator=g) * 0.04, torch.zeros(2048)
+    labels = torch.randint(0, 2048, (4, 64), generator=g)
+    mask = (torch.rand(4, 64, generator=g) < 0.3).long().numpy()
+    a = _run_fused(cuda_dev, h, W, b, labels, mask, None)
+    c = _run_fused(cuda_dev, h, W, b, labels, mask, None)
+    for u, v in zip(a, c):
+        assert torch.equal(u, v)
+
+
+def test_empty_mask_gives_nan_like_reference(cuda_dev):
+    g = torch.Generator(device="cpu").manual_seed(1)
+    h, W, b = torch.randn(2, 8, 64, generator=g), torch.randn(100, 64, generator=g), torch.zeros(100)
+    labels = torch.randint(0, 100, (2, 8), generator=g)
+    loss, gh, gW, gb = _run_fused(cuda_dev, h, W, b, labels, np.zeros((2, 8), dtype=int), None)
+    assert torch.isnan(loss)
+
+
+def test_logits_in_loss_golden(cuda_dev):
+    from pero_pretraining_b200 import MaskedCrossEntropyLoss
+    g = load_golden("masked_ce")
+    for tag, uw in (("plain", None), ("unmasked", float(g["unmasked_weight"]))):
+        logits = T(g[f"{tag}_logits"]).to(cuda_dev).requires_grad_(True)
+        loss = MaskedCrossEntropyLoss(uw)(logits, T(g["labels"]).to(cuda_dev), T(g["mask"]).to(cuda_dev))
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), float(g[f"{tag}_loss"]), rtol=1e-5)
+        np.testing.assert_allclose(logits.grad.cpu().numpy(), g[f"{tag}_g_logits"], rtol=1e-4, atol=1e-7)
+
+
+def test_model_glue_train_and_eval(cuda_dev):
+    """MaskedTransformerEncoder.forward contract (model.py:41-56): dict keys; loss in training without
+    materialising logits; logits for every frame in eval; numpy or tensor mask."""
+    from pero_pretraining_b200 import LinearHead, MaskedTransformerEncoder
+
+    class Backbone(torch.nn.Module):          # stand-in for the (out-of-scope) transformer: [n, 3, 40, W] -> [n, 64, W/8]
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 64, (40, 8), stride=(40, 8))
+
+        def forward(self, images, mask=None):
+            return self.conv(images).squeeze(2)
+
+    torch.manual_seed(0)
+    model = MaskedTransformerEncoder(Backbone(), LinearHead(64, 200)).to(cuda_dev)
+    images = torch.rand(4, 3, 40, 256, device=cuda_dev)
+    labels = torch.randint(0, 200, (4, 32), device=cuda_dev)
+    mask = (np.random.default_rng(0).random((4, 32)) < 0.3).astype(int)
+    model.train()
+    out = model(images, labels, mask)
+    assert set(out.keys()) == {"output", "loss"} and out["output"] is None and out["loss"].dim() == 0
+    out["loss"].backward()
+    assert model.backbone.conv.weight.grad is not None and model.head.linear.weight.grad is not None
+    model.eval()
+    with torch.no_grad():
+        ev = model(images, labels, torch.from_numpy(mask).to(cuda_dev))
+    assert ev["output"].shape == (4, 32, 200)
+    ref = O.masked_ce(ev["output"].float().cpu(), labels.cpu(), T(mask))
+    assert abs(ev["loss"].item() - ref.item()) <= LOSS_RTOL * abs(ref.item())
+    assert abs(out["loss"].item() - ref.item()) <= LOSS_RTOL * abs(ref.item())
+    assert model(images)["loss"] is None
+
+
+def test_mask_compact_matches_nonzero(cuda_dev):
+    from pero_pretraining_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(4)
+    for dtype in (torch.int64, torch.int32, torch.uint8, torch.bool):
+        m = (torch.rand(5, 777, generator=g) < 0.2).to(dtype).to(cuda_dev)
+        labels = torch.randint(-1, 5, (5, 777), generator=g).to(cuda_dev)
+        rows, count = ops.mask_compact(m, None, 1)
+        ref = torch.nonzero(m.reshape(-1).long() == 1).flatten()
+        assert int(count) == ref.numel() and torch.equal(rows[:ref.numel()].long(), ref)
+        rows0, count0 = ops.mask_compact(m, labels, 0)
+        ref0 = torch.nonzero((m.reshape(-1).long() == 0) & (labels.reshape(-1) >= 0)).flatten()
+        assert int(count0) == ref0.numel() and torch.equal(rows0[:ref0.numel()].long(), ref0)

@@ -1,0 +1,224 @@
+"""GPU parity of the drop-in VectorQuantizer / VQVAE (gather + straight-through, commitment loss, EMA
+codebook update, counts) against the golden fixtures produced by the reference and against the oracle.
+
+Method: (1) indices must equal the reference's except on near-ties (fp64 gap < EPS_TIE); (2) everything
+downstream of the assignment is compared with the oracle evaluated ON THE CUDA INDICES, so a legal near-tie
+flip does not hide (or fake) an error in the gather / EMA arithmetic.  Tolerances are fp32 re-association
+only: the gather output is bit-exact, EMA sums differ by summation order (rtol 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import pero_oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS_TIE = 2e-3
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _make_vq(g, dev):
+    from pero_pretraining_b200 import VectorQuantizer
+    decay = float(g["decay"])
+    vq = VectorQuantizer(int(g["K"]), int(g["D"]), float(g["commitment_cost"]), decay).to(dev)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(T(g["weight0"]))
+        if decay > 0:
+            vq.ema_w.copy_(T(g["ema_w0"]))
+            vq.ema_cluster_size.copy_(T(g["ema_cluster_size0"]))
+    return vq
+
+
+def _replay(name, dev):
+    g = load_golden(name)
+    decay, cc, eps = float(g["decay"]), float(g["commitment_cost"]), float(g["epsilon"])
+    training = bool(int(g["training"]))
+    vq = _make_vq(g, dev)
+    vq.train(training)
+    w_ptr = vq.embedding.weight.data_ptr()
+    w, ema_w, cs = T(g["weight0"]), (T(g["ema_w0"]) if decay > 0 else None), (T(g["ema_cluster_size0"]) if decay > 0 else None)
+    any_flip = False
+    for s in range(int(g["steps"])):
+        x = T(g[f"x{s}"]).to(dev).requires_grad_(True)
+        q, idx = vq(x)
+        loss = vq.calculate_loss(q, x)
+        (loss + (q * T(g[f"gq{s}"]).to(dev)).sum()).backward()
+        torch.cuda.synchronize()
+        assert q.shape == x.shape and q.is_contiguous() and idx.dtype == torch.int64 and idx.shape == (x.numel() // x.shape[1],)
+        # (1) indices vs the reference, near-tie rule (state `w` is the oracle's, which tracks the CUDA indices)
+        flat, _ = O.flatten_frames(T(g[f"x{s}"]))
+        ref_idx, _, gap = O.assign_fp64(flat.numpy(), w.numpy())
+        differs = idx.cpu().numpy() != ref_idx
+        assert (gap[differs] < EPS_TIE).all()
+        if not any_flip:
+            d2 = idx.cpu().numpy() != g[f"idx{s}"]
+            assert (gap[d2] < EPS_TIE).all()
+            any_flip = any_flip or bool(d2.any())
+        # (2) downstream arithmetic vs the oracle on the CUDA indices
+        ref = O.vq_forward(T(g[f"x{s}"]), w, ema_w, cs, decay, eps, training, indices_override=idx.cpu())
+        assert torch.equal(q.detach().cpu(), ref["quantized"]), "gather + straight-through must be bit-exact"
+        ref_loss = O.vq_calculate_loss(ref["quantized"], T(g[f"x{s}"]), cc, decay)
+        np.testing.assert_allclose(loss.item(), float(ref_loss), rtol=2e-6)
+        g_tok, g_feat = O.vq_calculate_loss_grads(ref["quantized"], T(g[f"x{s}"]), cc, decay)
+        gx = T(g[f"gq{s}"]) + g_tok + g_feat
+        np.testing.assert_allclose(x.grad.cpu().numpy(), gx.numpy(), rtol=1e-5, atol=1e-7)
+        if decay > 0 and training:
+            np.testing.assert_allclose(vq.ema_cluster_size.cpu().numpy(), ref["ema_cluster_size"].numpy(), rtol=2e-6)
+            np.testing.assert_allclose(vq.ema_w.detach().cpu().numpy(), ref["ema_w"].numpy(), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(vq.embedding.weight.detach().cpu().numpy(), ref["weight"].numpy(), rtol=2e-5, atol=1e-6)
+            w, ema_w, cs = ref["weight"], ref["ema_w"], ref["ema_cluster_size"]
+            if not any_flip:     # no flip so far: the state must also equal the reference's own
+                np.testing.assert_allclose(vq.embedding.weight.detach().cpu().numpy(), g[f"weight{s + 1}"], rtol=2e-5, atol=1e-6)
+        else:
+            assert torch.equal(vq.embedding.weight.detach().cpu(), T(g["weight0"]))
+        assert vq.embedding.weight.data_ptr() == w_ptr       # updated in place (documented difference)
+    return vq
+
+
+def test_vq_cold_start_three_steps(cuda_dev):
+    vq = _replay("vq_cold_3steps", cuda_dev)
+    assert vq.embedding.weight.abs().max().item() > 1e3      # the reference's cold-start blow-up is reproduced
+
+
+def test_vq_warm_three_steps(cuda_dev):
+    _replay("vq_warm_3steps", cuda_dev)
+
+
+def test_vq_no_decay_and_eval(cuda_dev):
+    _replay("vq_nodecay", cuda_dev)
+    _replay("vq_eval", cuda_dev)
+
+
+def test_state_dict_keys_and_reload(cuda_dev):
+    from pero_pretraining_b200 import VectorQuantizer
+    vq = VectorQuantizer(32, 16, 0.25, 0.99).to(cuda_dev)
+    assert list(vq.state_dict().keys()) == ["ema_w", "ema_cluster_size", "embedding.weight"]
+    x = torch.randn(2, 16, 1, 8, device=cuda_dev)
+    vq.eval()
+    _, i1 = vq(x)
+    vq2 = VectorQuantizer(32, 16, 0.25, 0.99).to(cuda_dev).eval()
+    _, i_other = vq2(x)
+    vq2.load_state_dict(vq.state_dict())        # derived bf16 codebook / |c|^2 cache must be rebuilt
+    _, i2 = vq2(x)
+    assert torch.equal(i1, i2) and not torch.equal(i1, i_other)
+    assert list(VectorQuantizer(8, 4, 0.25, 0.0).state_dict().keys()) == ["embedding.weight"]
+
+
+def test_calculate_loss_golden(cuda_dev):
+    from pero_pretraining_b200 import VectorQuantizer
+    g = load_golden("vq_calculate_loss")
+    for tag in ("ema", "nodecay"):
+        vq = VectorQuantizer(16, 8, 0.25, float(g[f"{tag}_decay"])).to(cuda_dev)
+        tokens = T(g[f"{tag}_tokens"]).to(cuda_dev).requires_grad_(True)
+        feats = T(g[f"{tag}_features"]).to(cuda_dev).requires_grad_(True)
+        loss = vq.calculate_loss(tokens, feats)
+        (loss * float(g["grad_out"])).backward()
+        np.testing.assert_allclose(loss.item(), float(g[f"{tag}_loss"]), rtol=2e-6)
+        np.testing.assert_allclose(feats.grad.cpu().numpy(), g[f"{tag}_g_features"], rtol=1e-5, atol=1e-8)
+        gt = tokens.grad.cpu().numpy() if tokens.grad is not None else np.zeros_like(g[f"{tag}_g_tokens"])
+        np.testing.assert_allclose(gt, g[f"{tag}_g_tokens"], rtol=1e-5, atol=1e-8)
+
+
+def test_vqvae_forward_golden(cuda_dev):
+    """VQVAE.forward with stand-in conv encoder/decoder: dict keys, the projection/loss wiring
+    (calculate_loss(tokens, features) across the 1x1 convs) and counts."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from pero_pretraining_b200 import VQVAE
+
+    class Enc(torch.nn.Module):
+        out_channels = 6
+
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 6, (4, 8), stride=(4, 8))
+
+        def forward(self, x):
+            return self.conv(x)
+
+    class Dec(torch.nn.Module):
+        base_channels = 6
+
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.ConvTranspose2d(6, 3, (4, 8), stride=(4, 8))
+
+        def forward(self, x):
+            return self.conv(x)
+
+    g = load_golden("vqvae_forward")
+    m = VQVAE(Enc(), Dec(), num_embeddings=32, embeddings_dim=8)
+    m.load_state_dict({k[len("state_"):]: T(v) for k, v in g.items() if k.startswith("state_")})
+    m = m.to(cuda_dev).train()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        out = m(T(g["images"]).to(cuda_dev))
+        out["loss"].backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert set(out.keys()) == {"tokens", "labels", "loss", "reconstructions", "counts"}
+    labels = out["labels"].cpu().numpy()
+    assert np.array_equal(out["counts"].cpu().numpy(), np.bincount(labels, minlength=32)) and out["counts"].dtype == torch.int64
+    if np.array_equal(labels, g["out_labels"]):      # 32 frames, K = 32: a bf16 near-tie flip is unlikely but legal
+        np.testing.assert_allclose(out["tokens"].detach().cpu().numpy(), g["out_tokens"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(out["loss"].item(), float(g["out_loss"]), rtol=1e-4)
+        np.testing.assert_allclose(m.encoder_projection_layer.weight.grad.cpu().numpy(), g["grad_enc_proj_w"], rtol=1e-3, atol=1e-5)
+        np.testing.assert_allclose(m.vq.embedding.weight.detach().cpu().numpy(), g["after_vq.embedding.weight"], rtol=1e-4, atol=1e-5)
+    else:
+        pytest.skip("near-tie flip changed a label; downstream values are covered by the VectorQuantizer replays")
+
+
+def test_ema_accumulate_deterministic_and_exact_counts(cuda_dev):
+    """Sort-based segmented sum: bit-identical across runs, counts exact, sums match an fp64 scatter-add;
+    includes the collapsed case (one codeword owns every frame) and empty codewords."""
+    from pero_pretraining_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(17)
+    for N, K, D, mode in [(8192, 8192, 256, "uniform"), (5000, 300, 96, "skewed"), (4097, 64, 130, "collapsed"), (33, 7, 5, "uniform")]:
+        x = torch.randn(N, D, generator=g).to(cuda_dev)
+        if mode == "uniform":
+            idx = torch.randint(0, K, (N,), generator=g)
+        elif mode == "skewed":
+            idx = (torch.rand(N, generator=g) ** 4 * K).long().clamp_(0, K - 1)
+        else:
+            idx = torch.full((N,), 3, dtype=torch.int64)
+        idx = idx.to(cuda_dev)
+        a = ops.vq_ema_accumulate(x, idx, K)
+        b = ops.vq_ema_accumulate(x, idx, K)
+        assert torch.equal(a, b), "EMA sums must be bit-identical run to run"
+        sums, counts = a[:K * D].view(K, D), a[K * D:]
+        assert torch.equal(counts.long(), torch.bincount(idx, minlength=K))
+        ref = torch.zeros(K, D, dtype=torch.float64, device=cuda_dev).index_add_(0, idx, x.double())
+        tol = 1e-6 * max(1.0, float(counts.max())) ** 0.5 * 8
+        assert (sums.double() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+        assert torch.equal(ops.vq_counts(idx, K), torch.bincount(idx, minlength=K))
+
+
+def test_gather_st_and_mse_kernels(cuda_dev):
+    from pero_pretraining_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(23)
+    for nl, D, T_ in [(3, 70, 45), (64, 256, 128), (1, 8, 1)]:
+        K = 50
+        x = torch.randn(nl, D, T_, generator=g).to(cuda_dev)
+        w = torch.randn(K, D, generator=g).to(cuda_dev)
+        idx = torch.randint(0, K, (nl * T_,), generator=g).to(cuda_dev)
+        rows = x.permute(0, 2, 1).reshape(nl * T_, D).contiguous()
+        out = ops.vq_gather_st(rows, idx, w, nl, T_, True)
+        ref = rows + (w[idx] - rows)
+        assert torch.equal(out, ref.view(nl, T_, D).permute(0, 2, 1).contiguous())
+        assert torch.equal(ops.vq_gather_st(rows, idx, w, nl, T_, False), ref)
+    a = torch.randn(1000003, generator=g).to(cuda_dev)
+    b = torch.randn(1000003, generator=g).to(cuda_dev)
+    m1, m2 = ops.mse_fwd(a, b, 0.0, 0.25), ops.mse_fwd(a, b, 0.0, 0.25)
+    assert torch.equal(m1, m2)
+    np.testing.assert_allclose(m1.item(), 0.25 * ((a.double() - b.double()) ** 2).mean().item(), rtol=1e-6)
+
+
+def test_quantizer_fails_loudly_on_cpu():
+    from pero_pretraining_b200 import PeroError, VectorQuantizer
+    vq = VectorQuantizer(8, 4, 0.25, 0.99)
+    with pytest.raises(PeroError):
+        vq(torch.randn(1, 4, 1, 3))
