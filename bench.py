@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py — masked frames/s of the quantize-and-predict hot path (VQ assign + masked CE fwd/bwd).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (B200 kernels)
+    python bench.py --impl reference --gpus N --steps K ...   # reference arm: the CPU restatement (oracle port)
+
+One "step" = one pass of the hot path over one synthetic batch (BASELINE.json configs[1], per GPU):
+  VectorQuantizer fwd (assign + gather/straight-through) + EMA codebook update + commitment loss fwd/bwd on
+  64 lines x 128 frames x D=256 against an 8192 x 256 codebook, then LinearHead + masked cross-entropy fwd/bwd
+  (Dh=512, V=8192 = the codebook's labels, 15 % masking) on the labels the quantizer just produced.
+`value`  : whole-job masked frames/s with every input resident in HBM (CUDA-graph replay of the step).
+`e2e`    : same metric through the public module API with HOST (pinned) inputs: H2D of features / hidden
+           states / mask rows and the D2H loss read are inside the timed region.
+`roofline`: the dominant kernel (distance GEMM + arg-min) timed alone with CUDA events.
+`cpu_baseline`: the oracle port of the reference path on this box's host cores (rank 0, N=1 only).
+Multi-GPU: weak scaling, batch-sharded (every rank owns 64 lines), codebook/head replicated, EMA sums|counts
+and head gradients all-reduced over NCCL inside the step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(lines=64, frames=128, K=8192, D=256, Dh=512, V=8192, p=0.15, commitment_cost=0.25, decay=0.99, epsilon=1e-5)
+WORKLOAD = ("configs[1]: VQ-VAE quantizer fwd/bwd + EMA update, 8192x256 codebook, 64 lines x 128 frames, "
+            "+ masked CE fwd/bwd over the 8192 labels (Dh=512, 15% masking)")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ data
+def make_batch(rank, seed=1236):
+    """Seeded synthetic '40-px text-line features' (warmed state): frames are drawn
+    around codewords so the index distribution stays spread; hidden states ~ N(0,1); head ~ nn.Linear init."""
+    c = CFG
+    g = torch.Generator().manual_seed(seed)                 # replicated state: same on every rank
+    weight = torch.randn(c["K"], c["D"], generator=g)
+    bound = 1.0 / np.sqrt(c["Dh"])
+    W = (torch.rand(c["V"], c["Dh"], generator=g) * 2 - 1) * bound
+    b = (torch.rand(c["V"], generator=g) * 2 - 1) * bound
+    gr = torch.Generator().manual_seed(seed + 1000 + rank)   # per-rank shard of the batch
+    N = c["lines"] * c["frames"]
+    j = torch.randint(0, c["K"], (N,), generator=gr)
+    rows = weight[j] + 0.5 * torch.randn(N, c["D"], generator=gr)
+    x = rows.view(c["lines"], c["frames"], c["D"]).permute(0, 2, 1).contiguous().view(c["lines"], c["D"], 1, c["frames"])
+    gq = torch.randn(c["lines"], c["D"], 1, c["frames"], generator=gr)
+    h = torch.randn(c["lines"], c["frames"], c["Dh"], generator=gr)
+    rng = np.random.default_rng(seed + rank)
+    mask = (rng.random((c["lines"], c["frames"])) < c["p"]).astype(int)
+    return dict(weight=weight, W=W, b=b, x=x, gq=gq, h=h, mask=mask)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_factory(batch):
+    """One step of the same workload restated on the reference's CPU ops (oracle port): VectorQuantizer
+    fwd + EMA + commitment loss and gradient, LinearHead over EVERY frame + MaskedCrossEntropyLoss fwd/bwd
+    (the reference's head is not mask-aware: masked_pretraining/model.py:60-61, 78-82)."""
+    from oracle import pero_oracle as O
+    c = CFG
+    state = dict(weight=batch["weight"].clone(), ema_w=batch["weight"].clone(), cs=torch.ones(c["K"]))
+    mask_t = torch.from_numpy(batch["mask"])
+
+    def step():
+        out = O.vq_forward(batch["x"], state["weight"], state["ema_w"], state["cs"], c["decay"], c["epsilon"], True)
+        loss_c = O.vq_calculate_loss(out["quantized"], batch["x"], c["commitment_cost"], c["decay"])
+        _, g_feat = O.vq_calculate_loss_grads(out["quantized"], batch["x"], c["commitment_cost"], c["decay"])
+        g_x = O.vq_forward_grad_inputs(batch["gq"]) + g_feat
+        state.update(weight=out["weight"], ema_w=out["ema_w"], cs=out["ema_cluster_size"])
+        labels = out["indices"].view(c["lines"], c["frames"])
+        loss, d_h, d_W, d_b = O.head_masked_ce(batch["h"], batch["W"], batch["b"], labels, mask_t)
+        return float(loss_c) + float(loss), g_x, d_h, d_W, d_b
+
+    return step
+
+
+def run_cpu(batch, reps, warm):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_factory(batch)
+    for _ in range(warm):
+        step()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), float(np.min(ts))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = make_batch(0)
+    M = int(batch["mask"].sum())
+    steps = max(1, min(args.steps, 5))           # bounded sample: each CPU step takes seconds
+    warm = 1 if args.warmup > 0 else 0
+    mean_s, _ = run_cpu(batch, steps, warm)
+    val = M / mean_s
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "masked_frames_per_sec", "value": val, "unit": "masked frames/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": mean_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, **{k: CFG[k] for k in ("lines", "frames", "K", "D", "Dh", "V", "p")},
+                       "note": "reference path restated on torch CPU ops (oracle port); rank 0 only, N ranks do not add CPU work"},
+            "cpu_baseline": {"value": val, "unit": "masked frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} full-size steps of one 64-line batch after {warm} warm-up"},
+            "e2e": {"value": val, "unit": "masked frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class DeviceStep:
+    """The step on device-resident inputs through the tensor-level wrappers of the C ABI."""
+
+    def __init__(self, batch, dev, dp):
+        from pero_pretraining_b200 import ops
+        self.ops, self.dp, c = ops, dp, CFG
+        self.x = batch["x"].to(dev).view(c["lines"], c["D"], c["frames"])
+        self.gq = batch["gq"].to(dev).view(c["lines"], c["D"], c["frames"])
+        self.h = batch["h"].to(dev).view(-1, c["Dh"])
+        self.W, self.b = batch["W"].to(dev), batch["b"].to(dev)
+        self.weight = batch["weight"].to(dev)
+        self.ema_w = self.weight.clone()
+        self.cs = torch.ones(c["K"], device=dev)
+        rows = np.flatnonzero(batch["mask"].reshape(-1) == 1).astype(np.int32)
+        self.M = int(rows.size)
+        self.rows = torch.from_numpy(rows).to(dev)
+        self.cb = ops.PreparedCodebook(c["K"], c["D"], dev).prepare(self.weight)
+        self.head = ops.PreparedHead(c["V"], c["Dh"], dev)
+        self.m_global = float(self.M)
+        if dp:
+            t = torch.tensor([float(self.M)], device=dev)
+            torch.distributed.all_reduce(t)
+            self.m_global = float(t.item())
+        self.out = {}
+
+    def __call__(self):
+        ops, c = self.ops, CFG
+        idx, _, x_rows = ops.vq_assign(self.x, self.cb, c["lines"], c["frames"], True, want_rows=True)
+        q = ops.vq_gather_st(x_rows, idx, self.weight, c["lines"], c["frames"], True)
+        sums = ops.vq_ema_accumulate(x_rows, idx, c["K"])
+        if self.dp:
+            torch.distributed.all_reduce(sums)
+        ops.vq_ema_apply(sums, self.ema_w, self.cs, self.weight, c["decay"], c["epsilon"], self.cb)
+        loss_c = ops.mse_fwd(q, self.x, 0.0, c["commitment_cost"])
+        g_x = ops.vq_st_commit_bwd(self.gq, q, self.x, 2.0 * c["commitment_cost"] / q.numel())
+        self.head.prepare(self.W, self.b)            # head weights change every optimizer step in training
+        loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head)
+        if self.dp:
+            torch.distributed.all_reduce(loss_sum)
+        d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
+                                                return_flat=True)
+        if self.dp:
+            torch.distributed.all_reduce(flat)       # d_W | d_b in one call
+        self.out = dict(idx=idx, q=q, loss_c=loss_c, g_x=g_x, loss_sum=loss_sum, d_h=d_h, d_W=d_W, d_b=d_b)
+        return self.out
+
+
+def count_kernels(fn):
+    """Kernels launched by one step (CUPTI via torch.profiler); -1 when the profiler is unavailable."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if getattr(e, "device_type", None) is not None and "cuda" in str(e.device_type).lower()]
+        ours = [n for n in names if "pero" in n or "cub" in n.lower()]
+        return len(names), len(ours)
+    except Exception:
+        return -1, -1
+
+
+def e2e_leg(batch, dev, dp, steps, warm):
+    """Public module API, host inputs: per step H2D of x / h / mask rows, D2H of the loss."""
+    from pero_pretraining_b200 import LinearHead, VectorQuantizer
+    c = CFG
+    vq = VectorQuantizer(c["K"], c["D"], c["commitment_cost"], c["decay"], c["epsilon"]).to(dev).train()
+    head = LinearHead(c["Dh"], c["V"]).to(dev)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(batch["weight"]); vq.ema_w.copy_(batch["weight"]); vq.ema_cluster_size.fill_(1.0)
+        head.linear.weight.copy_(batch["W"]); head.linear.bias.copy_(batch["b"])
+    group = torch.distributed.group.WORLD if dp else None
+    if dp:
+        vq.enable_data_parallel(group)
+    x_host, h_host = batch["x"].pin_memory(), batch["h"].pin_memory()
+    gq = batch["gq"].to(dev)
+    mask = batch["mask"]
+    h2d = x_host.numel() * 4 + h_host.numel() * 4 + int(mask.sum()) * 4
+    loss_val = None
+
+    def step():
+        x = x_host.to(dev, non_blocking=True).requires_grad_(True)
+        h = h_host.to(dev, non_blocking=True).requires_grad_(True)
+        q, idx = vq(x)
+        loss = vq.calculate_loss(q, x) + head.masked_loss(h, idx.view(c["lines"], c["frames"]), mask, None, group)
+        head.linear.weight.grad = None
+        head.linear.bias.grad = None
+        torch.autograd.backward([loss, q], [None, gq])
+        return float(loss.item())                      # D2H read of the step's result
+
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if dp:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss_val = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dp:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dt = float(t.item())
+    return dt / steps, h2d, 4, loss_val
+
+
+def gemm_roofline_leg(ds, dev, iters, flush):
+    """The dominant kernel alone: distance GEMM + arg-min on prepared bf16 frames, CUDA events around each
+    launch on the launching stream, L2 flushed between launches."""
+    from pero_pretraining_b200 import _lib
+    c = CFG
+    L = _lib.lib()
+    N = c["lines"] * c["frames"]
+    xb = ds.x.permute(0, 2, 1).reshape(N, c["D"]).contiguous().bfloat16()
+    packed = torch.empty(N, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ts = []
+    for i in range(iters + 3):
+        L.pero_vq_packed_init(packed.data_ptr(), N, stream)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = L.pero_vq_assign_bf16(xb.data_ptr(), N, c["K"], c["D"], ds.cb.blob.data_ptr(), 0, packed.data_ptr(), stream)
+        e1.record()
+        _lib.check(rc, "pero_vq_assign_bf16")
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    return float(np.mean(ts)), float(np.min(ts))
+
+
+def our_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dp = world > 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if dp:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    from pero_pretraining_b200 import ops
+    ops.require_device()
+    c = CFG
+    batch = make_batch(rank)
+    ds = DeviceStep(batch, dev, dp)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    # ---- warm-up (eager), kernel count, optional CUDA graph
+    for _ in range(max(3, args.warmup)):
+        ds()
+    torch.cuda.synchronize()
+    n_kernels, n_ours = count_kernels(ds)
+    graph = None
+    if not args.no_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                ds()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                ds()
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:          # noqa: BLE001 — fall back to eager launches, say so in the config
+            graph = None
+            sys.stderr.write(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); eager launches\n")
+            torch.cuda.synchronize()
+    run = graph.replay if graph is not None else ds
+    for _ in range(args.warmup):
+        run()
+
+    # ---- timed region: K steps, device time per step, L2 flushed between steps, max over ranks
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    if dp:
+        torch.distributed.barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record()
+        run()
+        e1.record()
+    torch.cuda.synchronize()
+    if dp:
+        torch.distributed.barrier()
+    clocks = sampler.stop()
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    m_total = ds.m_global
+    if dp:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = m_total / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel, e2e, CPU baseline
+    N = c["lines"] * c["frames"]
+    gemm_ms, gemm_min = gemm_roofline_leg(ds, dev, 20, flush)
+    burst, sustained, hbm, src = peaks()
+    flops = 2.0 * N * c["K"] * c["D"]
+    achieved = flops / (gemm_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_tn_kernel<2,true,ArgminEpi> (distance GEMM + arg-min)",
+                "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+                "peak_source": f"{src} bf16 burst (kernel timed alone)", "kernel_us": gemm_ms * 1e3, "kernel_us_min": gemm_min * 1e3,
+                "algorithmic_flops_per_launch": flops,
+                "step_tensor_tflops": (flops + 6.0 * ds.M * c["Dh"] * c["V"]) / (ms_per_step * 1e-3) / 1e12,
+                "step_frac_of_sustained": (flops + 6.0 * ds.M * c["Dh"] * c["V"]) / (ms_per_step * 1e-3) / 1e12 / sustained}
+    e2e = None
+    if not args.skip_e2e:
+        s_per_step, h2d, d2h, _ = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup))
+        e2e = {"value": m_total / s_per_step, "unit": "masked frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": s_per_step * 1e3, "api": "VectorQuantizer.forward/calculate_loss + LinearHead.masked_loss + backward"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        mean_s, min_s = run_cpu(make_batch(0), 3, 1)
+        cpu = {"value": ds.M / mean_s, "unit": "masked frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "3 full-size steps of one 64-line batch after 1 warm-up", "ms_per_step": mean_s * 1e3}
+
+    if rank == 0:
+        line = {"metric": "masked_frames_per_sec", "value": value, "unit": "masked frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, **{k: c[k] for k in ("lines", "frames", "K", "D", "Dh", "V", "p")},
+                           "masked_frames_per_step": m_total, "frames_per_step": N * world, "parallelism": f"dp{world}" if dp else "single",
+                           "l2": "flushed (256 MiB write) between timed steps", "launch": "cuda_graph" if graph is not None else "eager"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": (n_ours if n_ours > 0 else n_kernels) * args.steps, "kernels_per_step": n_kernels, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if dp:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        our_arm(a)

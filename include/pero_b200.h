@@ -72,6 +72,10 @@ int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int
                    int64_t D, const void* codebook, int64_t index_offset, int64_t* idx, float* dmin,
                    int64_t* packed_io, float* x_rows, void* workspace, size_t workspace_bytes,
                    pero_stream_t stream);
+/* The distance GEMM + arg-min alone, for callers that already hold the frames as bf16 rows
+ * [N, Dp] (Dp = D rounded up to 64, zero padded): min-merges into packed_io (see above). */
+int pero_vq_assign_bf16(const void* x_bf16, int64_t N, int64_t K, int64_t D, const void* codebook, int64_t index_offset,
+                        int64_t* packed_io, pero_stream_t stream);
 int pero_vq_packed_init(int64_t* packed, int64_t N, pero_stream_t stream);
 int pero_vq_unpack(const int64_t* packed, int64_t N, int64_t* idx, float* dmin, pero_stream_t stream);
 
@@ -116,6 +120,12 @@ int pero_mse_fwd(const float* a, const float* b, int64_t numel, float scale_a, f
                  void* workspace, size_t workspace_bytes, pero_stream_t stream);
 int pero_mse_bwd(const float* a, const float* b, int64_t numel, float coef, const float* grad_out, float* g_a,
                  float* g_b, pero_stream_t stream);
+/* Backward of VectorQuantizer.forward + calculate_loss(quantized, inputs) in one pass
+ * (models/autoencoders.py:239 straight-through, :198 commitment term):
+ *   g_inputs = g_quantized + coef * grad_loss[0] * (inputs - quantized),  coef = 2 * commitment_cost / numel.
+ * All tensors share one layout (the NCHW layout of the module's input/output). */
+int pero_vq_st_commit_bwd(const float* g_quantized, const float* quantized, const float* inputs, int64_t numel, float coef,
+                          const float* grad_loss, float* g_inputs, pero_stream_t stream);
 
 /* ------------------------------------------------------------------ masked-label cross-entropy
  * Replaces  masked_pretraining/model.py:104-105 (LinearHead) + :78-82 (MaskedCrossEntropyLoss):

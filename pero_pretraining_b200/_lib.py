@@ -28,6 +28,7 @@ SIGNATURES = {
     "pero_vq_assign_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pero_vq_assign": (c_int, [c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                c_vp, c_sz, c_vp]),
+    "pero_vq_assign_bf16": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "pero_vq_packed_init": (c_int, [c_vp, c_i64, c_vp]),
     "pero_vq_unpack": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "pero_vq_gather_st": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_vp]),
@@ -39,6 +40,7 @@ SIGNATURES = {
     "pero_mse_workspace_bytes": (c_sz, [c_i64]),
     "pero_mse_fwd": (c_int, [c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_sz, c_vp]),
     "pero_mse_bwd": (c_int, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "pero_vq_st_commit_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "pero_head_bytes": (c_sz, [c_i64, c_i64]),
     "pero_head_prepare": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
     "pero_masked_ce_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_i64]),

@@ -68,7 +68,7 @@ class _WeightedMse(torch.autograd.Function):
         numel = t.numel()
         g_t = g_f = None
         if ctx.needs_input_grad[0] and w_t != 0.0:
-            g_t, _ = ops.mse_bwd(t, f, -2.0 * w_t / numel, g, want_a=False, want_b=True)   # w_t*2/n*(t - f)
+            _, g_t = ops.mse_bwd(t, f, -2.0 * w_t / numel, g, want_a=False, want_b=True)   # w_t*2/n*(t - f)
             g_t = g_t.to(ctx.dtypes[0])
         if ctx.needs_input_grad[1] and w_f != 0.0:
             _, g_f = ops.mse_bwd(t, f, 2.0 * w_f / numel, g, want_a=False, want_b=True)    # w_f*2/n*(f - t)

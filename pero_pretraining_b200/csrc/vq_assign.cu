@@ -217,6 +217,18 @@ int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int
     return PERO_OK;
 }
 
+int pero_vq_assign_bf16(const void* x_bf16, int64_t N, int64_t K, int64_t D, const void* codebook, int64_t index_offset,
+                        int64_t* packed_io, pero_stream_t stream) {
+    if (N == 0) return PERO_OK;
+    if (!x_bf16 || !codebook || !packed_io) return PERO_ERR_NULL;
+    if (N < 0 || K <= 0 || D <= 0 || N > (1ll << 31) - 256 || K + index_offset > (1ll << 31) - 1 || index_offset < 0)
+        return PERO_ERR_BAD_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(x_bf16) & 15) || (reinterpret_cast<uintptr_t>(codebook) & 255)) return PERO_ERR_BAD_ALIGN;
+    const CodebookLayout cl = codebook_layout(K, D);
+    return run_assign_gemm(static_cast<const __nv_bfloat16*>(x_bf16), N, (int)cl.Dp, cl, codebook, K, (int)index_offset,
+                           reinterpret_cast<long long*>(packed_io), (cudaStream_t)stream);
+}
+
 int pero_debug_gemm_tn(const void* a_bf16, int64_t rows_a, const void* b_bf16, int64_t rows_b, int64_t kd,
                        int variant, int num_splits, float* out, pero_stream_t stream) {
     if (!a_bf16 || !b_bf16 || !out) return PERO_ERR_NULL;

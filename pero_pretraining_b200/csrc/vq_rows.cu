@@ -121,6 +121,31 @@ mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long lo
     }
 }
 
+// Backward of quantize + commitment loss in one pass: the straight-through estimator passes
+// g_quantized unchanged and the commitment term adds coef * g_loss * (inputs - quantized).
+__global__ void __launch_bounds__(256)
+st_commit_bwd_kernel(const float* __restrict__ gq, const float* __restrict__ q, const float* __restrict__ x, long long numel,
+                     float coef, const float* __restrict__ grad_loss, float* __restrict__ gx) {
+    const float c = coef * (grad_loss ? __ldg(grad_loss) : 1.0f);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(gq) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(x) |
+                       reinterpret_cast<uintptr_t>(gx)) & 15) == 0;
+    if (vec) {
+        const long long n4 = numel >> 2;
+        for (long long i = t0; i < n4; i += stride) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gq) + i);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(q) + i);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(x) + i);
+            reinterpret_cast<float4*>(gx)[i] = make_float4(g.x + c * (b.x - a.x), g.y + c * (b.y - a.y),
+                                                          g.z + c * (b.z - a.z), g.w + c * (b.w - a.w));
+        }
+        for (long long i = (n4 << 2) + t0; i < numel; i += stride) gx[i] = gq[i] + c * (x[i] - q[i]);
+    } else {
+        for (long long i = t0; i < numel; i += stride) gx[i] = gq[i] + c * (x[i] - q[i]);
+    }
+}
+
 __global__ void counts_kernel(const long long* __restrict__ idx, long long N, long long K, unsigned long long* __restrict__ counts) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -183,6 +208,15 @@ int pero_mse_bwd(const float* a, const float* b, int64_t numel, float coef, cons
     if (!a || !b || (!g_a && !g_b)) return PERO_ERR_NULL;
     if (numel <= 0) return PERO_ERR_BAD_SHAPE;
     mse_bwd_kernel<<<grid_for(numel, 256 * 4, 148 * 16), 256, 0, stream>>>(a, b, numel, coef, grad_out, g_a, g_b);
+    return (int)cudaGetLastError();
+}
+
+int pero_vq_st_commit_bwd(const float* g_quantized, const float* quantized, const float* inputs, int64_t numel, float coef,
+                          const float* grad_loss, float* g_inputs, pero_stream_t stream) {
+    if (!g_quantized || !quantized || !inputs || !g_inputs) return PERO_ERR_NULL;
+    if (numel <= 0) return PERO_ERR_BAD_SHAPE;
+    st_commit_bwd_kernel<<<grid_for(numel, 256 * 4, 148 * 16), 256, 0, stream>>>(g_quantized, quantized, inputs, numel, coef,
+                                                                               grad_loss, g_inputs);
     return (int)cudaGetLastError();
 }
 

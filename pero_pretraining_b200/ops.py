@@ -159,6 +159,16 @@ def mse_bwd(a, b, coef, grad_out, want_a, want_b):
     return g_a, g_b
 
 
+def vq_st_commit_bwd(g_quantized, quantized, inputs, coef, grad_loss=None):
+    """g_inputs = g_quantized + coef * grad_loss * (inputs - quantized) (same layout for all tensors)."""
+    gq, q, x = _f32c(g_quantized, "g_quantized"), _f32c(quantized, "quantized"), _f32c(inputs, "inputs")
+    out = torch.empty_like(x)
+    gl = None if grad_loss is None else _f32c(grad_loss, "grad_loss")
+    check(_lib.lib().pero_vq_st_commit_bwd(gq.data_ptr(), q.data_ptr(), x.data_ptr(), x.numel(), float(coef), _p(gl),
+                                           out.data_ptr(), _stream()), "pero_vq_st_commit_bwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------------ masked CE
 class PreparedHead:
     """Device blob with bf16 W, bf16 W^T and the bias of a Linear(Dh -> V) head."""
@@ -198,15 +208,16 @@ def masked_ce_fwd(h, rows, labels, head):
     return loss_sum, lse, ws
 
 
-def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None):
-    """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32)."""
+def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False):
+    """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32[, flat buffer holding d_W|d_b])."""
     L = _lib.lib()
     h = _check_h(h)
     N, Dh = h.shape
     M = rows.numel()
     d_h = torch.empty_like(h) if want_dh else None
-    d_W = torch.empty(head.V, Dh, dtype=torch.float32, device=h.device)
-    d_b = torch.empty(head.V, dtype=torch.float32, device=h.device)
+    # d_W and d_b share one flat buffer so that data-parallel ranks all-reduce them in a single call
+    flat = torch.empty(head.V * Dh + head.V, dtype=torch.float32, device=h.device)
+    d_W, d_b = flat[:head.V * Dh].view(head.V, Dh), flat[head.V * Dh:]
     wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
     if ws is None or ws.numel() < wsb:
         ws = _ws(wsb, h.device)
@@ -215,7 +226,7 @@ def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=Tru
                                labels.data_ptr(), head.blob.data_ptr(), head.V, lse.data_ptr(), _p(gs),
                                float(inv_count), _p(d_h), d_W.data_ptr(), d_b.data_ptr(), ws.data_ptr(), wsb,
                                _stream()), "pero_masked_ce_bwd")
-    return d_h, d_W, d_b
+    return (d_h, d_W, d_b, flat) if return_flat else (d_h, d_W, d_b)
 
 
 _MASK_DTYPES = {torch.int64: 0, torch.int32: 1, torch.uint8: 2, torch.bool: 2}
