@@ -1,20 +1,43 @@
-// Epilogue policies for gemm_core.cuh.  Each epilogue thread owns ONE accumulator row and walks the
-// 256 columns of a tile 32 at a time (tcgen05.ld 32x32b.x32).
+// Epilogue policies for gemm_core.cuh.  Each epilogue thread owns ONE accumulator row and walks its
+// half tile (128 columns) 32 columns at a time (tcgen05.ld 32x32b.x32); the TMEM load of chunk c+1 is in
+// flight while chunk c is processed.  Per-column vectors (|c|^2, bias) are read from the shared-memory
+// copy the core stages one tile ahead (TileCtx::cv), as 16-byte broadcast loads.
 #pragma once
 #include "gemm_core.cuh"
 #include <math_constants.h>
 
 namespace pero {
 
+constexpr int kChunks = kHalfN / 32;   // 4
+
+// Runs body(c, r) for the 4 chunks of a half tile with the next chunk's TMEM load already issued.
+template <class Body>
+__device__ __forceinline__ void for_each_chunk(uint32_t taddr, Body&& body) {
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32(taddr, r0);
+    tmem_ld_wait_on(r0);
+#pragma unroll
+    for (int c = 0; c < kChunks; c += 2) {
+        tmem_ld_32x32(taddr + (c + 1) * 32, r1);
+        body(c, r0);
+        tmem_ld_wait_on(r1);
+        if (c + 2 < kChunks) tmem_ld_32x32(taddr + (c + 2) * 32, r0);
+        body(c + 1, r1);
+        if (c + 2 < kChunks) tmem_ld_wait_on(r0);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Nearest codeword: d[row, col] = |c_col|^2 - 2 * <x_row, c_col>  (|x_row|^2 is constant along the
 // row and cannot change the arg-min; reference: models/autoencoders.py:212-217).  The running
 // (min, argmin) stays in registers across the column sweep; strict '<' in ascending column order keeps
-// torch.argmin's first-index-on-ties rule.  Results of different workers on the same row are merged
-// with one signed 64-bit atomicMin on (order_key(d) << 32 | index): min distance first, then lowest index.
+// torch.argmin's first-index-on-ties rule.  Results of different workers / column halves on the same row
+// are merged with one signed 64-bit atomicMin on (order_key(d) << 32 | index): min distance first, then
+// lowest index.
 struct ArgminEpi {
+    static constexpr bool kColVec = true;
     struct Params {
-        const float* cnorm;            // [num_ct * 256] |c|^2 in fp32, +inf beyond the last codeword
+        const float* colvec;           // |c|^2 in fp32 [num_ct * 256], +inf beyond the last codeword
         long long* packed;             // [rows] pre-set to kPackedEmpty
         int rows;
         int index_offset;              // global index of this shard's codeword 0
@@ -24,40 +47,46 @@ struct ArgminEpi {
     static __device__ __forceinline__ void begin_rb(State& st, const Params&, const TileCtx&) {
         st.best = CUDART_INF_F; st.besti = 0;
     }
-    static __device__ __forceinline__ void tile(State& st, const Params& ep, const TileCtx& cx, uint32_t taddr) {
-        float tb = CUDART_INF_F; int tj = 0;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c * 32, r);
-            const float4* cn = reinterpret_cast<const float4*>(ep.cnorm + cx.col0 + c * 32);
-            float4 n[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) n[i] = __ldg(cn + i);
-            tmem_ld_wait();
+    // 32 columns: d = |c|^2 - 2 acc, minimum by an FMNMX3 tree; only when some lane of the warp beats its
+    // running minimum (rare once the first tiles are done) the scalar search for the first minimal column
+    // runs.  One warp-uniform branch per 32 columns.
+    static __device__ __forceinline__ void tile(State& st, const Params&, const TileCtx& cx, uint32_t taddr) {
+        const float4* cv = reinterpret_cast<const float4*>(cx.cv);
+        for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
+            float d[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float nn[4] = {n[i].x, n[i].y, n[i].z, n[i].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float d = fmaf(__uint_as_float(r[i * 4 + e]), -2.0f, nn[e]);
-                    if (d < tb) { tb = d; tj = c * 32 + i * 4 + e; }
-                }
+                const float4 nn = cv[c * 8 + i];
+                d[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), -2.0f, nn.x);
+                d[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), -2.0f, nn.y);
+                d[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), -2.0f, nn.z);
+                d[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), -2.0f, nn.w);
             }
-        }
-        if (tb < st.best) { st.best = tb; st.besti = cx.col0 + tj; }
+            float m8[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                m8[g] = fminf(fminf(fminf(d[8 * g], d[8 * g + 1]), fminf(d[8 * g + 2], d[8 * g + 3])),
+                              fminf(fminf(d[8 * g + 4], d[8 * g + 5]), fminf(d[8 * g + 6], d[8 * g + 7])));
+            const float m = fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3]));
+            const bool better = m < st.best;       // strict '<': a later equal value never replaces an earlier one
+            if (__any_sync(0xffffffffu, better)) {
+                int j = 31;
+#pragma unroll
+                for (int e = 30; e >= 0; --e) j = (d[e] == m) ? e : j;
+                if (better) { st.best = m; st.besti = cx.col0 + c * 32 + j; }
+            }
+        });
     }
     static __device__ __forceinline__ void end_rb(State& st, const Params& ep, const TileCtx& cx) {
-        if (cx.row < ep.rows) {
-            atomicMin(ep.packed + cx.row, pack_dist_index(st.best, st.besti + ep.index_offset));
-        }
+        if (cx.row < ep.rows) atomicMin(ep.packed + cx.row, pack_dist_index(st.best, st.besti + ep.index_offset));
     }
 };
 
 // ------------------------------------------------------------------------------------------------
 // Plain fp32 store C[row, col] (one plane per contraction split).  128 contiguous bytes per thread per
-// step, so every 32-byte sector written is full.
+// chunk, so every 32-byte sector written is full.
 struct StoreEpi {
+    static constexpr bool kColVec = false;
     struct Params {
         float* out;
         long long ld;             // elements between output rows
@@ -71,12 +100,8 @@ struct StoreEpi {
         const bool row_ok = cx.row < ep.rows;
         const bool vec_ok = ((ep.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
                             ((ep.split_stride & 3) == 0);
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c * 32, r);
-            tmem_ld_wait();
-            if (!row_ok) continue;
+        for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
+            if (!row_ok) return;
             const int col = cx.col0 + c * 32;
             if (vec_ok && col + 32 <= ep.cols) {
 #pragma unroll
@@ -89,9 +114,36 @@ struct StoreEpi {
                 for (int j = 0; j < 32; ++j)
                     if (col + j < ep.cols) dst[c * 32 + j] = __uint_as_float(r[j]);
             }
-        }
+        });
     }
     static __device__ __forceinline__ void end_rb(State&, const Params&, const TileCtx&) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// Measurement-only epilogues (pero_debug_gemm_tn): NullEpi never touches TMEM (MMA + TMA ceiling),
+// LoadEpi only streams the accumulator out of TMEM (adds the tcgen05.ld cost).
+struct NullEpi {
+    static constexpr bool kColVec = false;
+    struct Params { float* out; };
+    struct State {};
+    static __device__ __forceinline__ void begin_rb(State&, const Params&, const TileCtx&) {}
+    static __device__ __forceinline__ void tile(State&, const Params&, const TileCtx&, uint32_t) {}
+    static __device__ __forceinline__ void end_rb(State&, const Params&, const TileCtx&) {}
+};
+struct LoadEpi {
+    static constexpr bool kColVec = false;
+    struct Params { float* out; };
+    struct State { uint32_t acc; };
+    static __device__ __forceinline__ void begin_rb(State& st, const Params&, const TileCtx&) { st.acc = 0; }
+    static __device__ __forceinline__ void tile(State& st, const Params&, const TileCtx&, uint32_t taddr) {
+        for_each_chunk(taddr, [&](int, const uint32_t (&r)[32]) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) st.acc ^= r[j];
+        });
+    }
+    static __device__ __forceinline__ void end_rb(State& st, const Params& ep, const TileCtx& cx) {
+        if (st.acc == 0x12345678u) ep.out[cx.row] = 1.f;      // keeps the loads alive
+    }
 };
 
 }  // namespace pero

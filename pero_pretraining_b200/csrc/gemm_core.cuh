@@ -8,19 +8,24 @@
 // 128 (256) rows of A at a time and sweeps 256-wide column tiles of B.  fp32 accumulators live in TMEM,
 // double-buffered across all 512 columns, so the epilogue of tile t overlaps the MMAs of tile t+1.
 //
-//   warp 0      TMA producer (one elected lane)
-//   warp 1      MMA issuer   (one elected lane, leader CTA only)
-//   warp 2      TMEM allocator
-//   warps 4..7  epilogue: thread <-> accumulator row, tcgen05.ld 32 columns at a time
+//   warps 0..7  epilogue: thread <-> accumulator row, tcgen05.ld 32 columns at a time.  Two warps per SM
+//               sub-partition: warps 0..3 reduce columns 0..127 of a tile, warps 4..7 columns 128..255,
+//               so each scheduler always has a second warp to issue from while one waits on TMEM.
+//               A per-column vector (|c|^2 or the bias) is staged through shared memory one tile ahead.
+//   warp 8      TMA producer (one elected lane)
+//   warp 9      MMA issuer   (one elected lane, leader CTA only)
+//   warp 10     barrier init + TMEM allocator
+//   The single-lane roles sit at the HIGHEST warp ids on purpose: the warp scheduler prefers the highest
+//   eligible warp id, and a producer / MMA issuer that loses issue slots to ALU-heavy epilogue warps
+//   stalls the tensor pipe (measured: 2400 instead of 2048 cycles per 256-deep tile).
 //
 // With kAResident the A row block is loaded ONCE per row block into its own k-block slots and only B
-// streams through the stage ring (8192/256 = 32 B/cycle/SM of L2 traffic in pair mode instead of 96);
-// otherwise A and B k-blocks share the ring (long contractions: dW, dh).
+// streams through the stage ring; otherwise A and B k-blocks share the ring (long contractions: dW, dh).
 //
-// The epilogue is a policy class (see epilogues in vq_assign.cu / masked_ce.cu):
-//   struct Epi { struct Params; struct State;
+// The epilogue is a policy class (see epilogues.cuh / masked_ce.cu):
+//   struct Epi { static constexpr bool kColVec; struct Params; struct State;
 //     static __device__ void begin_rb(State&, const Params&, const TileCtx&);
-//     static __device__ void tile    (State&, const Params&, const TileCtx&, uint32_t taddr);
+//     static __device__ void tile    (State&, const Params&, const TileCtx&, uint32_t taddr);   // 128 columns
 //     static __device__ void end_rb  (State&, const Params&, const TileCtx&); };
 // Row-reducing epilogues (arg-min, log-sum-exp) keep their running state in registers across the
 // column sweep, so the rows x columns matrix never reaches HBM.
@@ -35,7 +40,9 @@ constexpr int kBlockK = 64;         // bf16 elements per k-block = one 128-byte 
 constexpr int kUmmaK = 16;
 constexpr int kMaxStages = 8;
 constexpr int kMaxAKb = 12;         // resident A: up to 12 k-blocks (Kd <= 768)
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;
+constexpr int kHalfN = kBlockN / 2; // columns per epilogue warp group
+constexpr int kEpiThreads = 256;
 constexpr int kABlockBytes = kBlockM * kBlockK * 2;   // 16 KiB
 
 struct GemmShape {
@@ -49,12 +56,15 @@ struct GemmShape {
     int split_mode;    // 0: balanced contiguous unit ranges; 1: worker = rb * fixed_s + s
     int fixed_s;
     int num_stages;    // ring depth chosen by the host from the shared-memory budget
+    unsigned long long* timeline;   // debug: per-unit clock64 stamps of worker 0 ([unit][8]); NULL in production
 };
 
 struct TileCtx {
     int rb, ct, ks;     // row block, column tile, contraction split
     int row;            // global output row owned by this thread
-    int col0;           // first global output column of this tile
+    int col0;           // first global output column of this thread's half tile (128 columns)
+    int half;           // 0: columns 0..127 of the tile, 1: columns 128..255
+    const float* cv;    // shared-memory copy of Params::colvec[col0 .. col0 + 128) (when Epi::kColVec)
     int worker;         // CTA (or pair) index
     int cta_rank;       // rank inside the pair
     int num_workers;
@@ -64,7 +74,7 @@ __host__ __device__ inline size_t gemm_smem_bytes(int cta_group, bool a_resident
     const size_t b_bytes = (size_t)(kBlockN / cta_group) * kBlockK * 2;
     const size_t stage = b_bytes + (a_resident ? 0 : kABlockBytes);
     const size_t a_res = a_resident ? (size_t)num_kb * kABlockBytes : 0;
-    return 1024 /*align slack*/ + a_res + stage * stages + 1024 /*barriers*/;
+    return 1024 /*align slack*/ + a_res + stage * stages + 1024 /*barriers*/ + 2 * kBlockN * 4 /*column vector x2*/;
 }
 
 __device__ __forceinline__ void unit_range(const GemmShape& sh, int worker, int num_workers, int& u0, int& u1) {
@@ -81,12 +91,46 @@ __device__ __forceinline__ void unit_range(const GemmShape& sh, int worker, int 
     }
 }
 
+// Walks the units [u0, u1) of one worker in (row block, column tile, contraction split) order without
+// a division per unit.
+struct UnitIter {
+    int u, u1, rb, ct, ks, num_ct, num_ks;
+    __device__ __forceinline__ UnitIter(const GemmShape& sh, int u0, int u1_)
+        : u(u0), u1(u1_), num_ct(sh.num_ct), num_ks(sh.num_ks) {
+        const int per_rb = num_ct * num_ks;
+        rb = u0 / per_rb;
+        const int rem = u0 - rb * per_rb;
+        ct = rem / num_ks;
+        ks = rem - ct * num_ks;
+    }
+    __device__ __forceinline__ bool valid() const { return u < u1; }
+    __device__ __forceinline__ bool last_of_rb() const { return (u + 1 == u1) || (ks + 1 == num_ks && ct + 1 == num_ct); }
+    __device__ __forceinline__ int next_ct() const { return (ks + 1 < num_ks) ? ct : ((ct + 1 == num_ct) ? 0 : ct + 1); }
+    __device__ __forceinline__ void next() {
+        ++u;
+        if (++ks == num_ks) { ks = 0; if (++ct == num_ct) { ct = 0; ++rb; } }
+    }
+};
+
+__device__ __forceinline__ void stamp(const GemmShape& sh, bool on, int unit, int slot) {
+    if (on) sh.timeline[unit * 8 + slot] = clock64();
+}
+// debug: per-CTA wall-clock (ns) stamps after the per-unit area: [4096 + cta * 4 + slot]
+__device__ __forceinline__ void stamp_cta(const GemmShape& sh, bool on, int slot) {
+    if (on && sh.timeline) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        sh.timeline[4096 + blockIdx.x * 4 + slot] = t;
+    }
+}
+
 template <int kCtaGroup, bool kAResident, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmShape sh, const typename Epi::Params ep) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    stamp_cta(sh, threadIdx.x == 0, 0);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -110,44 +154,45 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     auto tfull_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 2 * kMaxAKb + b); };
     auto tempty_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 2 * kMaxAKb + 2 + b); };
     const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 2 * kMaxAKb + 4);
+    float* const cv_smem = reinterpret_cast<float*>(smem_raw + (bars + 1024u - smem_u32(smem_raw)));   // [2][256]
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == 10 && lane == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), kCtaGroup); mbar_init(empty_bar(s), 1); }
         for (int k = 0; k < kMaxAKb; ++k) { mbar_init(afull_bar(k), kCtaGroup); mbar_init(aempty_bar(k), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128 * kCtaGroup); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiThreads * kCtaGroup); }
         fence_mbar_init();
     }
     if constexpr (kCtaGroup == 2) cluster_sync_all();   // peer barriers must exist before remote arrives
-    if (warp == 2) tmem_alloc<kCtaGroup>(tmem_slot, 512);
+    if (warp == 10) tmem_alloc<kCtaGroup>(tmem_slot, 512);
     tc_fence_before();
     if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    stamp_cta(sh, threadIdx.x == 0, 1);
     int u0, u1;
     unit_range(sh, worker, num_workers, u0, u1);
-    const int per_rb = sh.num_ct * sh.num_ks;
+    const bool tl = sh.timeline != nullptr && worker == 0 && cta_rank == 0;
 
-    if (warp == 0) {
+    if (warp == 8) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             int prev_rb = -1, rbi = -1;
-            for (int u = u0; u < u1; ++u) {
-                const int rb = u / per_rb, rem = u - rb * per_rb;
-                const int ct = rem / sh.num_ks, ks = rem - ct * sh.num_ks;
-                const bool new_rb = (rb != prev_rb);
-                if (new_rb) { ++rbi; prev_rb = rb; }
-                const int row0 = (rb * kCtaGroup + (int)cta_rank) * kBlockM;
-                const int brow0 = ct * kBlockN + (int)cta_rank * (int)kBRows;
-                const int kb0 = ks * sh.kb_per_split;
+            for (UnitIter ui(sh, u0, u1); ui.valid(); ui.next()) {
+                const bool new_rb = (ui.rb != prev_rb);
+                if (new_rb) { ++rbi; prev_rb = ui.rb; }
+                const int row0 = (ui.rb * kCtaGroup + (int)cta_rank) * kBlockM;
+                const int brow0 = ui.ct * kBlockN + (int)cta_rank * (int)kBRows;
+                const int kb0 = ui.ks * sh.kb_per_split;
                 const int kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    if (kb == kb0) stamp(sh, tl, ui.u - u0, 6);
                     if (kAResident && new_rb) {
                         mbar_wait(aempty_bar(kb), (rbi & 1) ^ 1);
                         if constexpr (kCtaGroup == 1) {
@@ -172,6 +217,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         tma_load_2d_pair(sbase, &tmap_b, full_bar(stage), kb * kBlockK, brow0);
                     }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
+                    if (kb + 1 == kb1) stamp(sh, tl, ui.u - u0, 7);
                 }
             }
             // Drain: every tcgen05.commit aimed at this CTA's barriers must have landed before the
@@ -183,34 +229,41 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (kAResident && rbi >= 0)
                 for (int kb = 0; kb < sh.num_kb; ++kb) mbar_wait(aempty_bar(kb), rbi & 1);
         }
-    } else if (warp == 1) {
+    } else if (warp == 9) {
         // ------------------------------------------------------------ MMA issuer (leader CTA)
-        if (leader) {
+        // The whole warp walks the loop (uniform control flow) and one elected lane issues.  The full-
+        // barrier probe of the NEXT stage is issued before the MMAs of the current one, so its latency
+        // hides behind the issue instead of adding ~100 cycles per k-block.
+        if (leader && u0 < u1) {
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, kBlockN);
             int stage = 0; uint32_t phase = 0;
             int prev_rb = -1, rbi = -1, it = 0;
-            for (int u = u0; u < u1; ++u, ++it) {
-                const int rb = u / per_rb, rem = u - rb * per_rb;
-                const int ct = rem / sh.num_ks, ks = rem - ct * sh.num_ks;
-                (void)ct;
-                const bool new_rb = (rb != prev_rb);
-                if (new_rb) { ++rbi; prev_rb = rb; }
-                const bool last_of_rb = (u + 1 == u1) || ((u + 1) / per_rb != rb);
-                const int kb0 = ks * sh.kb_per_split;
+            uint32_t ready = 0;
+            for (UnitIter ui(sh, u0, u1); ui.valid(); ui.next(), ++it) {
+                const bool new_rb = (ui.rb != prev_rb);
+                if (new_rb) { ++rbi; prev_rb = ui.rb; }
+                const bool last_of_rb = ui.last_of_rb();
+                const int kb0 = ui.ks * sh.kb_per_split;
                 const int kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
                 const int buf = it & 1;
+                stamp(sh, tl && lane == 0, it, 0);
                 mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
+                stamp(sh, tl && lane == 0, it, 1);
                 const uint32_t tmem_d = tmem_base + buf * kBlockN;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (kAResident && new_rb) mbar_wait(afull_bar(kb), rbi & 1);
-                    mbar_wait(full_bar(stage), phase);
+                    if (!ready) mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t sbase = ring + stage * kStageBytes;
-                        const uint32_t a_addr = kAResident ? (a_res + kb * kABlockBytes) : (sbase + kBBlockBytes);
-                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-                        const uint64_t bdesc = make_kmajor_sw128_desc(sbase);
+                    if (kb == kb0) stamp(sh, tl && lane == 0, it, 2);
+                    int nstage = stage + 1; uint32_t nphase = phase;
+                    if (nstage == stages) { nstage = 0; nphase ^= 1; }
+                    // probe only if another k-block follows: a probe of a phase that never completes would stall
+                    ready = (kb + 1 < kb1 || ui.u + 1 < u1) ? mbar_test_wait(full_bar(nstage), nphase) : 0u;
+                    const uint32_t sbase = ring + stage * kStageBytes;
+                    const uint32_t a_addr = kAResident ? (a_res + kb * kABlockBytes) : (sbase + kBBlockBytes);
+                    const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sbase);
+                    if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                             // +32 B per UMMA_K step inside the 128-byte swizzle row: +2 in the >>4 address field
@@ -218,42 +271,59 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         }
                         umma_commit<kCtaGroup>(empty_bar(stage));
                         if (kAResident && last_of_rb) umma_commit<kCtaGroup>(aempty_bar(kb));
-                        if (kb + 1 == kb1) umma_commit<kCtaGroup>(tfull_bar(buf));
+                        if (kb + 1 == kb1) { umma_commit<kCtaGroup>(tfull_bar(buf)); stamp(sh, tl, it, 3); }
                     }
                     __syncwarp();
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    stage = nstage; phase = nphase;
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 8) {
         // ------------------------------------------------------------ epilogue (both CTAs of a pair)
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int half = warp >> 2;                   // which 128 columns of every tile
+        const int ht = q * 32 + lane;                 // thread index inside its half group
         typename Epi::State st;
         TileCtx cx;
-        cx.worker = worker; cx.cta_rank = (int)cta_rank; cx.num_workers = num_workers;
+        cx.worker = worker; cx.cta_rank = (int)cta_rank; cx.num_workers = num_workers; cx.half = half; cx.cv = nullptr;
+        UnitIter ui(sh, u0, u1);
+        float pre = 0.f;                              // column-vector element of the NEXT tile, loaded a tile ahead
+        if constexpr (Epi::kColVec) {
+            if (ui.valid()) pre = __ldg(ep.colvec + ui.ct * kBlockN + half * kHalfN + ht);
+        }
         int prev_rb = -1, it = 0;
-        for (int u = u0; u < u1; ++u, ++it) {
-            const int rb = u / per_rb, rem = u - rb * per_rb;
-            cx.rb = rb; cx.ct = rem / sh.num_ks; cx.ks = rem - cx.ct * sh.num_ks;
-            cx.row = (rb * kCtaGroup + (int)cta_rank) * kBlockM + q * 32 + lane;
-            cx.col0 = cx.ct * kBlockN;
-            if (rb != prev_rb) { prev_rb = rb; Epi::begin_rb(st, ep, cx); }
-            const bool last_of_rb = (u + 1 == u1) || ((u + 1) / per_rb != rb);
+        for (; ui.valid(); ui.next(), ++it) {
+            cx.rb = ui.rb; cx.ct = ui.ct; cx.ks = ui.ks;
+            cx.row = (ui.rb * kCtaGroup + (int)cta_rank) * kBlockM + q * 32 + lane;
+            cx.col0 = ui.ct * kBlockN + half * kHalfN;
             const int buf = it & 1;
+            if constexpr (Epi::kColVec) {
+                float* dst = cv_smem + buf * kBlockN + half * kHalfN;
+                dst[ht] = pre;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");     // this half group only
+                cx.cv = dst;
+                if (ui.u + 1 < u1) pre = __ldg(ep.colvec + ui.next_ct() * kBlockN + half * kHalfN + ht);
+            }
+            if (ui.rb != prev_rb) { prev_rb = ui.rb; Epi::begin_rb(st, ep, cx); }
+            const bool last_of_rb = ui.last_of_rb();
             mbar_wait(tfull_bar(buf), (it >> 1) & 1);
             tc_fence_after();
-            Epi::tile(st, ep, cx, tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBlockN);
+            stamp(sh, tl && warp == 0 && lane == 0, it, 4);
+            Epi::tile(st, ep, cx, tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBlockN + half * kHalfN);
             tc_fence_before();
             if constexpr (kCtaGroup == 1) mbar_arrive(tempty_bar(buf));
             else mbar_arrive_remote(tempty_bar(buf), 0);
+            stamp(sh, tl && warp == 0 && lane == 0, it, 5);
             if (last_of_rb) Epi::end_rb(st, ep, cx);
         }
+        stamp_cta(sh, threadIdx.x == 0, 2);
     }
 
     // ---------------------------------------------------------------- teardown
     tc_fence_before();
     if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
-    if (warp == 2) tmem_dealloc<kCtaGroup>(tmem_base, 512);
+    if (warp == 10) tmem_dealloc<kCtaGroup>(tmem_base, 512);
+    stamp_cta(sh, threadIdx.x == 0, 3);
 }
 
 }  // namespace pero

@@ -4,6 +4,7 @@
 #pragma once
 #include "gemm_core.cuh"
 #include "errors.h"
+#include <stdlib.h>
 
 namespace pero {
 
@@ -53,6 +54,9 @@ inline int device_sm_count() {
     return sms;
 }
 
+// Debug only (pero_debug_set_timeline): when set, every GEMM launch records worker 0's clock64 stamps there.
+inline unsigned long long* g_debug_timeline = nullptr;
+
 constexpr size_t kSmemBudget = 227 * 1024;
 constexpr size_t kSmemFloor = 120 * 1024;   // > half an SM: never two TMEM-hungry CTAs on one SM
 
@@ -68,9 +72,10 @@ inline int pick_stages(int cta_group, bool a_resident, int num_kb) {
 template <int kCtaGroup, bool kAResident, class Epi>
 int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int rows_b, int pitch_b, int kd,
                    int num_ks, int split_mode, int fixed_s, int workers, const typename Epi::Params& ep,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, unsigned long long* timeline = nullptr) {
     if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
     GemmShape sh;
+    sh.timeline = timeline ? timeline : g_debug_timeline;
     sh.rows_a = rows_a; sh.rows_b = rows_b;
     sh.num_kb = kd / kBlockK;
     sh.num_rb = (rows_a + kBlockM * kCtaGroup - 1) / (kBlockM * kCtaGroup);
@@ -90,7 +95,12 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     if (rc) return rc;
 
     const long long units = (long long)sh.num_rb * sh.num_ct * sh.num_ks;
-    const int max_workers = device_sm_count() / kCtaGroup;
+    int max_workers = device_sm_count() / kCtaGroup;
+    {
+        static int env_cap = -2;       // PERO_GEMM_MAX_CTAS: tuning knob for the co-residency experiments
+        if (env_cap == -2) { const char* e = getenv("PERO_GEMM_MAX_CTAS"); env_cap = e ? atoi(e) : -1; }
+        if (env_cap > 0 && env_cap / kCtaGroup < max_workers) max_workers = env_cap / kCtaGroup;
+    }
     if (split_mode == 1) workers = sh.num_rb * sh.fixed_s;
     else if (workers <= 0 || workers > max_workers) workers = max_workers;
     if (split_mode == 0 && workers > units) workers = (int)units;

@@ -36,7 +36,7 @@ constexpr int kMaxLseSplits = 64;
 
 struct CeWsLayout {
     int64_t Dhp, Vp, Mp64, Mpad, S, KS;
-    size_t a_off, at_off, lab_off, inv_off, p_off, pt_off, pm_off, ps_off, zlab_off, planes_off, total;
+    size_t a_off, at_off, lab_off, inv_off, p_off, pt_off, pm_off, ps_off, zlab_off, rowloss_off, planes_off, total;
 };
 inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     CeWsLayout l;
@@ -60,9 +60,10 @@ inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     l.inv_off = take((size_t)N * 4);
     l.p_off = take((size_t)M * l.Vp * 2);
     l.pt_off = take((size_t)V * l.Mp64 * 2);
-    l.pm_off = take((size_t)S * l.Mpad * 4);
-    l.ps_off = take((size_t)S * l.Mpad * 4);
+    l.pm_off = take((size_t)2 * S * l.Mpad * 4);
+    l.ps_off = take((size_t)2 * S * l.Mpad * 4);
     l.zlab_off = take((size_t)l.Mpad * 4);
+    l.rowloss_off = take((size_t)l.Mpad * 4);
     l.planes_off = take((size_t)KS * M * Dh * 4);
     l.total = off;
     return l;
@@ -141,12 +142,13 @@ ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const lo
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
-// Online log-sum-exp over the label axis; one partial (max, sum) per row and column split.
+// Online log-sum-exp over the label axis; one partial (max, sum) per row, column split and column half.
 struct LseEpi {
+    static constexpr bool kColVec = true;
     struct Params {
-        const float* bias;    // [Vt], -inf beyond V
+        const float* colvec;  // bias [Vt], -inf beyond V
         const int* lab;       // [Mpad]
-        float* pm; float* ps; // [S, Mpad] partial max / sum(exp(z - max))
+        float* pm; float* ps; // [2 * S, Mpad] partial max / sum(exp(z - max))
         float* zlab;          // [Mpad] logit at the label
         int M, Mpad, S;
     };
@@ -155,27 +157,25 @@ struct LseEpi {
         st.m = -CUDART_INF_F; st.s = 0.f; st.zl = 0.f; st.has = false;
         st.label = cx.row < ep.M ? __ldg(ep.lab + cx.row) : -1;
     }
-    static __device__ __forceinline__ void tile(State& st, const Params& ep, const TileCtx& cx, uint32_t taddr) {
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c * 32, r);
+    static __device__ __forceinline__ void tile(State& st, const Params&, const TileCtx& cx, uint32_t taddr) {
+        const float4* cv = reinterpret_cast<const float4*>(cx.cv);
+        for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
             const int col = cx.col0 + c * 32;
-            const float4* bp = reinterpret_cast<const float4*>(ep.bias + col);
-            float4 b[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) b[i] = __ldg(bp + i);
-            tmem_ld_wait();
             float z[32];
-            float cmax = -CUDART_INF_F;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                z[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b[i].x;
-                z[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b[i].y;
-                z[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b[i].z;
-                z[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b[i].w;
-                cmax = fmaxf(cmax, fmaxf(fmaxf(z[4 * i], z[4 * i + 1]), fmaxf(z[4 * i + 2], z[4 * i + 3])));
+                const float4 b = cv[c * 8 + i];
+                z[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + b.x;
+                z[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b.y;
+                z[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b.z;
+                z[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b.w;
             }
+            float m8[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                m8[g] = fmaxf(fmaxf(fmaxf(z[8 * g], z[8 * g + 1]), fmaxf(z[8 * g + 2], z[8 * g + 3])),
+                              fmaxf(fmaxf(z[8 * g + 4], z[8 * g + 5]), fmaxf(z[8 * g + 6], z[8 * g + 7])));
+            const float cmax = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
             const unsigned rel = (unsigned)(st.label - col);
             if (rel < 32u) {
 #pragma unroll
@@ -185,26 +185,35 @@ struct LseEpi {
             if (cmax > -CUDART_INF_F) {
                 const float mn = fmaxf(st.m, cmax);
                 const float mn2 = mn * kLog2e;
-                float acc = 0.f;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(z[j], kLog2e, -mn2));
-                st.s = st.s * exp2f((st.m - mn) * kLog2e) + acc;
+                for (int j = 0; j < 32; j += 4) {
+                    a0 += exp2f(fmaf(z[j + 0], kLog2e, -mn2));
+                    a1 += exp2f(fmaf(z[j + 1], kLog2e, -mn2));
+                    a2 += exp2f(fmaf(z[j + 2], kLog2e, -mn2));
+                    a3 += exp2f(fmaf(z[j + 3], kLog2e, -mn2));
+                }
+                st.s = st.s * exp2f((st.m - mn) * kLog2e) + ((a0 + a1) + (a2 + a3));
                 st.m = mn;
             }
-        }
+        });
     }
     static __device__ __forceinline__ void end_rb(State& st, const Params& ep, const TileCtx& cx) {
-        const int slot = cx.worker % ep.S;
+        const int slot = (cx.worker % ep.S) * 2 + cx.half;
         ep.pm[(size_t)slot * ep.Mpad + cx.row] = st.m;
         ep.ps[(size_t)slot * ep.Mpad + cx.row] = st.s;
         if (st.has) ep.zlab[cx.row] = st.zl;
     }
 };
 
-// dlogits tile = (exp(z - lse) - [col == label]) * scale, written bf16 as P [M, Vp] and P^T [V, Mp64].
+// dlogits tile = (exp(z - lse) - [col == label]) * scale, written bf16 as P [M, Vp] (16-byte stores) and
+// P^T [V, Mp64]: neighbouring lanes (= neighbouring rows) swap one value per column pair so that every
+// lane writes a packed bf16 pair, i.e. 4-byte stores that coalesce to 64 B per column.
 struct DlogitsEpi {
+    static constexpr bool kColVec = true;
     struct Params {
-        const float* bias; const int* lab; const float* lse; const float* grad_scale;
+        const float* colvec;  // bias [Vt], -inf beyond V
+        const int* lab; const float* lse; const float* grad_scale;
         float inv_count;
         __nv_bfloat16* p; __nv_bfloat16* pt;
         int M, V, Vp, Mp64;
@@ -218,82 +227,73 @@ struct DlogitsEpi {
         st.scale = ok ? ep.inv_count * (ep.grad_scale ? __ldg(ep.grad_scale) : 1.0f) : 0.f;
     }
     static __device__ __forceinline__ void tile(State& st, const Params& ep, const TileCtx& cx, uint32_t taddr) {
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c * 32, r);
+        const float4* cv = reinterpret_cast<const float4*>(cx.cv);
+        const bool odd = (threadIdx.x & 1) != 0;
+        for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
             const int col = cx.col0 + c * 32;
-            const float4* bp = reinterpret_cast<const float4*>(ep.bias + col);
-            float4 b[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) b[i] = __ldg(bp + i);
-            tmem_ld_wait();
-            if (col >= ep.Vp) continue;
+            if (col >= ep.Vp) return;               // warp-uniform: Vp is a multiple of 64
             const unsigned rel = (unsigned)(st.label - col);
-            __nv_bfloat162 o[16];
+            float g[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float bb[4] = {b[i].x, b[i].y, b[i].z, b[i].w};
-                float g[4];
+                const float4 b = cv[c * 8 + i];
+                const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int j = 4 * i + e;
                     const float z = __uint_as_float(r[j]) + bb[e];
                     float pz = exp2f(fmaf(z, kLog2e, -st.lse2));      // exp(-inf) = 0 on padded label columns
                     if (rel == (unsigned)j) pz -= 1.0f;
-                    g[e] = st.ok ? pz * st.scale : 0.f;      // rows in [M, Mp64) are zero padding of P^T
+                    g[j] = st.ok ? pz * st.scale : 0.f;               // rows in [M, Mp64) are zero padding of P^T
                 }
-                o[2 * i] = __floats2bfloat162_rn(g[0], g[1]);
-                o[2 * i + 1] = __floats2bfloat162_rn(g[2], g[3]);
             }
             if (cx.row < ep.M) {
-                // Vp is a multiple of 64, so a 32-column chunk is either fully inside the pitch or skipped above
                 uint4* dst = reinterpret_cast<uint4*>(ep.p + (size_t)cx.row * ep.Vp + col);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = *reinterpret_cast<uint4*>(&o[4 * i]);
-            }
-            if (cx.row < ep.Mp64) {
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 o[4];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (col + j < ep.V) {
-                        const __nv_bfloat162 v2 = o[j >> 1];
-                        ep.pt[(size_t)(col + j) * ep.Mp64 + cx.row] = (j & 1) ? v2.y : v2.x;
-                    }
+                    for (int e = 0; e < 4; ++e) o[e] = __floats2bfloat162_rn(g[8 * i + 2 * e], g[8 * i + 2 * e + 1]);
+                    dst[i] = *reinterpret_cast<uint4*>(o);
                 }
             }
-        }
+            // P^T: the even lane (row l) ends up with rows (l, l+1) of column j, the odd lane with rows
+            // (l-1, l) of column j+1.
+            const int prow = odd ? cx.row - 1 : cx.row;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const float recv = __shfl_xor_sync(0xffffffffu, odd ? g[j] : g[j + 1], 1);
+                const __nv_bfloat162 pr = odd ? __floats2bfloat162_rn(recv, g[j + 1]) : __floats2bfloat162_rn(g[j], recv);
+                const int pc = col + j + (odd ? 1 : 0);
+                if (prow < ep.Mp64 && pc < ep.V)
+                    *reinterpret_cast<__nv_bfloat162*>(ep.pt + (size_t)pc * ep.Mp64 + prow) = pr;
+            }
+        });
     }
     static __device__ __forceinline__ void end_rb(State&, const Params&, const TileCtx&) {}
 };
 
 // ------------------------------------------------------------------------------------------------ small kernels
-// lse[m] = log-sum-exp combined over the S column splits; loss_sum = sum_m (lse[m] - z[label]) in a
-// fixed order (single CTA).
-__global__ void __launch_bounds__(1024)
+// lse[m] = log-sum-exp combined over the column-split partials, one thread per masked row;
+// rowloss[m] = lse[m] - z[label].  The loss sum is taken by ce_sum_kernel in a fixed order.
+__global__ void __launch_bounds__(128)
 ce_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ zlab, int M, int Mpad,
-                   int S, float* __restrict__ lse, float* __restrict__ loss_sum) {
-    __shared__ float sh[32];
-    float part = 0.f;
-    for (int m = threadIdx.x; m < M; m += blockDim.x) {
-        float mx = -CUDART_INF_F;
-        for (int s = 0; s < S; ++s) mx = fmaxf(mx, pm[(size_t)s * Mpad + m]);
-        float sum = 0.f;
-        for (int s = 0; s < S; ++s) sum += ps[(size_t)s * Mpad + m] * exp2f((pm[(size_t)s * Mpad + m] - mx) * kLog2e);
-        const float l = mx + log2f(sum) * kLn2;
-        lse[m] = l;
-        part += l - zlab[m];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float t = sh[threadIdx.x];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) loss_sum[0] = t;
-    }
+                   int slots, float* __restrict__ lse, float* __restrict__ rowloss) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float mx = -CUDART_INF_F;
+#pragma unroll 4
+    for (int s = 0; s < slots; ++s) mx = fmaxf(mx, __ldg(pm + (size_t)s * Mpad + m));
+    float sum = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < slots; ++s)
+        sum += __ldg(ps + (size_t)s * Mpad + m) * exp2f((__ldg(pm + (size_t)s * Mpad + m) - mx) * kLog2e);
+    const float l = mx + log2f(sum) * kLn2;
+    lse[m] = l;
+    rowloss[m] = l - zlab[m];
 }
+
+__global__ void ce_sum_kernel(const float* __restrict__ v, int M, float* __restrict__ out);
 
 // d_b[v] = sum_m P^T[v, m]: one warp per label, fixed lane-strided order.
 __global__ void __launch_bounds__(256)
@@ -481,7 +481,7 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
                    : launch_ce_gather<float>(h, rows, labels, (int)M, (int)Dh, l, ws, false, false, stream);
     if (rc) return rc;
     LseEpi::Params ep;
-    ep.bias = reinterpret_cast<const float*>(hb + hl.bias_off);
+    ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
     ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
     ep.pm = reinterpret_cast<float*>(ws + l.pm_off);
     ep.ps = reinterpret_cast<float*>(ws + l.ps_off);
@@ -490,7 +490,10 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     rc = launch_gemm_tn<1, true, LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
                                          /*split_mode=*/1, (int)l.S, 0, ep, stream);
     if (rc) return rc;
-    ce_finalize_kernel<<<1, 1024, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, (int)l.S, lse, loss_sum);
+    float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
+    ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
+                                                                    rowloss);
+    ce_sum_kernel<<<1, 1024, 0, stream>>>(rowloss, (int)M, loss_sum);
     return (int)cudaGetLastError();
 }
 
@@ -516,7 +519,7 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + l.p_off);
     __nv_bfloat16* PT = reinterpret_cast<__nv_bfloat16*>(ws + l.pt_off);
     DlogitsEpi::Params ep;
-    ep.bias = reinterpret_cast<const float*>(hb + hl.bias_off);
+    ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
     ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
     ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
     ep.p = P; ep.pt = PT; ep.M = (int)M; ep.V = (int)V; ep.Vp = (int)l.Vp; ep.Mp64 = (int)l.Mp64;

@@ -13,6 +13,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// One lane of a converged warp (elect.sync).  Code predicated on it is known to ptxas to run in a
+// single lane, so tcgen05 / TMA operands go to uniform registers directly; with `lane == 0` instead
+// every such instruction is wrapped in an ELECT / R2UR / BRA.U waterfall loop (~100 cycles each).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred) : "r"(0xffffffffu));
+    return pred;
+}
+
 // ---------------------------------------------------------------- cluster
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -50,6 +63,16 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+// Non-blocking probe (test_wait never suspends the thread; try_wait may sleep up to a HW time limit).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
@@ -141,6 +164,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
+}
+
+// tcgen05.wait::ld that also names the destination registers as in/out operands, so the compiler cannot
+// schedule an instruction that consumes them above the wait.
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
 }
 
 // ---------------------------------------------------------------- UMMA descriptors

@@ -113,7 +113,7 @@ int assign_variant_default(int num_kb) {
 int run_assign_gemm(const __nv_bfloat16* xb, long long N, int Dp, const CodebookLayout& cl, const void* codebook,
                     long long K, int index_offset, long long* packed, cudaStream_t stream) {
     ArgminEpi::Params ep;
-    ep.cnorm = reinterpret_cast<const float*>(static_cast<const char*>(codebook) + cl.cnorm_off);
+    ep.colvec = reinterpret_cast<const float*>(static_cast<const char*>(codebook) + cl.cnorm_off);
     ep.packed = packed; ep.rows = (int)N; ep.index_offset = index_offset;
     const void* cb = static_cast<const char*>(codebook) + cl.cb_off;
     const int v = assign_variant_default(Dp / kBlockK);
@@ -229,12 +229,41 @@ int pero_vq_assign_bf16(const void* x_bf16, int64_t N, int64_t K, int64_t D, con
                            reinterpret_cast<long long*>(packed_io), (cudaStream_t)stream);
 }
 
+int pero_debug_set_timeline(void* device_buffer) {
+    g_debug_timeline = static_cast<unsigned long long*>(device_buffer);
+    return PERO_OK;
+}
+
 int pero_debug_gemm_tn(const void* a_bf16, int64_t rows_a, const void* b_bf16, int64_t rows_b, int64_t kd,
                        int variant, int num_splits, float* out, pero_stream_t stream) {
     if (!a_bf16 || !b_bf16 || !out) return PERO_ERR_NULL;
     StoreEpi::Params ep;
     ep.out = out; ep.ld = rows_b; ep.split_stride = rows_a * rows_b; ep.rows = (int)rows_a; ep.cols = (int)rows_b;
     const int ra = (int)rows_a, rb = (int)rows_b, k = (int)kd;
+    if (variant & 16) {          // timeline: `out` receives clock64 stamps [unit][8] of worker 0 (u64)
+        NullEpi::Params np; np.out = nullptr;
+        unsigned long long* tl = reinterpret_cast<unsigned long long*>(out);
+        const bool pair = variant & 1, res = variant & 2;
+        if (pair && res) return launch_gemm_tn<2, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
+        if (pair) return launch_gemm_tn<2, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
+        if (res) return launch_gemm_tn<1, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
+        return launch_gemm_tn<1, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
+    }
+    if (variant & 12) {          // measurement only: bit2 = no TMEM reads at all, bit3 = TMEM reads without math
+        NullEpi::Params np; np.out = out;
+        LoadEpi::Params lp; lp.out = out;
+        const bool pair = variant & 1, res = variant & 2, load = variant & 8;
+        if (load) {
+            if (pair && res) return launch_gemm_tn<2, true, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
+            if (pair) return launch_gemm_tn<2, false, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
+            if (res) return launch_gemm_tn<1, true, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
+            return launch_gemm_tn<1, false, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
+        }
+        if (pair && res) return launch_gemm_tn<2, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
+        if (pair) return launch_gemm_tn<2, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
+        if (res) return launch_gemm_tn<1, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
+        return launch_gemm_tn<1, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
+    }
     switch (variant & 3) {
         case 0: return launch_gemm_tn<1, false, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, num_splits, 0, 1, 0, ep, stream);
         case 1: return launch_gemm_tn<2, false, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, num_splits, 0, 1, 0, ep, stream);
