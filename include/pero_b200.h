@@ -98,6 +98,7 @@ int pero_vq_gather_st(const float* x_rows, const int64_t* idx, const float* weig
  *     cs <- cs*decay + (1-decay)*counts;  n = sum(cs);  cs <- (cs + eps) / (n + K*eps) * n
  *     ema_w <- ema_w*decay + (1-decay)*sums;  weight <- ema_w / cs[:, None]
  *   and, when `codebook` is not NULL, refreshes the prepared blob for the next assign.
+ *   Its workspace needs 256 bytes (any pero_vq_ema_workspace_bytes() buffer is large enough).
  */
 size_t pero_vq_ema_workspace_bytes(int64_t N, int64_t K, int64_t D);
 int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, int64_t K, int64_t D,

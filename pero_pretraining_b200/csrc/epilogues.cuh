@@ -36,6 +36,7 @@ __device__ __forceinline__ void for_each_chunk(uint32_t taddr, Body&& body) {
 // lowest index.
 struct ArgminEpi {
     static constexpr bool kColVec = true;
+    static constexpr int kScratchPerWarp = 0;
     struct Params {
         const float* colvec;           // |c|^2 in fp32 [num_ct * 256], +inf beyond the last codeword
         long long* packed;             // [rows] pre-set to kPackedEmpty
@@ -83,10 +84,13 @@ struct ArgminEpi {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Plain fp32 store C[row, col] (one plane per contraction split).  128 contiguous bytes per thread per
-// chunk, so every 32-byte sector written is full.
+// Plain fp32 store C[row, col] (one plane per contraction split).  A thread holds one row, which would
+// make every store instruction touch 32 different cache lines with 16 bytes each; instead each 32 x 32
+// chunk is transposed through a warp-private shared-memory tile (144-byte pitch: conflict-free both ways)
+// so that one store instruction writes 4 full 128-byte lines.
 struct StoreEpi {
     static constexpr bool kColVec = false;
+    static constexpr int kScratchPerWarp = 32 * 144;
     struct Params {
         float* out;
         long long ld;             // elements between output rows
@@ -96,23 +100,33 @@ struct StoreEpi {
     struct State {};
     static __device__ __forceinline__ void begin_rb(State&, const Params&, const TileCtx&) {}
     static __device__ __forceinline__ void tile(State&, const Params& ep, const TileCtx& cx, uint32_t taddr) {
-        float* dst = ep.out + (long long)cx.ks * ep.split_stride + (long long)cx.row * ep.ld + cx.col0;
-        const bool row_ok = cx.row < ep.rows;
+        const int lane = threadIdx.x & 31;
+        const int row_base = cx.row - lane;
+        float* base = ep.out + (long long)cx.ks * ep.split_stride + (long long)row_base * ep.ld + cx.col0;
         const bool vec_ok = ((ep.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
                             ((ep.split_stride & 3) == 0);
         for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
-            if (!row_ok) return;
             const int col = cx.col0 + c * 32;
             if (vec_ok && col + 32 <= ep.cols) {
+                float4* srow = reinterpret_cast<float4*>(cx.scratch + lane * 144);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    reinterpret_cast<float4*>(dst + c * 32)[i] =
-                        make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                    __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-            } else {
+                    srow[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                          __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int rr = 4 * k + (lane >> 3), piece = lane & 7;
+                    const float4 v = *reinterpret_cast<const float4*>(cx.scratch + rr * 144 + piece * 16);
+                    if (row_base + rr < ep.rows)
+                        *reinterpret_cast<float4*>(base + (long long)rr * ep.ld + c * 32 + piece * 4) = v;
+                }
+                __syncwarp();
+            } else if (cx.row < ep.rows) {
+                float* dst = base + (long long)lane * ep.ld + c * 32;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (col + j < ep.cols) dst[c * 32 + j] = __uint_as_float(r[j]);
+                    if (col + j < ep.cols) dst[j] = __uint_as_float(r[j]);
             }
         });
     }
@@ -124,6 +138,7 @@ struct StoreEpi {
 // LoadEpi only streams the accumulator out of TMEM (adds the tcgen05.ld cost).
 struct NullEpi {
     static constexpr bool kColVec = false;
+    static constexpr int kScratchPerWarp = 0;
     struct Params { float* out; };
     struct State {};
     static __device__ __forceinline__ void begin_rb(State&, const Params&, const TileCtx&) {}
@@ -132,6 +147,7 @@ struct NullEpi {
 };
 struct LoadEpi {
     static constexpr bool kColVec = false;
+    static constexpr int kScratchPerWarp = 0;
     struct Params { float* out; };
     struct State { uint32_t acc; };
     static __device__ __forceinline__ void begin_rb(State& st, const Params&, const TileCtx&) { st.acc = 0; }

@@ -65,16 +65,19 @@ struct TileCtx {
     int col0;           // first global output column of this thread's half tile (128 columns)
     int half;           // 0: columns 0..127 of the tile, 1: columns 128..255
     const float* cv;    // shared-memory copy of Params::colvec[col0 .. col0 + 128) (when Epi::kColVec)
+    uint8_t* scratch;   // warp-private shared memory, Epi::kScratchPerWarp bytes (16-byte aligned)
     int worker;         // CTA (or pair) index
     int cta_rank;       // rank inside the pair
     int num_workers;
 };
 
-__host__ __device__ inline size_t gemm_smem_bytes(int cta_group, bool a_resident, int num_kb, int stages) {
+__host__ __device__ inline size_t gemm_smem_bytes(int cta_group, bool a_resident, int num_kb, int stages,
+                                                  int scratch_per_warp) {
     const size_t b_bytes = (size_t)(kBlockN / cta_group) * kBlockK * 2;
     const size_t stage = b_bytes + (a_resident ? 0 : kABlockBytes);
     const size_t a_res = a_resident ? (size_t)num_kb * kABlockBytes : 0;
-    return 1024 /*align slack*/ + a_res + stage * stages + 1024 /*barriers*/ + 2 * kBlockN * 4 /*column vector x2*/;
+    return 1024 /*align slack*/ + a_res + stage * stages + 1024 /*barriers*/ + 2 * kBlockN * 4 /*column vector x2*/ +
+           (size_t)scratch_per_warp * (kEpiThreads / 32);
 }
 
 __device__ __forceinline__ void unit_range(const GemmShape& sh, int worker, int num_workers, int& u0, int& u1) {
@@ -155,6 +158,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     auto tempty_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 2 * kMaxAKb + 2 + b); };
     const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 2 * kMaxAKb + 4);
     float* const cv_smem = reinterpret_cast<float*>(smem_raw + (bars + 1024u - smem_u32(smem_raw)));   // [2][256]
+    uint8_t* const scratch_smem = reinterpret_cast<uint8_t*>(cv_smem) + 2 * kBlockN * 4;
 
     if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -286,6 +290,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         typename Epi::State st;
         TileCtx cx;
         cx.worker = worker; cx.cta_rank = (int)cta_rank; cx.num_workers = num_workers; cx.half = half; cx.cv = nullptr;
+        cx.scratch = scratch_smem + warp * Epi::kScratchPerWarp;
         UnitIter ui(sh, u0, u1);
         float pre = 0.f;                              // column-vector element of the NEXT tile, loaded a tile ahead
         if constexpr (Epi::kColVec) {

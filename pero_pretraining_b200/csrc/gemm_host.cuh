@@ -61,9 +61,9 @@ constexpr size_t kSmemBudget = 227 * 1024;
 constexpr size_t kSmemFloor = 120 * 1024;   // > half an SM: never two TMEM-hungry CTAs on one SM
 
 // Picks the deepest ring that fits; returns 0 when even 2 stages do not fit.
-inline int pick_stages(int cta_group, bool a_resident, int num_kb) {
+inline int pick_stages(int cta_group, bool a_resident, int num_kb, int scratch_per_warp) {
     for (int s = kMaxStages; s >= 2; --s)
-        if (gemm_smem_bytes(cta_group, a_resident, num_kb, s) <= kSmemBudget) return s;
+        if (gemm_smem_bytes(cta_group, a_resident, num_kb, s, scratch_per_warp) <= kSmemBudget) return s;
     return 0;
 }
 
@@ -76,6 +76,7 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
     GemmShape sh;
     sh.timeline = timeline ? timeline : g_debug_timeline;
+    if (!timeline && g_debug_timeline) g_debug_timeline += 8192;    // debug: one 64 KiB slot per GEMM launch
     sh.rows_a = rows_a; sh.rows_b = rows_b;
     sh.num_kb = kd / kBlockK;
     sh.num_rb = (rows_a + kBlockM * kCtaGroup - 1) / (kBlockM * kCtaGroup);
@@ -85,7 +86,7 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     sh.num_ks = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;   // no empty splits
     sh.split_mode = split_mode; sh.fixed_s = fixed_s < 1 ? 1 : fixed_s;
     if (kAResident && (sh.num_ks != 1 || sh.num_kb > kMaxAKb)) return PERO_ERR_BAD_SHAPE;
-    sh.num_stages = pick_stages(kCtaGroup, kAResident, sh.num_kb);
+    sh.num_stages = pick_stages(kCtaGroup, kAResident, sh.num_kb, Epi::kScratchPerWarp);
     if (sh.num_stages < 2) return PERO_ERR_BAD_SHAPE;
 
     CUtensorMap ta, tb;
@@ -105,7 +106,7 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     else if (workers <= 0 || workers > max_workers) workers = max_workers;
     if (split_mode == 0 && workers > units) workers = (int)units;
 
-    size_t smem = gemm_smem_bytes(kCtaGroup, kAResident, sh.num_kb, sh.num_stages);
+    size_t smem = gemm_smem_bytes(kCtaGroup, kAResident, sh.num_kb, sh.num_stages, Epi::kScratchPerWarp);
     if (smem < kSmemFloor) smem = kSmemFloor;
     auto kern = gemm_tn_kernel<kCtaGroup, kAResident, Epi>;
     static bool attr_set = false;

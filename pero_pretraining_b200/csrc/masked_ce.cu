@@ -19,6 +19,14 @@ namespace pero {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+// One MUFU.EX2 (rel. error ~2^-22, denormals flushed): exp2f() costs three more instructions per element
+// for its denormal-input scaling, and the epilogues below are instruction-issue bound.
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Prepared head: bf16 W [V, Dhp] | bf16 W^T [Dh, Vp] | bias fp32 [Vt] (-inf beyond V so padded label
 // columns vanish from the log-sum-exp).  Dhp, Vp: rounded up to 64; Vt: rounded up to 256.
 struct HeadLayout { int64_t Dhp, Vp, Vt; size_t w_off, wt_off, bias_off, total; };
@@ -40,9 +48,10 @@ struct CeWsLayout {
 };
 inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     CeWsLayout l;
-    l.Dhp = round_up(Dh, 64); l.Vp = round_up(V, 64); l.Mp64 = round_up(M, 64); l.Mpad = round_up(M, 128);
-    const int64_t num_rb = l.Mpad / 128, num_ct = (V + 255) / 256, num_ct_dh = (Dh + 255) / 256;
-    int64_t S = 148 / num_rb;
+    // The logits GEMMs (forward LSE, backward dlogits) run on CTA pairs: 256-row blocks, 74 workers.
+    l.Dhp = round_up(Dh, 64); l.Vp = round_up(V, 64); l.Mp64 = round_up(M, 64); l.Mpad = round_up(M, 256);
+    const int64_t num_rb_pair = l.Mpad / 256, num_rb = (M + 127) / 128, num_ct = (V + 255) / 256, num_ct_dh = (Dh + 255) / 256;
+    int64_t S = 74 / num_rb_pair;
     if (S < 1) S = 1;
     if (S > num_ct) S = num_ct;
     if (S > kMaxLseSplits) S = kMaxLseSplits;
@@ -145,6 +154,7 @@ ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const lo
 // Online log-sum-exp over the label axis; one partial (max, sum) per row, column split and column half.
 struct LseEpi {
     static constexpr bool kColVec = true;
+    static constexpr int kScratchPerWarp = 0;
     struct Params {
         const float* colvec;  // bias [Vt], -inf beyond V
         const int* lab;       // [Mpad]
@@ -188,12 +198,12 @@ struct LseEpi {
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    a0 += exp2f(fmaf(z[j + 0], kLog2e, -mn2));
-                    a1 += exp2f(fmaf(z[j + 1], kLog2e, -mn2));
-                    a2 += exp2f(fmaf(z[j + 2], kLog2e, -mn2));
-                    a3 += exp2f(fmaf(z[j + 3], kLog2e, -mn2));
+                    a0 += ex2_fast(fmaf(z[j + 0], kLog2e, -mn2));
+                    a1 += ex2_fast(fmaf(z[j + 1], kLog2e, -mn2));
+                    a2 += ex2_fast(fmaf(z[j + 2], kLog2e, -mn2));
+                    a3 += ex2_fast(fmaf(z[j + 3], kLog2e, -mn2));
                 }
-                st.s = st.s * exp2f((st.m - mn) * kLog2e) + ((a0 + a1) + (a2 + a3));
+                st.s = st.s * ex2_fast((st.m - mn) * kLog2e) + ((a0 + a1) + (a2 + a3));
                 st.m = mn;
             }
         });
@@ -211,63 +221,79 @@ struct LseEpi {
 // lane writes a packed bf16 pair, i.e. 4-byte stores that coalesce to 64 B per column.
 struct DlogitsEpi {
     static constexpr bool kColVec = true;
+    static constexpr int kScratchPerWarp = 32 * 80;      // 32 rows x 32 bf16, 80-byte pitch
     struct Params {
         const float* colvec;  // bias [Vt], -inf beyond V
         const int* lab; const float* lse; const float* grad_scale;
         float inv_count;
         __nv_bfloat16* p; __nv_bfloat16* pt;
         int M, V, Vp, Mp64;
+        int debug_skip;       // measurement only: 1 = skip P stores, 2 = skip P^T stores
     };
-    struct State { float lse2, scale; int label; bool ok; };
+    struct State { float lse2, scale; int label; };
     static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
         const bool ok = cx.row < ep.M;
-        st.ok = ok;
         st.label = ok ? __ldg(ep.lab + cx.row) : -1;
-        st.lse2 = ok ? __ldg(ep.lse + cx.row) * kLog2e : 0.f;
+        // rows in [M, Mp64) are the zero padding of P^T: lse = +inf makes exp2(z - lse) exactly 0, no select needed
+        st.lse2 = ok ? __ldg(ep.lse + cx.row) * kLog2e : CUDART_INF_F;
         st.scale = ok ? ep.inv_count * (ep.grad_scale ? __ldg(ep.grad_scale) : 1.0f) : 0.f;
     }
     static __device__ __forceinline__ void tile(State& st, const Params& ep, const TileCtx& cx, uint32_t taddr) {
         const float4* cv = reinterpret_cast<const float4*>(cx.cv);
-        const bool odd = (threadIdx.x & 1) != 0;
+        const int lane = threadIdx.x & 31;
+        const int row_base = cx.row - lane;
+        const bool rows_in_pt = row_base < ep.Mp64;            // warp-uniform: Mp64 is a multiple of 64
         for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
             const int col = cx.col0 + c * 32;
-            if (col >= ep.Vp) return;               // warp-uniform: Vp is a multiple of 64
-            const unsigned rel = (unsigned)(st.label - col);
+            const bool col_ok = col < ep.Vp;                    // warp-uniform: Vp is a multiple of 64
             float g[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 b = cv[c * 8 + i];
-                const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = 4 * i + e;
-                    const float z = __uint_as_float(r[j]) + bb[e];
-                    float pz = exp2f(fmaf(z, kLog2e, -st.lse2));      // exp(-inf) = 0 on padded label columns
-                    if (rel == (unsigned)j) pz -= 1.0f;
-                    g[j] = st.ok ? pz * st.scale : 0.f;               // rows in [M, Mp64) are zero padding of P^T
-                }
+                g[4 * i + 0] = ex2_fast(fmaf(__uint_as_float(r[4 * i + 0]) + b.x, kLog2e, -st.lse2)) * st.scale;
+                g[4 * i + 1] = ex2_fast(fmaf(__uint_as_float(r[4 * i + 1]) + b.y, kLog2e, -st.lse2)) * st.scale;
+                g[4 * i + 2] = ex2_fast(fmaf(__uint_as_float(r[4 * i + 2]) + b.z, kLog2e, -st.lse2)) * st.scale;
+                g[4 * i + 3] = ex2_fast(fmaf(__uint_as_float(r[4 * i + 3]) + b.w, kLog2e, -st.lse2)) * st.scale;
             }
-            if (cx.row < ep.M) {
-                uint4* dst = reinterpret_cast<uint4*>(ep.p + (size_t)cx.row * ep.Vp + col);
+            const unsigned rel = (unsigned)(st.label - col);    // (p - 1) * scale at the label column
+            if (rel < 32u) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = __floats2bfloat162_rn(g[8 * i + 2 * e], g[8 * i + 2 * e + 1]);
-                    dst[i] = *reinterpret_cast<uint4*>(o);
-                }
+                for (int j = 0; j < 32; ++j) if (rel == (unsigned)j) g[j] -= st.scale;
             }
-            // P^T: the even lane (row l) ends up with rows (l, l+1) of column j, the odd lane with rows
-            // (l-1, l) of column j+1.
-            const int prow = odd ? cx.row - 1 : cx.row;
+            __nv_bfloat162 o[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                const float recv = __shfl_xor_sync(0xffffffffu, odd ? g[j] : g[j + 1], 1);
-                const __nv_bfloat162 pr = odd ? __floats2bfloat162_rn(recv, g[j + 1]) : __floats2bfloat162_rn(g[j], recv);
-                const int pc = col + j + (odd ? 1 : 0);
-                if (prow < ep.Mp64 && pc < ep.V)
-                    *reinterpret_cast<__nv_bfloat162*>(ep.pt + (size_t)pc * ep.Mp64 + prow) = pr;
+            for (int j = 0; j < 16; ++j) o[j] = __floats2bfloat162_rn(g[2 * j], g[2 * j + 1]);
+
+            // ---- P rows: chunk staged row-major (80-byte pitch); one store instruction = 8 rows x 64 B
+            uint4* srow = reinterpret_cast<uint4*>(cx.scratch + lane * 80);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) srow[i] = *reinterpret_cast<uint4*>(&o[4 * i]);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rr = 8 * k + (lane >> 2), piece = lane & 3;
+                const uint4 v = *reinterpret_cast<const uint4*>(cx.scratch + rr * 80 + piece * 16);
+                if (col_ok && row_base + rr < ep.M && !(ep.debug_skip & 1))
+                    *reinterpret_cast<uint4*>(ep.p + (size_t)(row_base + rr) * ep.Vp + col + piece * 8) = v;
             }
+            __syncwarp();
+            // ---- P^T columns: chunk staged column-major in the same buffer; one store instruction = 4 columns
+            //      x 64 B (the warp's 32 rows are contiguous in P^T)
+            __nv_bfloat16* tcol = reinterpret_cast<__nv_bfloat16*>(cx.scratch) + lane;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                tcol[(2 * j) * 40] = o[j].x;                     // 40 bf16 = 80-byte pitch
+                tcol[(2 * j + 1) * 40] = o[j].y;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int cc = 4 * k + (lane >> 3), piece = lane & 7;     // column cc, rows 4*piece .. 4*piece+3
+                const uint2 v = *reinterpret_cast<const uint2*>(cx.scratch + cc * 80 + piece * 8);
+                if (rows_in_pt && col + cc < ep.V && !(ep.debug_skip & 2))
+                    *reinterpret_cast<uint2*>(ep.pt + (size_t)(col + cc) * ep.Mp64 + row_base + piece * 4) = v;
+            }
+            __syncwarp();
         });
     }
     static __device__ __forceinline__ void end_rb(State&, const Params&, const TileCtx&) {}
@@ -276,21 +302,34 @@ struct DlogitsEpi {
 // ------------------------------------------------------------------------------------------------ small kernels
 // lse[m] = log-sum-exp combined over the column-split partials, one thread per masked row;
 // rowloss[m] = lse[m] - z[label].  The loss sum is taken by ce_sum_kernel in a fixed order.
-__global__ void __launch_bounds__(128)
+// One warp per row, lanes over the partial slots (all loads in flight at once; fixed butterfly order).
+__global__ void __launch_bounds__(256)
 ce_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ zlab, int M, int Mpad,
                    int slots, float* __restrict__ lse, float* __restrict__ rowloss) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (m >= M) return;
+    float pmv[4], psv[4];                    // slots <= 2 * kMaxLseSplits = 128 = 4 per lane
     float mx = -CUDART_INF_F;
-#pragma unroll 4
-    for (int s = 0; s < slots; ++s) mx = fmaxf(mx, __ldg(pm + (size_t)s * Mpad + m));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int s = lane + 32 * i;
+        pmv[i] = s < slots ? __ldg(pm + (size_t)s * Mpad + m) : -CUDART_INF_F;
+        psv[i] = s < slots ? __ldg(ps + (size_t)s * Mpad + m) : 0.f;
+        mx = fmaxf(mx, pmv[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
-#pragma unroll 4
-    for (int s = 0; s < slots; ++s)
-        sum += __ldg(ps + (size_t)s * Mpad + m) * exp2f((__ldg(pm + (size_t)s * Mpad + m) - mx) * kLog2e);
-    const float l = mx + log2f(sum) * kLn2;
-    lse[m] = l;
-    rowloss[m] = l - zlab[m];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sum += psv[i] * exp2f((pmv[i] - mx) * kLog2e);     // exp2(-inf) = 0 on empty slots
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) {
+        const float l = mx + log2f(sum) * kLn2;
+        lse[m] = l;
+        rowloss[m] = l - zlab[m];
+    }
 }
 
 __global__ void ce_sum_kernel(const float* __restrict__ v, int M, float* __restrict__ out);
@@ -318,16 +357,29 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ inv, long long N, int M, int Dh, int KS,
                      T* __restrict__ dh) {
-    const long long total = N * Dh;
+    // one thread per 4 consecutive channels (Dh % 4 == 0): 16-byte plane reads, 16/8-byte stores
+    const int g4 = Dh >> 2;
+    const long long total = N * g4;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const long long n = i / Dh;
-        const int d = (int)(i - n * Dh);
+        const long long n = i / g4;
+        const int g = (int)(i - n * g4);
         const int m = __ldg(inv + n);
-        float s = 0.f;
-        if (m >= 0)
-            for (int k = 0; k < KS; ++k) s += __ldg(planes + ((size_t)k * M + m) * Dh + d);
-        dh[i] = (T)s;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m >= 0) {
+            for (int k = 0; k < KS; ++k) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(planes + ((size_t)k * M + m) * Dh) + g);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        }
+        if constexpr (sizeof(T) == 4) {
+            reinterpret_cast<float4*>(dh)[i] = s;
+        } else {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(s.x, s.y), hi = __floats2bfloat162_rn(s.z, s.w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(dh)[i] = o;
+        }
     }
 }
 
@@ -487,12 +539,12 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     ep.ps = reinterpret_cast<float*>(ws + l.ps_off);
     ep.zlab = reinterpret_cast<float*>(ws + l.zlab_off);
     ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S;
-    rc = launch_gemm_tn<1, true, LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
+    rc = launch_gemm_tn<2, true, LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
                                          /*split_mode=*/1, (int)l.S, 0, ep, stream);
     if (rc) return rc;
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
-    ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
-                                                                    rowloss);
+    ce_finalize_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
+                                                                rowloss);
     ce_sum_kernel<<<1, 1024, 0, stream>>>(rowloss, (int)M, loss_sum);
     return (int)cudaGetLastError();
 }
@@ -522,8 +574,9 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
     ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
     ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
+    { const char* e = getenv("PERO_DLOGITS_SKIP"); ep.debug_skip = e ? atoi(e) : 0; }
     ep.p = P; ep.pt = PT; ep.M = (int)M; ep.V = (int)V; ep.Vp = (int)l.Vp; ep.Mp64 = (int)l.Mp64;
-    rc = launch_gemm_tn<1, true, DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
+    rc = launch_gemm_tn<2, true, DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
                                              0, 1, 0, ep, stream);
     if (rc) return rc;
 
@@ -543,7 +596,7 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
         rc = launch_gemm_tn<1, false, StoreEpi>(P, (int)M, (int)l.Vp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0, 1,
                                                 0, sh, stream);
         if (rc) return rc;
-        const long long total = N * Dh;
+        const long long total = N * (Dh / 4);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         // the number of planes actually produced is recomputed exactly as launch_gemm_tn does

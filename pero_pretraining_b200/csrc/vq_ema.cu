@@ -1,14 +1,16 @@
 // EMA codebook update (models/autoencoders.py:225-237), deterministic:
-//   1. sort (codeword, frame) pairs by codeword  — radix sort is stable, so frames stay ascending
-//   2. segment the sorted list (binary search per codeword) -> counts
-//   3. chunked segmented sum of the fp32 frame rows in sorted order: every 32 sorted positions form one
+//   1. sort (codeword, frame) pairs by codeword, frames ascending inside a codeword.  Up to 8192 frames
+//      one CTA does it in a single launch with a stable block radix sort (and emits the segment
+//      boundaries); larger batches use CUB's device radix sort (stable as well).
+//   2. chunked segmented sum of the fp32 frame rows in sorted order: every 16 sorted positions form one
 //      chunk; runs that lie inside a chunk are summed and stored directly, runs that cross chunk borders
 //      leave a head/tail partial that a second kernel adds up in chunk order.  No atomics, so the sums
 //      are bit-identical run to run, and a collapsed codebook (one codeword owning every frame, as in
 //      the reference's cold start) still spreads over all SMs.
-//   4. apply: cluster-size EMA + Laplace smoothing, ema_w EMA, weight = ema_w / size, and refresh of the
+//   3. apply: cluster-size EMA + Laplace smoothing, ema_w EMA, weight = ema_w / size, and refresh of the
 //      bf16 operand + |c|^2 used by the next assign.
 // Row reads/writes are 16-byte vectors, coalesced along D.
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -17,10 +19,12 @@
 
 namespace pero {
 
-constexpr int kChunk = 32;   // sorted positions per chunk
+constexpr int kChunk = 16;            // sorted positions per chunk
+constexpr int kSmallSortMax = 8192;   // frames handled by the single-CTA sort (8 per thread x 1024 threads)
+constexpr int kClusterBlocks = 64;    // partial sums of the cluster-size reduction
 
 struct EmaWsLayout {
-    size_t keys_in, keys_out, vals_in, vals_out, seg, partial, scalar, cub, total;
+    size_t keys_in, keys_out, vals_in, vals_out, seg, partial, cluster_partial, cub, total;
     size_t cub_bytes;
 };
 
@@ -41,18 +45,53 @@ inline EmaWsLayout ema_ws_layout(int64_t N, int64_t K, int64_t D) {
     l.seg = take((size_t)(K + 1) * 4);
     const int64_t chunks = (N + kChunk - 1) / kChunk;
     l.partial = take((size_t)chunks * 2 * D * 4);
-    l.scalar = take(256);
+    l.cluster_partial = take(kClusterBlocks * 4);
     size_t cub_bytes = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)N, 0, key_bits(K));
-    if (e != cudaSuccess || cub_bytes == 0) {   // no device to query (CPU-only host): conservative bound
-        (void)cudaGetLastError();
-        cub_bytes = (size_t)N * 16 + (1u << 20);
+    if (N > kSmallSortMax) {
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                        (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)N, 0, key_bits(K));
+        if (e != cudaSuccess || cub_bytes == 0) {   // no device to query (CPU-only host): conservative bound
+            (void)cudaGetLastError();
+            cub_bytes = (size_t)N * 16 + (1u << 20);
+        }
     }
     l.cub_bytes = cub_bytes;
     l.cub = take(cub_bytes);
     l.total = off;
     return l;
+}
+
+// ------------------------------------------------------------------------------------------------ sort
+// Single CTA: stable block radix sort (cub::BlockRadixSort) of (codeword, frame) pairs held 8 per
+// thread in blocked order -- frames therefore stay ascending inside a codeword -- then the keys, the frame
+// ids and the segment table seg[k] = first sorted position with codeword >= k (seg[K] = N).
+template <int ITEMS>
+__global__ void __launch_bounds__(1024)
+ema_sort_small_kernel(const long long* __restrict__ idx, int N, int K, int end_bit, uint32_t* __restrict__ keys_out,
+                      uint32_t* __restrict__ vals_out, int* __restrict__ seg) {
+    using Sort = cub::BlockRadixSort<uint32_t, 1024, ITEMS, uint32_t>;
+    __shared__ typename Sort::TempStorage temp;
+    uint32_t keys[ITEMS], vals[ITEMS];
+    const uint32_t sentinel = 1u << (end_bit - 1);          // above every codeword: padding sorts last
+#pragma unroll
+    for (int e = 0; e < ITEMS; ++e) {
+        const int i = threadIdx.x * ITEMS + e;
+        keys[e] = i < N ? (uint32_t)idx[i] : sentinel;
+        vals[e] = (uint32_t)i;
+    }
+    Sort(temp).Sort(keys, vals, 0, end_bit);
+#pragma unroll
+    for (int e = 0; e < ITEMS; ++e) {
+        const int p = threadIdx.x * ITEMS + e;
+        if (p < N) { keys_out[p] = keys[e]; vals_out[p] = vals[e]; }
+    }
+    __syncthreads();
+    // boundaries from the sorted keys just written (same CTA: visible after the barrier)
+    for (int p = threadIdx.x; p <= N; p += blockDim.x) {
+        const int k = p < N ? (int)keys_out[p] : K;
+        const int kprev = p == 0 ? -1 : (int)keys_out[p - 1];
+        for (int kk = kprev + 1; kk <= k; ++kk) seg[kk] = p;
+    }
 }
 
 __global__ void ema_keys_kernel(const long long* __restrict__ idx, long long N, uint32_t* __restrict__ keys,
@@ -63,60 +102,75 @@ __global__ void ema_keys_kernel(const long long* __restrict__ idx, long long N, 
     vals[i] = (uint32_t)i;
 }
 
-// seg[k] = first sorted position whose key >= k; seg[K] = N.
-__global__ void ema_segments_kernel(const uint32_t* __restrict__ keys, int N, int K, int* __restrict__ seg) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > K) return;
-    int lo = 0, hi = N;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(keys + mid) < (uint32_t)k) lo = mid + 1; else hi = mid;
-    }
-    seg[k] = lo;
+// seg[k] = first sorted position whose key >= k; seg[K] = N.  One thread per sorted position writes the
+// (usually zero or one) boundaries that fall between its predecessor's key and its own.
+__global__ void ema_boundaries_kernel(const uint32_t* __restrict__ keys, int N, int K, int* __restrict__ seg) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > N) return;
+    const int k = p < N ? (int)keys[p] : K;
+    const int kprev = p == 0 ? -1 : (int)keys[p - 1];
+    for (int kk = kprev + 1; kk <= k; ++kk) seg[kk] = p;
 }
 
-// One CTA per chunk; thread t owns float4 column groups t, t + blockDim, ...
+// ------------------------------------------------------------------------------------------------ segmented sum
+// One CTA per chunk of 16 sorted positions; thread t owns 16-byte column groups t, t + blockDim, ...
+// All 16 row loads of a column group are issued before the running sums are formed.
 template <int VEC>
 __global__ void __launch_bounds__(128)
 ema_chunk_sum_kernel(const float* __restrict__ xr, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rows,
                      const int* __restrict__ seg, int N, int D, float* __restrict__ sums, float* __restrict__ partial) {
     __shared__ uint32_t s_key[kChunk], s_row[kChunk];
+    __shared__ int s_dst[kChunk];      // where the run ending at position p goes: -1 none, 0 sums, 1 head, 2 tail
     const int c = blockIdx.x;
     const int pos0 = c * kChunk, pos1 = min(N, pos0 + kChunk), len = pos1 - pos0;
-    if (threadIdx.x < len) { s_key[threadIdx.x] = keys[pos0 + threadIdx.x]; s_row[threadIdx.x] = rows[pos0 + threadIdx.x]; }
+    if (threadIdx.x < kChunk) {
+        const int p = threadIdx.x;
+        int dst = -1;
+        uint32_t k = 0, r = 0;
+        if (p < len) {
+            k = keys[pos0 + p]; r = rows[pos0 + p];
+            const bool run_end = (p + 1 == len) || (keys[pos0 + p + 1] != k);
+            if (run_end) {
+                const int s0 = __ldg(seg + k), s1 = __ldg(seg + k + 1);
+                dst = (s0 >= pos0 && s1 <= pos1) ? 0 : (s0 < pos0 ? 1 : 2);
+            }
+        }
+        s_key[p] = k; s_row[p] = r; s_dst[p] = dst;
+    }
     __syncthreads();
     const int groups = D / VEC;
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        float acc[VEC];
+        float v[kChunk][VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-        uint32_t cur = s_key[0];
-        auto flush = [&](uint32_t k) {
-            const int s0 = __ldg(seg + k), s1 = __ldg(seg + k + 1);
-            float* dst;
-            if (s0 >= pos0 && s1 <= pos1) dst = sums + (size_t)k * D;                 // whole run in this chunk
-            else if (s0 < pos0) dst = partial + ((size_t)c * 2 + 0) * D;                // head: began earlier
-            else dst = partial + ((size_t)c * 2 + 1) * D;                               // tail: continues later
-            if constexpr (VEC == 4) reinterpret_cast<float4*>(dst)[g] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            else dst[g] = acc[0];
-        };
-        for (int p = 0; p < len; ++p) {
-            const uint32_t k = s_key[p];
-            if (k != cur) {
-                flush(cur);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-                cur = k;
-            }
-            const float* src = xr + (size_t)s_row[p] * D;
-            if constexpr (VEC == 4) {
-                const float4 x = __ldg(reinterpret_cast<const float4*>(src) + g);
-                acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
-            } else {
-                acc[0] += __ldg(src + g);
+        for (int p = 0; p < kChunk; ++p) {
+            if (p < len) {
+                const float* src = xr + (size_t)s_row[p] * D;
+                if constexpr (VEC == 4) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(src) + g);
+                    v[p][0] = x.x; v[p][1] = x.y; v[p][2] = x.z; v[p][3] = x.w;
+                } else {
+                    v[p][0] = __ldg(src + g);
+                }
             }
         }
-        flush(cur);
+        float acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int p = 0; p < kChunk; ++p) {
+            if (p < len) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] += v[p][e];
+                const int dst = s_dst[p];
+                if (dst >= 0) {
+                    float* out = dst == 0 ? sums + (size_t)s_key[p] * D : partial + ((size_t)c * 2 + (dst - 1)) * D;
+                    if constexpr (VEC == 4) reinterpret_cast<float4*>(out)[g] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    else out[g] = acc[0];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+                }
+            }
+        }
     }
 }
 
@@ -165,45 +219,46 @@ ema_finalize_kernel(const int* __restrict__ seg, int K, int D, const float* __re
     }
 }
 
-// cluster size: cs <- cs*decay + (1-decay)*counts; n = sum(cs); cs <- (cs + eps) / (n + K*eps) * n.
-// Single CTA, fixed-order tree: K <= 2^20 values.
-__global__ void __launch_bounds__(1024)
-ema_cluster_size_kernel(const float* __restrict__ counts, int K, float decay, float one_minus_decay, float eps,
-                        float k_eps, float* __restrict__ cs) {
-    __shared__ float sh[32];
-    __shared__ float s_n;
+// ------------------------------------------------------------------------------------------------ apply
+// cs' = cs*decay + (1-decay)*counts (not stored); block partial sums of cs' in a fixed order.
+__global__ void __launch_bounds__(256)
+ema_cluster_partial_kernel(const float* __restrict__ counts, const float* __restrict__ cs, int K, float decay,
+                           float one_minus_decay, float* __restrict__ partial) {
+    __shared__ float sh[8];
     float part = 0.f;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        const float v = __fadd_rn(__fmul_rn(cs[k], decay), __fmul_rn(one_minus_decay, counts[k]));   // no FMA: torch rounds each op
-        cs[k] = v;
-        part += v;
-    }
+    const int per = (K + gridDim.x - 1) / gridDim.x;
+    const int k0 = blockIdx.x * per, k1 = min(K, k0 + per);
+    for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x)
+        part += __fadd_rn(__fmul_rn(cs[k], decay), __fmul_rn(one_minus_decay, counts[k]));   // no FMA: torch rounds each op
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
     __syncthreads();
     if (threadIdx.x < 32) {
-        float t = sh[threadIdx.x];
+        float t = threadIdx.x < 8 ? sh[threadIdx.x] : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) s_n = t;
+        if (threadIdx.x == 0) partial[blockIdx.x] = t;
     }
-    __syncthreads();
-    const float n = s_n;
-    const float denom = n + k_eps;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) cs[k] = __fmul_rn(__fdiv_rn(__fadd_rn(cs[k], eps), denom), n);
 }
 
-// One warp per codeword: ema_w and weight update plus the refreshed GEMM operand and |c|^2.
+// One warp per codeword: n = sum of the block partials (same fixed order in every warp),
+// cs <- (cs' + eps) / (n + K*eps) * n, ema_w and weight update, refreshed GEMM operand and |c|^2.
 __global__ void __launch_bounds__(256)
-ema_apply_rows_kernel(const float* __restrict__ sums, const float* __restrict__ cs, int K, int D, int Dp, int Kp, float decay,
-                      float one_minus_decay, float* __restrict__ ema_w, float* __restrict__ weight, __nv_bfloat16* __restrict__ cb,
-                      float* __restrict__ cnorm) {
+ema_apply_rows_kernel(const float* __restrict__ sums, const float* __restrict__ counts, const float* __restrict__ cluster_partial,
+                      int nblocks, int K, int D, int Dp, int Kp, float decay, float one_minus_decay, float eps, float k_eps,
+                      float* __restrict__ cs, float* __restrict__ ema_w, float* __restrict__ weight,
+                      __nv_bfloat16* __restrict__ cb, float* __restrict__ cnorm) {
     const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (k >= Kp) return;
     if (k >= K) { if (cnorm && lane == 0) cnorm[k] = CUDART_INF_F; return; }
-    const float size = cs[k];
+    float n = 0.f;
+    for (int b = 0; b < nblocks; ++b) n += __ldg(cluster_partial + b);
+    const float csp = __fadd_rn(__fmul_rn(cs[k], decay), __fmul_rn(one_minus_decay, counts[k]));
+    const float size = __fmul_rn(__fdiv_rn(__fadd_rn(csp, eps), n + k_eps), n);
+    __syncwarp();                     // every lane has read cs[k] before lane 0 overwrites it
+    if (lane == 0) cs[k] = size;
     float s = 0.f;
     for (int d = lane; d < Dp; d += 32) {
         float wv = 0.f;
@@ -250,12 +305,18 @@ int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, i
     float* sums = sums_counts;
     float* counts = sums_counts + (size_t)K * D;
 
-    ema_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const long long*>(idx), N, keys_in, vals_in);
-    size_t cub_bytes = l.cub_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)N, 0,
-                                                    key_bits(K), stream);
-    if (e != cudaSuccess) return (int)e;
-    ema_segments_kernel<<<(unsigned)((K + 1 + 255) / 256), 256, 0, stream>>>(keys_out, (int)N, (int)K, seg);
+    if (N <= kSmallSortMax) {
+        const int end_bit = key_bits(K) + 1;
+        ema_sort_small_kernel<8><<<1, 1024, 0, stream>>>(reinterpret_cast<const long long*>(idx), (int)N, (int)K, end_bit, keys_out,
+                                                        vals_out, seg);
+    } else {
+        ema_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const long long*>(idx), N, keys_in, vals_in);
+        size_t cub_bytes = l.cub_bytes;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)N, 0,
+                                                        key_bits(K), stream);
+        if (e != cudaSuccess) return (int)e;
+        ema_boundaries_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, stream>>>(keys_out, (int)N, (int)K, seg);
+    }
     const unsigned chunks = (unsigned)((N + kChunk - 1) / kChunk);
     const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_rows) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(sums_counts) & 15) == 0);
@@ -273,9 +334,9 @@ int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, i
 int pero_vq_ema_apply(const float* sums_counts, int64_t K, int64_t D, double decay, double epsilon, float* ema_w,
                       float* ema_cluster_size, float* weight, void* codebook, size_t codebook_bytes,
                       void* workspace, size_t workspace_bytes, pero_stream_t stream) {
-    (void)workspace; (void)workspace_bytes;
-    if (!sums_counts || !ema_w || !ema_cluster_size || !weight) return PERO_ERR_NULL;
-    if (K <= 0 || D <= 0 || K > (1ll << 20)) return PERO_ERR_BAD_SHAPE;
+    if (!sums_counts || !ema_w || !ema_cluster_size || !weight || !workspace) return PERO_ERR_NULL;
+    if (K <= 0 || D <= 0 || K > (1ll << 24)) return PERO_ERR_BAD_SHAPE;
+    if (workspace_bytes < align256(kClusterBlocks * 4)) return PERO_ERR_WORKSPACE;
     const CodebookLayout cl = codebook_layout(K, D);
     __nv_bfloat16* cb = nullptr;
     float* cnorm = nullptr;
@@ -287,14 +348,17 @@ int pero_vq_ema_apply(const float* sums_counts, int64_t K, int64_t D, double dec
     }
     const float* sums = sums_counts;
     const float* counts = sums_counts + (size_t)K * D;
+    float* cluster_partial = static_cast<float*>(workspace);
     // Python scalars of the reference are doubles that torch casts to fp32 per operand:
     // decay, (1 - decay), epsilon and K * epsilon are each rounded once, here on the host.
     const float decay_f = (float)decay, omd_f = (float)(1.0 - decay), eps_f = (float)epsilon,
                 keps_f = (float)((double)K * epsilon);
-    ema_cluster_size_kernel<<<1, 1024, 0, stream>>>(counts, (int)K, decay_f, omd_f, eps_f, keps_f, ema_cluster_size);
+    const int nblocks = (int)std::min<int64_t>(kClusterBlocks, (K + 255) / 256);
+    ema_cluster_partial_kernel<<<nblocks, 256, 0, stream>>>(counts, ema_cluster_size, (int)K, decay_f, omd_f, cluster_partial);
     const int rows = (int)(codebook ? cl.Kp : K);
-    ema_apply_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(sums, ema_cluster_size, (int)K, (int)D, (int)cl.Dp,
-                                                                         rows, decay_f, omd_f, ema_w, weight, cb, cnorm);
+    ema_apply_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(sums, counts, cluster_partial, nblocks, (int)K, (int)D,
+                                                                         (int)cl.Dp, rows, decay_f, omd_f, eps_f, keps_f,
+                                                                         ema_cluster_size, ema_w, weight, cb, cnorm);
     return (int)cudaGetLastError();
 }
 

@@ -120,10 +120,11 @@ def vq_ema_apply(sums_counts, ema_w, ema_cluster_size, weight, decay, epsilon, c
     for t, n in ((ema_w, "ema_w"), (ema_cluster_size, "ema_cluster_size"), (weight, "weight")):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise TypeError(f"{n} must be a contiguous CUDA float32 tensor")
+    ws = _ws(256, weight.device)
     check(_lib.lib().pero_vq_ema_apply(sums_counts.data_ptr(), K, D, float(decay), float(epsilon), ema_w.data_ptr(),
                                        ema_cluster_size.data_ptr(), weight.data_ptr(),
                                        None if codebook is None else codebook.blob.data_ptr(),
-                                       0 if codebook is None else codebook.nbytes, None, 0, _stream()),
+                                       0 if codebook is None else codebook.nbytes, ws.data_ptr(), ws.numel(), _stream()),
           "pero_vq_ema_apply")
 
 

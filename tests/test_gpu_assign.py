@@ -26,6 +26,8 @@ def _ops():
 def test_gemm_core_matches_matmul(cuda_dev, variant, shape):
     ops = _ops()
     ra, rb, kd = shape
+    if variant == 2 and kd > 256:
+        pytest.skip("plain-store epilogue (37 KB staging) + 128 KB resident A + 32 KB stages exceeds one CTA's shared memory")
     g = torch.Generator(device="cpu").manual_seed(ra * 7 + rb)
     a = torch.randn(ra, kd, generator=g).to(cuda_dev).bfloat16()
     b = torch.randn(rb, kd, generator=g).to(cuda_dev).bfloat16()
