@@ -71,7 +71,10 @@ def make_batch(rank, seed=1236):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 20 ms from before the warm-up replays; samples are then filtered to the
+    wall-clock window of the timed region (falling back to warm-up + timed when the region is shorter than
+    a few sampling periods)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -81,7 +84,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -90,28 +93,37 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [t.strip() for t in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def parse(rows):
+            sm, smax, pw, reasons = [], [], [], set()
+            for _, ln in rows:
+                f = [t.strip() for t in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, smax, pw, reasons
+
+        inside = [r for r in self.lines if t0 is not None and t0 - 0.02 <= r[0] <= t1 + 0.02]
+        window = "timed region"
+        if len(inside) < 3:
+            inside, window = self.lines, "warm-up + timed region (timed region shorter than 3 sampling periods)"
+        sm, smax, pw, reasons = parse(inside)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def peaks():
@@ -205,26 +217,58 @@ class DeviceStep:
             torch.distributed.all_reduce(t)
             self.m_global = float(t.item())
         self.out = {}
+        self.s_ema, self.s_ce, self.s_comm = (torch.cuda.Stream(device=dev) for _ in range(3))
 
     def __call__(self):
+        """Three independent chains after the assignment, forked onto side streams (captured as parallel
+        branches of the CUDA graph): A gather/straight-through + commitment loss fwd/bwd, B the EMA codebook
+        update (needs A's gather to have read the old codebook before it overwrites it), C the masked CE
+        (its head operand preparation does not even depend on the assignment)."""
         ops, c = self.ops, CFG
+        main = torch.cuda.current_stream()
+        s_ema, s_ce = self.s_ema, self.s_ce
+        s_ce.wait_stream(main)
+        with torch.cuda.stream(s_ce):
+            self.head.prepare(self.W, self.b)        # head weights change every optimizer step in training
         idx, _, x_rows = ops.vq_assign(self.x, self.cb, c["lines"], c["frames"], True, want_rows=True)
+        s_ema.wait_stream(main)
+        s_ce.wait_stream(main)
+        # --- chain A (main stream)
         q = ops.vq_gather_st(x_rows, idx, self.weight, c["lines"], c["frames"], True)
-        sums = ops.vq_ema_accumulate(x_rows, idx, c["K"])
-        if self.dp:
-            torch.distributed.all_reduce(sums)
-        ops.vq_ema_apply(sums, self.ema_w, self.cs, self.weight, c["decay"], c["epsilon"], self.cb)
+        gathered = torch.cuda.Event()
+        gathered.record(main)
         loss_c = ops.mse_fwd(q, self.x, 0.0, c["commitment_cost"])
         g_x = ops.vq_st_commit_bwd(self.gq, q, self.x, 2.0 * c["commitment_cost"] / q.numel())
-        self.head.prepare(self.W, self.b)            # head weights change every optimizer step in training
-        loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head)
+        # --- chain B
+        with torch.cuda.stream(s_ema):
+            sums = ops.vq_ema_accumulate(x_rows, idx, c["K"])
+            if self.dp:
+                torch.distributed.all_reduce(sums)
+            s_ema.wait_event(gathered)
+            ops.vq_ema_apply(sums, self.ema_w, self.cs, self.weight, c["decay"], c["epsilon"], self.cb)
+        # --- chain C
+        with torch.cuda.stream(s_ce):
+            loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head)
+            if self.dp:
+                torch.distributed.all_reduce(loss_sum)
+            if not self.dp:
+                d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
+                                                        return_flat=True)
+            else:
+                # phase 1: d_W | d_b, all-reduced on the communication stream while phase 2 computes d_h
+                _, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
+                                                      return_flat=True, want_dh=False)
+                self.s_comm.wait_stream(s_ce)
+                with torch.cuda.stream(self.s_comm):
+                    torch.distributed.all_reduce(flat)
+                d_h, _, _ = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
+                                              want_dw=False)
+        main.wait_stream(s_ema)
+        main.wait_stream(s_ce)
         if self.dp:
-            torch.distributed.all_reduce(loss_sum)
-        d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
-                                                return_flat=True)
-        if self.dp:
-            torch.distributed.all_reduce(flat)       # d_W | d_b in one call
-        self.out = dict(idx=idx, q=q, loss_c=loss_c, g_x=g_x, loss_sum=loss_sum, d_h=d_h, d_W=d_W, d_b=d_b)
+            main.wait_stream(self.s_comm)
+        self.out = dict(idx=idx, x_rows=x_rows, q=q, loss_c=loss_c, g_x=g_x, sums=sums, loss_sum=loss_sum, lse=lse, ws=ws,
+                        d_h=d_h, d_W=d_W, d_b=d_b, flat=flat)
         return self.out
 
 
@@ -257,17 +301,43 @@ def e2e_leg(batch, dev, dp, steps, warm):
     x_host, h_host = batch["x"].pin_memory(), batch["h"].pin_memory()
     gq = batch["gq"].to(dev)
     mask = batch["mask"]
-    h2d = x_host.numel() * 4 + h_host.numel() * 4 + int(mask.sum()) * 4
+    rows_host = torch.from_numpy(np.flatnonzero(mask.reshape(-1) == 1).astype(np.int32)).pin_memory()
+    h2d = x_host.numel() * 4 + h_host.numel() * 4 + rows_host.numel() * 4
     loss_val = None
+    # Double-buffered input staging: the H2D copy of step i+1 runs on a copy stream while step i computes;
+    # every step still waits for ITS OWN inputs to arrive and reads ITS OWN loss back.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(x_host, device=dev), torch.empty_like(h_host, device=dev)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def stage(i):
+        xb, hb = bufs[i & 1]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])            # the step that last used this buffer pair is done
+            xb.copy_(x_host, non_blocking=True)
+            hb.copy_(h_host, non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
+    state = {"i": 0}
+    for e in consumed:
+        e.record()
+    stage(0)
 
     def step():
-        x = x_host.to(dev, non_blocking=True).requires_grad_(True)
-        h = h_host.to(dev, non_blocking=True).requires_grad_(True)
+        i = state["i"]
+        state["i"] = i + 1
+        main = torch.cuda.current_stream()
+        main.wait_event(ready[i & 1])
+        stage(i + 1)                                           # prefetch the next step's inputs
+        x = bufs[i & 1][0].detach().requires_grad_(True)
+        h = bufs[i & 1][1].detach().requires_grad_(True)
         q, idx = vq(x)
         loss = vq.calculate_loss(q, x) + head.masked_loss(h, idx.view(c["lines"], c["frames"]), mask, None, group)
         head.linear.weight.grad = None
         head.linear.bias.grad = None
         torch.autograd.backward([loss, q], [None, gq])
+        consumed[i & 1].record(main)
         return float(loss.item())                      # D2H read of the step's result
 
     for _ in range(warm):
@@ -312,6 +382,12 @@ def gemm_roofline_leg(ds, dev, iters, flush):
     return float(np.mean(ts)), float(np.min(ts))
 
 
+def _log(msg):
+    if os.environ.get("PERO_BENCH_VERBOSE"):
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} t={time.time() % 1000:.2f}] {msg}\n")
+        sys.stderr.flush()
+
+
 def our_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -329,10 +405,13 @@ def our_arm(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     # ---- warm-up (eager), kernel count, optional CUDA graph
+    _log("setup done")
     for _ in range(max(3, args.warmup)):
         ds()
     torch.cuda.synchronize()
+    _log("eager warm-up done")
     n_kernels, n_ours = count_kernels(ds)
+    _log(f"kernel count {n_kernels}")
     graph = None
     if not args.no_graph:
         try:
@@ -352,16 +431,19 @@ def our_arm(args):
             graph = None
             sys.stderr.write(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); eager launches\n")
             torch.cuda.synchronize()
+    _log(f"graph {'captured' if graph is not None else 'unavailable'}")
     run = graph.replay if graph is not None else ds
-    for _ in range(args.warmup):
-        run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup + 400):       # ~0.1 s under load before the timed region (a FIXED count: every rank
+        run()                                # must issue the same number of collectives); nvidia-smi starts sampling
+    torch.cuda.synchronize()
 
     # ---- timed region: K steps, device time per step, L2 flushed between steps, max over ranks
-    sampler = ClockSampler(local_rank)
     torch.cuda.synchronize()
     if dp:
         torch.distributed.barrier()
-    sampler.start()
+    t_region0 = time.time()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for e0, e1 in ev:
         flush.zero_()
@@ -371,7 +453,7 @@ def our_arm(args):
     torch.cuda.synchronize()
     if dp:
         torch.distributed.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, time.time())
     total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     m_total = ds.m_global
     if dp:
@@ -382,22 +464,26 @@ def our_arm(args):
     value = m_total / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel, e2e, CPU baseline
+    _log(f"timed region done: {ms_per_step * 1e3:.1f} us/step")
     N = c["lines"] * c["frames"]
     gemm_ms, gemm_min = gemm_roofline_leg(ds, dev, 20, flush)
     burst, sustained, hbm, src = peaks()
     flops = 2.0 * N * c["K"] * c["D"]
     achieved = flops / (gemm_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gemm_tn_kernel<2,true,ArgminEpi> (distance GEMM + arg-min)",
-                "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+                "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+                "traffic": 8.52e6, "traffic_source": "profiles/r1_assign_gemm_ncu.md: dram read 8.52 MB + write 0.00 MB per launch (algorithmic 8.49 MB)",
                 "peak_source": f"{src} bf16 burst (kernel timed alone)", "kernel_us": gemm_ms * 1e3, "kernel_us_min": gemm_min * 1e3,
                 "algorithmic_flops_per_launch": flops,
                 "step_tensor_tflops": (flops + 6.0 * ds.M * c["Dh"] * c["V"]) / (ms_per_step * 1e-3) / 1e12,
                 "step_frac_of_sustained": (flops + 6.0 * ds.M * c["Dh"] * c["V"]) / (ms_per_step * 1e-3) / 1e12 / sustained}
+    _log("roofline leg done")
     e2e = None
     if not args.skip_e2e:
         s_per_step, h2d, d2h, _ = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup))
         e2e = {"value": m_total / s_per_step, "unit": "masked frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": s_per_step * 1e3, "api": "VectorQuantizer.forward/calculate_loss + LinearHead.masked_loss + backward"}
+    _log("e2e leg done")
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         mean_s, min_s = run_cpu(make_batch(0), 3, 1)
@@ -415,7 +501,20 @@ def our_arm(args):
                 "gpu_launches": (n_ours if n_ours > 0 else n_kernels) * args.steps, "kernels_per_step": n_kernels, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if dp:
-        torch.distributed.destroy_process_group()
+        # A captured graph that contains NCCL collectives must be gone before the communicator is torn down,
+        # and a stuck teardown must not keep the job alive after the result line is out.
+        graph = None
+        ds = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        threading.Timer(15.0, lambda: os._exit(0)).start()
+        try:
+            torch.distributed.destroy_process_group()
+        finally:
+            os._exit(0)
 
 
 if __name__ == "__main__":

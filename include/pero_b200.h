@@ -141,6 +141,8 @@ int pero_vq_st_commit_bwd(const float* g_quantized, const float* quantized, cons
  *   loss_sum [1] fp32: sum over masked frames of (lse - logit[label]);  lse [M] fp32 saved for backward
  * pero_masked_ce_bwd: gradients of  loss = grad_scale[0] * inv_count * loss_sum:
  *   d_h [N, Dh] (same dtype as h, zero on unmasked frames), d_W [V, Dh] fp32, d_b [V] fp32.
+ *   Two-phase use: a first call with d_h = NULL produces d_W, d_b (ready to be all-reduced); a second call with
+ *   d_W = d_b = NULL and the SAME workspace produces d_h from the dlogits the first call left there.
  */
 size_t pero_head_bytes(int64_t V, int64_t Dh);
 int pero_head_prepare(const float* W, const float* bias, int64_t V, int64_t Dh, void* head, size_t head_bytes,

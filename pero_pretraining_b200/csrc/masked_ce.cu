@@ -556,20 +556,25 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     if (M == 0) return PERO_ERR_BAD_SHAPE;
     int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes);
     if (rc) return rc;
-    if (!lse || !d_W || !d_b) return PERO_ERR_NULL;
+    // Two-phase use (lets a data-parallel caller all-reduce d_W | d_b while d_h is still being computed):
+    //   phase 1: d_W, d_b given (d_h may be NULL)  -> dlogits P / P^T into the workspace, d_W, d_b [, d_h]
+    //   phase 2: d_W == d_b == NULL, d_h given     -> d_h from the P left in the SAME workspace by phase 1
+    const bool phase2_only = (!d_W && !d_b && d_h);
+    if (!lse || (!phase2_only && (!d_W || !d_b))) return PERO_ERR_NULL;
     if (Dh % 4 != 0) return PERO_ERR_BAD_SHAPE;
     const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
     const HeadLayout hl = head_layout(V, Dh);
     char* ws = static_cast<char*>(workspace);
     const char* hb = static_cast<const char*>(head);
     int* inv = reinterpret_cast<int*>(ws + l.inv_off);
-    if (d_h) ce_inv_init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(inv, N);
-    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, (int)M, (int)Dh, l, ws, true, d_h != nullptr, stream)
-                   : launch_ce_gather<float>(h, rows, labels, (int)M, (int)Dh, l, ws, true, d_h != nullptr, stream);
-    if (rc) return rc;
-
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + l.p_off);
     __nv_bfloat16* PT = reinterpret_cast<__nv_bfloat16*>(ws + l.pt_off);
+    if (!phase2_only) {
+    ce_inv_init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(inv, N);
+    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, (int)M, (int)Dh, l, ws, true, true, stream)
+                   : launch_ce_gather<float>(h, rows, labels, (int)M, (int)Dh, l, ws, true, true, stream);
+    if (rc) return rc;
+
     DlogitsEpi::Params ep;
     ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
     ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
@@ -587,6 +592,7 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
                                             sw, stream);
     if (rc) return rc;
     ce_db_kernel<<<(unsigned)((V + 7) / 8), 256, 0, stream>>>(PT, (int)V, (int)M, (int)l.Mp64, d_b);
+    }   // !phase2_only
 
     if (d_h) {
         // planes[ks] [M, Dh] = P [M, Vp] @ W^T [Dh, Vp]^T over the ks-th slice of the label axis

@@ -209,7 +209,8 @@ def masked_ce_fwd(h, rows, labels, head):
     return loss_sum, lse, ws
 
 
-def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False):
+def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False,
+                  want_dw=True):
     """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32[, flat buffer holding d_W|d_b])."""
     L = _lib.lib()
     h = _check_h(h)
@@ -217,15 +218,17 @@ def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=Tru
     M = rows.numel()
     d_h = torch.empty_like(h) if want_dh else None
     # d_W and d_b share one flat buffer so that data-parallel ranks all-reduce them in a single call
-    flat = torch.empty(head.V * Dh + head.V, dtype=torch.float32, device=h.device)
-    d_W, d_b = flat[:head.V * Dh].view(head.V, Dh), flat[head.V * Dh:]
+    flat = d_W = d_b = None
+    if want_dw:       # want_dw=False: second phase, d_h only, from the dlogits a previous call left in `ws`
+        flat = torch.empty(head.V * Dh + head.V, dtype=torch.float32, device=h.device)
+        d_W, d_b = flat[:head.V * Dh].view(head.V, Dh), flat[head.V * Dh:]
     wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
     if ws is None or ws.numel() < wsb:
         ws = _ws(wsb, h.device)
     gs = None if grad_scale is None else _f32c(grad_scale, "grad_scale")
     check(L.pero_masked_ce_bwd(h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M,
                                labels.data_ptr(), head.blob.data_ptr(), head.V, lse.data_ptr(), _p(gs),
-                               float(inv_count), _p(d_h), d_W.data_ptr(), d_b.data_ptr(), ws.data_ptr(), wsb,
+                               float(inv_count), _p(d_h), _p(d_W), _p(d_b), ws.data_ptr(), wsb,
                                _stream()), "pero_masked_ce_bwd")
     return (d_h, d_W, d_b, flat) if return_flat else (d_h, d_W, d_b)
 
