@@ -13,6 +13,24 @@ import torch
 from . import ops
 
 
+_PINNED_RING = {"bufs": [], "next": 0}
+
+
+def _pinned_rows(rows, ring=8):
+    """Copy `rows` (numpy int32) into one of `ring` reusable pinned host buffers and return the view.
+    A buffer is reused only `ring` calls later, long after the asynchronous copy that read it."""
+    st = _PINNED_RING
+    if len(st["bufs"]) < ring:
+        st["bufs"] = [torch.empty(max(4096, rows.size), dtype=torch.int32).pin_memory() for _ in range(ring)]
+    i = st["next"]
+    st["next"] = (i + 1) % ring
+    if st["bufs"][i].numel() < rows.size:
+        st["bufs"][i] = torch.empty(int(rows.size * 1.5) + 16, dtype=torch.int32).pin_memory()
+    buf = st["bufs"][i][:rows.size]
+    buf.numpy()[:] = rows
+    return buf
+
+
 def _rows_from_mask(mask, labels, want, require_label, device):
     """Ordered int32 frame indices with mask == want.  A numpy mask (what BatchOperator._create_mask
     returns, batch_operator.py:27-32) is compacted on the host: M is known without a device sync.  A tensor
@@ -23,7 +41,12 @@ def _rows_from_mask(mask, labels, want, require_label, device):
             lab = labels.detach().cpu().numpy().reshape(-1) if isinstance(labels, torch.Tensor) else np.asarray(labels).reshape(-1)
             sel = sel & (lab >= 0)
         rows = np.flatnonzero(sel).astype(np.int32)
-        return torch.from_numpy(rows).to(device, non_blocking=True), int(rows.size)
+        if device.type != "cuda":
+            return torch.from_numpy(rows), int(rows.size)
+        # A pageable-memory H2D copy blocks the host until everything already queued on the stream has
+        # run; staging through a small ring of pinned buffers keeps the copy asynchronous.
+        staged = _pinned_rows(rows)
+        return staged.to(device, non_blocking=True), int(rows.size)
     mask = mask.to(device)
     rows, count = ops.mask_compact(mask, labels if require_label else None, want)
     m = int(count.item())
