@@ -14,7 +14,7 @@ One "step" = one pass of the hot path over one synthetic batch (BASELINE.json co
 `roofline`: the dominant kernel (distance GEMM + arg-min) timed alone with CUDA events.
 `cpu_baseline`: the oracle port of the reference path on this box's host cores (rank 0, N=1 only).
 Multi-GPU: weak scaling, batch-sharded (every rank owns 64 lines), codebook/head replicated, EMA sums|counts
-and head gradients all-reduced over NCCL inside the step.
+and head gradients|loss reduced in place inside the step by the library's peer-memory kernel (NVSwitch multimem).
 """
 import argparse
 import json
@@ -218,6 +218,18 @@ class DeviceStep:
             self.m_global = float(t.item())
         self.out = {}
         self.s_ema, self.s_ce, self.s_comm = (torch.cuda.Stream(device=dev) for _ in range(3))
+        # Data-parallel exchange ranges (EMA sums|counts and d_W|d_b|loss_sum) live in a peer-mapped buffer and
+        # are reduced in place by the library's own NVLink/NVSwitch kernel.
+        self.peer = self.ema_x = self.grad_x = None
+        self.n_ema = c["K"] * c["D"] + c["K"]
+        self.n_grad = c["V"] * c["Dh"] + c["V"]
+        if dp:
+            from pero_pretraining_b200.peer import PeerBuffer, PeerRange
+            blocks = int(os.environ.get("PERO_PEER_BLOCKS", "24"))
+            self.peer = PeerBuffer(4 * (self.n_ema + self.n_grad) + 4096, dev, n_blocks=blocks,
+                                   use_multicast=os.environ.get("PERO_PEER_MULTICAST", "1") != "0")
+            self.ema_x = PeerRange(self.peer, self.n_ema, torch.float32)
+            self.grad_x = PeerRange(self.peer, self.n_grad + 1, torch.float32)
 
     def __call__(self):
         """Three independent chains after the assignment, forked onto side streams (captured as parallel
@@ -241,26 +253,33 @@ class DeviceStep:
         g_x = ops.vq_st_commit_bwd(self.gq, q, self.x, 2.0 * c["commitment_cost"] / q.numel())
         # --- chain B
         with torch.cuda.stream(s_ema):
-            sums = ops.vq_ema_accumulate(x_rows, idx, c["K"])
-            if self.dp:
-                torch.distributed.all_reduce(sums)
+            if not self.dp:
+                sums = ops.vq_ema_accumulate(x_rows, idx, c["K"])
+            else:
+                # both exchanges run on ONE communication stream, in the same order on every rank
+                sums = ops.vq_ema_accumulate(x_rows, idx, c["K"], out=self.ema_x.tensor)
+                self.s_comm.wait_stream(s_ema)
+                with torch.cuda.stream(self.s_comm):
+                    self.ema_x.all_reduce_sum_()
+                s_ema.wait_stream(self.s_comm)
             s_ema.wait_event(gathered)
             ops.vq_ema_apply(sums, self.ema_w, self.cs, self.weight, c["decay"], c["epsilon"], self.cb)
         # --- chain C
         with torch.cuda.stream(s_ce):
-            loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head)
-            if self.dp:
-                torch.distributed.all_reduce(loss_sum)
             if not self.dp:
+                loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head)
                 d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
                                                         return_flat=True)
             else:
-                # phase 1: d_W | d_b, all-reduced on the communication stream while phase 2 computes d_h
+                # loss_sum rides in the same exchange range as d_W | d_b.  Phase 1 produces d_W | d_b, which are
+                # reduced over the ranks on the communication stream while phase 2 computes d_h.
+                g = self.grad_x.tensor
+                loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head, loss_out=g[self.n_grad:])
                 _, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
-                                                      return_flat=True, want_dh=False)
+                                                      return_flat=True, want_dh=False, flat_out=g[:self.n_grad])
                 self.s_comm.wait_stream(s_ce)
                 with torch.cuda.stream(self.s_comm):
-                    torch.distributed.all_reduce(flat)
+                    self.grad_x.all_reduce_sum_()
                 d_h, _, _ = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
                                               want_dw=False)
         main.wait_stream(s_ema)
@@ -297,7 +316,8 @@ def e2e_leg(batch, dev, dp, steps, warm):
         head.linear.weight.copy_(batch["W"]); head.linear.bias.copy_(batch["b"])
     group = torch.distributed.group.WORLD if dp else None
     if dp:
-        vq.enable_data_parallel(group)
+        vq.enable_data_parallel(group)          # peer-memory exchange of the EMA sums|counts
+        head.enable_peer_exchange(group)        # ... and of d_W | d_b
     x_host, h_host = batch["x"].pin_memory(), batch["h"].pin_memory()
     gq = batch["gq"].to(dev)
     mask = batch["mask"]
@@ -496,6 +516,7 @@ def our_arm(args):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, **{k: c[k] for k in ("lines", "frames", "K", "D", "Dh", "V", "p")},
                            "masked_frames_per_step": m_total, "frames_per_step": N * world, "parallelism": f"dp{world}" if dp else "single",
+                           "exchange": (f"libpero peer all-reduce ({ds.peer.transport}, {ds.peer.n_blocks} CTAs)" if dp else None),
                            "l2": "flushed (256 MiB write) between timed steps", "launch": "cuda_graph" if graph is not None else "eager"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": (n_ours if n_ours > 0 else n_kernels) * args.steps, "kernels_per_step": n_kernels, "clocks": clocks}

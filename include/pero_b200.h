@@ -173,6 +173,35 @@ int pero_mask_compact(const void* mask, int mask_dtype, int want_value, const in
                       int32_t* rows, int32_t* count, void* workspace, size_t workspace_bytes,
                       pero_stream_t stream);
 
+/* ------------------------------------------------------------------ peer-memory collectives (NVLink 5 / NVSwitch)
+ * The reference is single-process; these are the two exchange steps of the sharded path:
+ *   batch-sharded    SUM of the EMA buffer [K*D + K] between pero_vq_ema_accumulate and pero_vq_ema_apply
+ *                    (models/autoencoders.py:225-237 evaluated on the concatenated batch) and of the head
+ *                    gradients d_W | d_b | loss_sum (masked_pretraining/model.py:78-82 on the concatenated batch);
+ *   codebook-sharded MIN of the packed (distance, index) winners (models/autoencoders.py:217 argmin over all K).
+ * Every rank owns one peer buffer of the same size which every rank has mapped: peer_bufs is a DEVICE array of
+ * `world` base pointers (entry r = rank r's buffer, entry `rank` = the local one).  The first
+ * PERO_PEER_HEADER_BYTES of every buffer are flag words owned by the library and must be zero before the
+ * first call; payload ranges live at offset_bytes >= PERO_PEER_HEADER_BYTES (16-byte aligned, the same offset
+ * on every rank) and are reduced IN PLACE: on return (in stream order) every rank's range holds the same bits.
+ * multicast_base: the NVSwitch multicast alias of the buffers (switch-side reduction, multimem.ld_reduce /
+ * multimem.st) or NULL (peer loads summed in rank order + peer stores).  One kernel per call, n_blocks CTAs
+ * (1..PERO_PEER_MAX_BLOCKS; 16-32 saturate NVLink and leave the other SMs to the GEMMs running beside it);
+ * all ranks must issue the same sequence of calls with the same n_blocks.  n_elems % 4 == 0 (f32) / % 2 == 0 (i64).
+ * A rank that does not arrive within ~4 s makes the waiting kernels trap (sticky CUDA error) instead of hanging.
+ * pero_peer_allreduce_emulate: the same protocol with all `world` buffers on ONE device and the ranks played
+ * by blockIdx.y of one cooperative launch (op 0 = f32 sum, 1 = i64 min) — single-GPU test of the protocol only.
+ */
+#define PERO_PEER_HEADER_BYTES 16384
+#define PERO_PEER_MAX_WORLD 16
+#define PERO_PEER_MAX_BLOCKS 64
+int pero_peer_allreduce_sum_f32(void* const* peer_bufs, void* multicast_base, int rank, int world, int64_t offset_bytes,
+                                int64_t n_elems, int n_blocks, pero_stream_t stream);
+int pero_peer_allreduce_min_i64(void* const* peer_bufs, void* multicast_base, int rank, int world, int64_t offset_bytes,
+                                int64_t n_elems, int n_blocks, pero_stream_t stream);
+int pero_peer_allreduce_emulate(void* const* bufs_on_one_device, int world, int op, int64_t offset_bytes, int64_t n_elems,
+                                int n_blocks, pero_stream_t stream);
+
 /* ------------------------------------------------------------------ test hook
  * C[rows_a, rows_b] = A @ B^T through the same tcgen05 core (bf16 operands with row pitch `kd`,
  * fp32 out).  variant: bit0 = CTA pairs (cta_group::2), bit1 = resident A.  Used by tests only. */

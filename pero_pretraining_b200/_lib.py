@@ -52,6 +52,9 @@ SIGNATURES = {
     "pero_ce_logits_bwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_int, c_vp, c_vp]),
     "pero_mask_compact_workspace_bytes": (c_sz, [c_i64]),
     "pero_mask_compact": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pero_peer_allreduce_sum_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
+    "pero_peer_allreduce_min_i64": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
+    "pero_peer_allreduce_emulate": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "pero_debug_set_timeline": (c_int, [c_vp]),
     "pero_debug_gemm_tn": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
 }

@@ -34,9 +34,13 @@ class _QuantizeST(torch.autograd.Function):
         weight = vq.embedding.weight.data
         out = ops.vq_gather_st(x_rows, idx, weight, n_lines, frames, channels_first=True)
         if update and idx.numel() > 0:
-            sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings)
-            if vq._dp_group is not None:
-                torch.distributed.all_reduce(sums_counts, group=vq._dp_group)   # [K, D+1] SUM over ranks
+            if vq._peer_range is not None:      # [K, D+1] SUM over ranks, in place in the peer-mapped range
+                sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings, out=vq._peer_range.tensor)
+                vq._peer_range.all_reduce_sum_()
+            else:
+                sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings)
+                if vq._dp_group is not None:
+                    torch.distributed.all_reduce(sums_counts, group=vq._dp_group)
             ops.vq_ema_apply(sums_counts, vq.ema_w.data, vq.ema_cluster_size, weight, vq.decay, vq.epsilon, cb)
             vq._codebook_tag = vq._weight_tag()
         ctx.mark_non_differentiable(idx)
@@ -97,12 +101,22 @@ class VectorQuantizer(torch.nn.Module):
         self._codebook = None         # derived cache (bf16 operand, |c|^2): non-persistent, rebuilt on demand
         self._codebook_tag = None
         self._dp_group = None
+        self._peer_range = None
 
     # -- data parallel: batch-sharded frames, replicated codebook, EMA sums/counts all-reduced
-    def enable_data_parallel(self, group=None):
+    def enable_data_parallel(self, group=None, peer=True):
+        """peer=True: the EMA sums|counts are exchanged by libpero_b200's own NVLink/NVSwitch kernel through a
+        peer-mapped buffer (pero_peer_allreduce_sum_f32); peer=False: torch.distributed.all_reduce (NCCL, or
+        gloo in the CPU tests of the semantics)."""
         if not torch.distributed.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self._dp_group = group if group is not None else torch.distributed.group.WORLD
+        self._peer_range = None
+        if peer:
+            from .peer import PeerBuffer, PeerRange
+            n = self.num_embeddings * self.embeddings_dim + self.num_embeddings
+            buf = PeerBuffer(4 * n + 256, self.embedding.weight.device, self._dp_group)
+            self._peer_range = PeerRange(buf, n, torch.float32)
         return self
 
     def _weight_tag(self):

@@ -1,0 +1,295 @@
+// Peer-memory collectives of the two exchange steps of the path, over NVLink 5 / NVSwitch:
+//   * SUM all-reduce of fp32 ranges (EMA sums|counts, head gradients d_W|d_b|loss) — batch-sharded mode,
+//   * MIN all-reduce of the packed (distance, index) int64 winners — codebook-sharded mode.
+// Every rank owns one "peer buffer" of identical size that all ranks have mapped (peer pointers) and, when
+// the NVSwitch multicast object exists, a multicast alias of it.  A collective is ONE kernel per rank:
+//
+//   barrier (all ranks' producers are done)  ->  rank r reduces slice r  ->  writes it to every rank
+//   -> barrier (every slice has landed everywhere).
+//
+// Slice reduction: `multimem.ld_reduce` (the switch adds the replicas, the reducing GPU receives one copy)
+// followed by `multimem.st` (the switch replicates the store) when a multicast alias is given; otherwise
+// plain peer loads summed in rank order 0..g-1 and peer stores.  Either way each element is reduced exactly
+// once, by its owner, and the same bits are delivered to every rank, so replicated state stays bit-identical.
+//
+// Barriers are CAS handshakes on flag words in the first PERO_PEER_HEADER_BYTES of each buffer
+// ([block][source rank] u32, 0 when idle); they reset themselves, so the kernels are CUDA-graph replayable.
+// A rank that never arrives makes the waiters trap after ~4 s instead of hanging the GPU.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pero_b200.h"
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kMaxWorld = PERO_PEER_MAX_WORLD;
+constexpr int kMaxBlocks = PERO_PEER_MAX_BLOCKS;
+constexpr unsigned long long kTimeoutNs = 4000000000ull;
+static_assert(kMaxWorld * kMaxBlocks * 4 <= PERO_PEER_HEADER_BYTES, "flag words must fit the buffer header");
+
+__device__ __forceinline__ uint32_t cas_release_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All threads of block `blk` on every rank meet here.  Thread t < world raises flag [blk][rank] on rank t and
+// consumes flag [blk][t] on its own rank; release/acquire at system scope order the block's earlier peer
+// stores before the flag and the later peer loads after it.
+__device__ __forceinline__ void rank_barrier(void* const* bufs, int rank, int world, int blk) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < world) {
+        uint32_t* remote = reinterpret_cast<uint32_t*>(bufs[t]) + blk * kMaxWorld + rank;
+        uint32_t* local = reinterpret_cast<uint32_t*>(bufs[rank]) + blk * kMaxWorld + t;
+        const unsigned long long t0 = now_ns();
+        while (cas_release_sys(remote, 0u, 1u) != 0u)
+            if (now_ns() - t0 > kTimeoutNs) __trap();
+        while (cas_acquire_sys(local, 1u, 0u) != 1u)
+            if (now_ns() - t0 > kTimeoutNs) __trap();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float4 mc_ld_reduce_add(const char* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(char* p, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ long long mc_ld_reduce_min(const char* p) {
+    long long v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.min.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(char* p, long long v) {
+    asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ float4 peer_ld(const float4* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void peer_st(float4* p, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ longlong2 peer_ld(const longlong2* p) {
+    longlong2 v;
+    asm volatile("ld.relaxed.sys.global.v2.s64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void peer_st(longlong2* p, longlong2 v) {
+    asm volatile("st.relaxed.sys.global.v2.s64 [%0], {%1, %2};" :: "l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+
+struct SumF32 {
+    using Vec = float4;
+    static __device__ __forceinline__ Vec combine(Vec a, Vec b) {
+        return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+    }
+};
+struct MinI64 {
+    using Vec = longlong2;
+    static __device__ __forceinline__ Vec combine(Vec a, Vec b) {
+        return make_longlong2(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y);
+    }
+};
+
+struct Range { int64_t lo, hi; };
+// Contiguous slice of `total` 16-byte vectors owned by `rank` (remainder spread over the first ranks).
+__device__ __forceinline__ Range slice_of(int64_t total, int world, int rank) {
+    const int64_t base = total / world, rem = total % world;
+    Range r;
+    r.lo = rank * base + (rank < rem ? rank : rem);
+    r.hi = r.lo + base + (rank < rem ? 1 : 0);
+    return r;
+}
+
+// Peer-pointer variant.  kWorld > 0 keeps all kWorld loads of a vector in flight at once (registers);
+// kWorld == 0 is the generic loop.  With kEmulate the rank is blockIdx.y: g "ranks" of ONE cooperative launch
+// on one GPU (the single-GPU test of the protocol, never the product path).
+template <class Op, int kWorld, bool kEmulate>
+__global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(void* const* __restrict__ bufs, int rank_arg, int world_arg,
+                                                                  int64_t off_bytes, int64_t nvec) {
+    using Vec = typename Op::Vec;
+    const int world = kWorld > 0 ? kWorld : world_arg;
+    const int rank = kEmulate ? (int)blockIdx.y : rank_arg;
+    rank_barrier(bufs, rank, world, blockIdx.x);
+    const Range r = slice_of(nvec, world, rank);
+    constexpr int U = 2;
+    const int64_t step = (int64_t)gridDim.x * kThreads * U;
+    for (int64_t base = r.lo + (int64_t)blockIdx.x * kThreads * U; base < r.hi; base += step) {
+        Vec acc[U];
+        if (kWorld > 0) {
+            Vec v[U][kWorld > 0 ? kWorld : 1];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = base + u * kThreads + threadIdx.x;
+                if (i < r.hi) {
+#pragma unroll
+                    for (int p = 0; p < kWorld; ++p)
+                        v[u][p] = peer_ld(reinterpret_cast<const Vec*>(static_cast<const char*>(bufs[p]) + off_bytes) + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                acc[u] = v[u][0];
+#pragma unroll
+                for (int p = 1; p < kWorld; ++p) acc[u] = Op::combine(acc[u], v[u][p]);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = base + u * kThreads + threadIdx.x;
+                if (i < r.hi) {
+                    acc[u] = peer_ld(reinterpret_cast<const Vec*>(static_cast<const char*>(bufs[0]) + off_bytes) + i);
+                    for (int p = 1; p < world; ++p)
+                        acc[u] = Op::combine(acc[u], peer_ld(reinterpret_cast<const Vec*>(static_cast<const char*>(bufs[p]) + off_bytes) + i));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kThreads + threadIdx.x;
+            if (i < r.hi) {
+                for (int p = 0; p < world; ++p)
+                    peer_st(reinterpret_cast<Vec*>(static_cast<char*>(bufs[p]) + off_bytes) + i, acc[u]);
+            }
+        }
+    }
+    rank_barrier(bufs, rank, world, blockIdx.x);
+}
+
+// Multicast variant: the switch reduces on load and replicates on store.
+__global__ void __launch_bounds__(kThreads) mc_allreduce_sum_f32_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
+                                                                        int world, int64_t off_bytes, int64_t nvec) {
+    rank_barrier(bufs, rank, world, blockIdx.x);
+    const Range r = slice_of(nvec, world, rank);
+    constexpr int U = 8;
+    char* base_ptr = mc + off_bytes;
+    const int64_t step = (int64_t)gridDim.x * kThreads * U;
+    for (int64_t base = r.lo + (int64_t)blockIdx.x * kThreads * U; base < r.hi; base += step) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kThreads + threadIdx.x;
+            if (i < r.hi) v[u] = mc_ld_reduce_add(base_ptr + i * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kThreads + threadIdx.x;
+            if (i < r.hi) mc_st(base_ptr + i * 16, v[u]);
+        }
+    }
+    rank_barrier(bufs, rank, world, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kThreads) mc_allreduce_min_i64_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
+                                                                        int world, int64_t off_bytes, int64_t n) {
+    rank_barrier(bufs, rank, world, blockIdx.x);
+    const Range r = slice_of(n, world, rank);
+    constexpr int U = 8;
+    char* base_ptr = mc + off_bytes;
+    const int64_t step = (int64_t)gridDim.x * kThreads * U;
+    for (int64_t base = r.lo + (int64_t)blockIdx.x * kThreads * U; base < r.hi; base += step) {
+        long long v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kThreads + threadIdx.x;
+            if (i < r.hi) v[u] = mc_ld_reduce_min(base_ptr + i * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kThreads + threadIdx.x;
+            if (i < r.hi) mc_st(base_ptr + i * 8, v[u]);
+        }
+    }
+    rank_barrier(bufs, rank, world, blockIdx.x);
+}
+
+int check_args(void* const* peer_bufs, int rank, int world, int64_t off_bytes, int64_t n, int64_t per_vec, int n_blocks) {
+    if (!peer_bufs) return PERO_ERR_NULL;
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n < 0) return PERO_ERR_BAD_SHAPE;
+    if (n_blocks < 1 || n_blocks > kMaxBlocks) return PERO_ERR_BAD_SHAPE;
+    if (off_bytes < PERO_PEER_HEADER_BYTES || (off_bytes & 15) || (n % per_vec)) return PERO_ERR_BAD_ALIGN;
+    return PERO_OK;
+}
+
+template <class Op, bool kEmulate>
+cudaError_t launch_peer(void* const* bufs, int rank, int world, int64_t off, int64_t nvec, int n_blocks, cudaStream_t s) {
+    dim3 grid(n_blocks, kEmulate ? world : 1);
+    void* args[] = {(void*)&bufs, (void*)&rank, (void*)&world, (void*)&off, (void*)&nvec};
+    const void* fn;
+    switch (world) {
+        case 2: fn = (const void*)peer_allreduce_kernel<Op, 2, kEmulate>; break;
+        case 4: fn = (const void*)peer_allreduce_kernel<Op, 4, kEmulate>; break;
+        case 8: fn = (const void*)peer_allreduce_kernel<Op, 8, kEmulate>; break;
+        default: fn = (const void*)peer_allreduce_kernel<Op, 0, kEmulate>; break;
+    }
+    // The emulated ranks spin on one another inside one grid: a cooperative launch guarantees co-residency.
+    return kEmulate ? cudaLaunchCooperativeKernel(fn, grid, dim3(kThreads), args, 0, s)
+                    : cudaLaunchKernel(fn, grid, dim3(kThreads), args, 0, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pero_peer_allreduce_sum_f32(void* const* peer_bufs, void* multicast_base, int rank, int world, int64_t offset_bytes,
+                                int64_t n_elems, int n_blocks, pero_stream_t stream) {
+    int rc = check_args(peer_bufs, rank, world, offset_bytes, n_elems, 4, n_blocks);
+    if (rc != PERO_OK) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (world == 1 || n_elems == 0) return PERO_OK;
+    const int64_t nvec = n_elems / 4;
+    if (multicast_base) {
+        mc_allreduce_sum_f32_kernel<<<n_blocks, kThreads, 0, s>>>(peer_bufs, static_cast<char*>(multicast_base), rank, world,
+                                                                 offset_bytes, nvec);
+        return (int)cudaGetLastError();
+    }
+    return (int)launch_peer<SumF32, false>(peer_bufs, rank, world, offset_bytes, nvec, n_blocks, s);
+}
+
+int pero_peer_allreduce_min_i64(void* const* peer_bufs, void* multicast_base, int rank, int world, int64_t offset_bytes,
+                                int64_t n_elems, int n_blocks, pero_stream_t stream) {
+    int rc = check_args(peer_bufs, rank, world, offset_bytes, n_elems, 2, n_blocks);
+    if (rc != PERO_OK) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (world == 1 || n_elems == 0) return PERO_OK;
+    if (multicast_base) {
+        mc_allreduce_min_i64_kernel<<<n_blocks, kThreads, 0, s>>>(peer_bufs, static_cast<char*>(multicast_base), rank, world,
+                                                                 offset_bytes, n_elems);
+        return (int)cudaGetLastError();
+    }
+    return (int)launch_peer<MinI64, false>(peer_bufs, rank, world, offset_bytes, n_elems / 2, n_blocks, s);
+}
+
+int pero_peer_allreduce_emulate(void* const* bufs_on_one_device, int world, int op, int64_t offset_bytes, int64_t n_elems,
+                                int n_blocks, pero_stream_t stream) {
+    int rc = check_args(bufs_on_one_device, 0, world, offset_bytes, n_elems, op == 0 ? 4 : 2, n_blocks);
+    if (rc != PERO_OK) return rc;
+    if (op != 0 && op != 1) return PERO_ERR_UNSUPPORTED;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (n_elems == 0) return PERO_OK;
+    if (op == 0) return (int)launch_peer<SumF32, true>(bufs_on_one_device, 0, world, offset_bytes, n_elems / 4, n_blocks, s);
+    return (int)launch_peer<MinI64, true>(bufs_on_one_device, 0, world, offset_bytes, n_elems / 2, n_blocks, s);
+}
+
+}  // extern "C"

@@ -57,7 +57,7 @@ class _FusedHeadCE(torch.autograd.Function):
     """sum-of-terms masked CE of Linear(h) against labels; each term = (rows, weight)."""
 
     @staticmethod
-    def forward(ctx, h, W, b, labels, head_prep, terms, dp_group):
+    def forward(ctx, h, W, b, labels, head_prep, terms, dp_group, peer_range=None):
         # terms: list of (rows int32 tensor, M_local int, weight float)
         n_frames = h.shape[0] * h.shape[1] if h.dim() == 3 else h.shape[0]
         h2 = h.detach().reshape(n_frames, h.shape[-1])
@@ -90,6 +90,7 @@ class _FusedHeadCE(torch.autograd.Function):
             saved.append((rows, m_local, weight, m_global, lse))
         ctx.saved = saved
         ctx.h2, ctx.lab, ctx.head_prep, ctx.dp_group = h2, lab, head_prep, dp_group
+        ctx.peer_range = peer_range
         ctx.h_shape, ctx.h_dtype, ctx.has_bias = h.shape, h.dtype, b is not None
         ctx.w_dtype = W.dtype
         return loss
@@ -100,25 +101,35 @@ class _FusedHeadCE(torch.autograd.Function):
         g = g.detach().float().reshape(1).contiguous()
         want_dh = ctx.needs_input_grad[0]
         d_h = d_W = d_b = None
+        peer = ctx.peer_range if ctx.dp_group is not None else None
+        flat = None
         for rows, m_local, weight, m_global, lse in ctx.saved:
             if m_local == 0 or m_global == 0:
                 continue
-            dh_t, dW_t, db_t = ops.masked_ce_bwd(h2, rows, lab, head, lse, g, weight / m_global, want_dh=want_dh)
+            first = flat is None
+            dh_t, _, _, flat_t = ops.masked_ce_bwd(h2, rows, lab, head, lse, g, weight / m_global, want_dh=want_dh,
+                                                   return_flat=True,
+                                                   flat_out=peer.tensor if (first and peer is not None) else None)
             d_h = dh_t if d_h is None else (d_h + dh_t if dh_t is not None else d_h)
-            d_W = dW_t if d_W is None else d_W + dW_t
-            d_b = db_t if d_b is None else d_b + db_t
-        if d_W is None:
-            d_W = torch.zeros(head.V, head.Dh, device=h2.device)
-            d_b = torch.zeros(head.V, device=h2.device)
+            if first:
+                flat = flat_t
+            else:
+                flat.add_(flat_t)
+        if flat is None:
+            flat = peer.tensor.zero_() if peer is not None else torch.zeros(head.V * head.Dh + head.V, device=h2.device)
             if want_dh:
                 d_h = torch.zeros_like(h2)
         if ctx.dp_group is not None:
             # every rank ends with the gradient of the single-process loss on the concatenated batch
-            torch.distributed.all_reduce(d_W, group=ctx.dp_group)
-            torch.distributed.all_reduce(d_b, group=ctx.dp_group)
+            if peer is not None:
+                peer.all_reduce_sum_()
+                flat = flat.clone()            # the exchange range is reused by the next step
+            else:
+                torch.distributed.all_reduce(flat, group=ctx.dp_group)
+        d_W, d_b = flat[:head.V * head.Dh].view(head.V, head.Dh), flat[head.V * head.Dh:]
         if d_h is not None:
             d_h = d_h.reshape(ctx.h_shape).to(ctx.h_dtype)
-        return d_h, d_W.to(ctx.w_dtype), (d_b if ctx.has_bias else None), None, None, None, None
+        return d_h, d_W.to(ctx.w_dtype), (d_b if ctx.has_bias else None), None, None, None, None, None
 
 
 class LinearHead(torch.nn.Module):
@@ -130,9 +141,20 @@ class LinearHead(torch.nn.Module):
         self.linear = torch.nn.Linear(in_features, out_features)
         self._prep = None
         self._prep_tag = None
+        self._peer_range = None
 
     def forward(self, x):
         return self.linear(x)
+
+    def enable_peer_exchange(self, group=None):
+        """Data-parallel gradients d_W | d_b of masked_loss(dp_group=...) are then reduced over the ranks by
+        libpero_b200's own NVLink/NVSwitch kernel in a peer-mapped buffer instead of torch.distributed."""
+        from .peer import PeerBuffer, PeerRange
+        W = self.linear.weight
+        n = W.shape[0] * W.shape[1] + W.shape[0]
+        buf = PeerBuffer(4 * n + 256, W.device, group)
+        self._peer_range = PeerRange(buf, n, torch.float32)
+        return self
 
     def _prepared(self):
         W, b = self.linear.weight, self.linear.bias
@@ -155,7 +177,8 @@ class LinearHead(torch.nn.Module):
         if unmasked_weight is not None:
             rows0, m0 = _rows_from_mask(mask, labels, 0, True, dev)     # model.py:85-90
             terms.append((rows0, m0, float(unmasked_weight)))
-        return _FusedHeadCE.apply(hidden, self.linear.weight, self.linear.bias, labels, self._prepared(), terms, dp_group)
+        return _FusedHeadCE.apply(hidden, self.linear.weight, self.linear.bias, labels, self._prepared(), terms, dp_group,
+                                  self._peer_range if dp_group is not None else None)
 
 
 class MaskedCrossEntropyLoss(torch.nn.Module):
@@ -181,10 +204,12 @@ class MaskedTransformerEncoder(torch.nn.Module):
         self.output_mode = output      # 'auto': logits for every frame only in eval mode; True / False to force
         self._dp_group = None
 
-    def enable_data_parallel(self, group=None):
+    def enable_data_parallel(self, group=None, peer=True):
         if not torch.distributed.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self._dp_group = group if group is not None else torch.distributed.group.WORLD
+        if peer and isinstance(self.head, LinearHead):
+            self.head.enable_peer_exchange(self._dp_group)
         return self
 
     def hidden(self, images, mask=None):

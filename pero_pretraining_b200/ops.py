@@ -76,8 +76,8 @@ def vq_assign(x, codebook, n_lines, frames_per_line, channels_first, want_dmin=F
     return idx, dmin, x_rows
 
 
-def vq_packed_init(N, device):
-    packed = torch.empty(int(N), dtype=torch.int64, device=device)
+def vq_packed_init(N, device, out=None):
+    packed = out if out is not None else torch.empty(int(N), dtype=torch.int64, device=device)
     check(_lib.lib().pero_vq_packed_init(packed.data_ptr(), int(N), _stream()), "pero_vq_packed_init")
     return packed
 
@@ -102,11 +102,14 @@ def vq_gather_st(x_rows, idx, weight, n_lines, frames_per_line, channels_first):
     return out
 
 
-def vq_ema_accumulate(x_rows, idx, K):
-    """Deterministic per-codeword sums and counts: one fp32 buffer [K*D + K]."""
+def vq_ema_accumulate(x_rows, idx, K, out=None):
+    """Deterministic per-codeword sums and counts: one fp32 buffer [K*D + K] (`out`: e.g. a peer-buffer range)."""
     L = _lib.lib()
     N, D = x_rows.shape
-    out = torch.empty(K * D + K, dtype=torch.float32, device=x_rows.device)
+    if out is None:
+        out = torch.empty(K * D + K, dtype=torch.float32, device=x_rows.device)
+    elif out.numel() != K * D + K or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 buffer of K*D + K elements")
     wsb = L.pero_vq_ema_workspace_bytes(N, K, D)
     ws = _ws(wsb, x_rows.device)
     check(L.pero_vq_ema_accumulate(x_rows.data_ptr(), idx.data_ptr(), N, K, D, out.data_ptr(), ws.data_ptr(), wsb,
@@ -193,13 +196,14 @@ def _check_h(h):
     return h if h.is_contiguous() else h.contiguous()
 
 
-def masked_ce_fwd(h, rows, labels, head):
-    """h [N, Dh]; rows int32 [M]; labels int64 [N].  Returns (loss_sum [1], lse [M], workspace)."""
+def masked_ce_fwd(h, rows, labels, head, loss_out=None):
+    """h [N, Dh]; rows int32 [M]; labels int64 [N].  Returns (loss_sum [1], lse [M], workspace).
+    `loss_out`: optional fp32 [1] destination (e.g. a slot of the peer-exchange range next to d_W|d_b)."""
     L = _lib.lib()
     h = _check_h(h)
     N, Dh = h.shape
     M = rows.numel()
-    loss_sum = torch.empty(1, dtype=torch.float32, device=h.device)
+    loss_sum = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=h.device)
     lse = torch.empty(M, dtype=torch.float32, device=h.device)
     wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
     ws = _ws(wsb, h.device)
@@ -210,7 +214,7 @@ def masked_ce_fwd(h, rows, labels, head):
 
 
 def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False,
-                  want_dw=True):
+                  want_dw=True, flat_out=None):
     """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32[, flat buffer holding d_W|d_b])."""
     L = _lib.lib()
     h = _check_h(h)
@@ -220,7 +224,7 @@ def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=Tru
     # d_W and d_b share one flat buffer so that data-parallel ranks all-reduce them in a single call
     flat = d_W = d_b = None
     if want_dw:       # want_dw=False: second phase, d_h only, from the dlogits a previous call left in `ws`
-        flat = torch.empty(head.V * Dh + head.V, dtype=torch.float32, device=h.device)
+        flat = flat_out if flat_out is not None else torch.empty(head.V * Dh + head.V, dtype=torch.float32, device=h.device)
         d_W, d_b = flat[:head.V * Dh].view(head.V, Dh), flat[head.V * Dh:]
     wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
     if ws is None or ws.numel() < wsb:
