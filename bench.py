@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--timeline", default=None, help="write the kernel timeline (CUPTI) of 2 step replays to this file")
     return ap.parse_args()
 
 
@@ -217,7 +218,11 @@ class DeviceStep:
             torch.distributed.all_reduce(t)
             self.m_global = float(t.item())
         self.out = {}
-        self.s_ema, self.s_ce, self.s_comm = (torch.cuda.Stream(device=dev) for _ in range(3))
+        # The masked-CE chain is the critical path: its stream (and the exchange stream) outrank the EMA chain, so
+        # that pending GEMM CTAs are scheduled ahead of the EMA chain's bandwidth-bound kernels.
+        self.s_ema = torch.cuda.Stream(device=dev, priority=0)
+        self.s_ce = torch.cuda.Stream(device=dev, priority=-1)
+        self.s_comm = torch.cuda.Stream(device=dev, priority=-1)
         # Data-parallel exchange ranges (EMA sums|counts and d_W|d_b|loss_sum) live in a peer-mapped buffer and
         # are reduced in place by the library's own NVLink/NVSwitch kernel.
         self.peer = self.ema_x = self.grad_x = None
@@ -225,9 +230,10 @@ class DeviceStep:
         self.n_grad = c["V"] * c["Dh"] + c["V"]
         if dp:
             from pero_pretraining_b200.peer import PeerBuffer, PeerRange
-            blocks = int(os.environ.get("PERO_PEER_BLOCKS", "24"))
+            blocks = int(os.environ.get("PERO_PEER_BLOCKS", "16"))
+            mc = os.environ.get("PERO_PEER_MULTICAST", "auto")
             self.peer = PeerBuffer(4 * (self.n_ema + self.n_grad) + 4096, dev, n_blocks=blocks,
-                                   use_multicast=os.environ.get("PERO_PEER_MULTICAST", "1") != "0")
+                                   use_multicast=None if mc == "auto" else mc != "0")
             self.ema_x = PeerRange(self.peer, self.n_ema, torch.float32)
             self.grad_x = PeerRange(self.peer, self.n_grad + 1, torch.float32)
 
@@ -269,14 +275,14 @@ class DeviceStep:
             if not self.dp:
                 loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head)
                 d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
-                                                        return_flat=True)
+                                                        return_flat=True, ws_from_fwd=True)
             else:
                 # loss_sum rides in the same exchange range as d_W | d_b.  Phase 1 produces d_W | d_b, which are
                 # reduced over the ranks on the communication stream while phase 2 computes d_h.
                 g = self.grad_x.tensor
                 loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head, loss_out=g[self.n_grad:])
                 _, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
-                                                      return_flat=True, want_dh=False, flat_out=g[:self.n_grad])
+                                                      return_flat=True, want_dh=False, flat_out=g[:self.n_grad], ws_from_fwd=True)
                 self.s_comm.wait_stream(s_ce)
                 with torch.cuda.stream(self.s_comm):
                     self.grad_x.all_reduce_sum_()
@@ -303,6 +309,21 @@ def count_kernels(fn):
         return len(names), len(ours)
     except Exception:
         return -1, -1
+
+
+def dump_timeline(run, path):
+    """Kernel start/duration/stream of 2 replays of the step (diagnostics only; not a timed number)."""
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if "cuda" in str(getattr(e, "device_type", "")).lower()]
+    evs.sort(key=lambda e: e.time_range.start)
+    t0 = evs[0].time_range.start if evs else 0
+    with open(path, "w") as f:
+        for e in evs:
+            f.write(f"{e.time_range.start - t0:10.1f} {e.time_range.end - e.time_range.start:8.1f} {e.name[:110]}\n")
 
 
 def e2e_leg(batch, dev, dp, steps, warm):
@@ -483,6 +504,12 @@ def our_arm(args):
     ms_per_step = total_ms / args.steps
     value = m_total / (ms_per_step * 1e-3)
 
+    if args.timeline and rank == 0:
+        dump_timeline(run, args.timeline)
+    elif args.timeline:
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
     # ---- roofline of the dominant kernel, e2e, CPU baseline
     _log(f"timed region done: {ms_per_step * 1e3:.1f} us/step")
     N = c["lines"] * c["frames"]

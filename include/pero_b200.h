@@ -143,6 +143,9 @@ int pero_vq_st_commit_bwd(const float* g_quantized, const float* quantized, cons
  *   d_h [N, Dh] (same dtype as h, zero on unmasked frames), d_W [V, Dh] fp32, d_b [V] fp32.
  *   Two-phase use: a first call with d_h = NULL produces d_W, d_b (ready to be all-reduced); a second call with
  *   d_W = d_b = NULL and the SAME workspace produces d_h from the dlogits the first call left there.
+ *   h = NULL: the workspace is the one pero_masked_ce_fwd ran on for the same (h, rows, labels) and has not been
+ *   written since; the operands gathered there are reused (h_is_bf16 must still describe d_h's dtype).
+ *   `rows` must be ascending (the order of mask == 1): the frame -> masked-row map is a binary search over it.
  */
 size_t pero_head_bytes(int64_t V, int64_t Dh);
 int pero_head_prepare(const float* W, const float* bias, int64_t V, int64_t Dh, void* head, size_t head_bytes,

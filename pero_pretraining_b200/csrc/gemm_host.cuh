@@ -31,6 +31,15 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
                           uint32_t box_rows) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return PERO_ERR_DRIVER;
+    // The encode is a DRIVER call and needs the primary context current on the calling thread.  A thread whose
+    // first CUDA action is this call (e.g. PyTorch's autograd worker entering a backward that starts with a
+    // GEMM) has none yet: cudaSetDevice binds it (legal during stream capture, once per thread).
+    static thread_local bool context_bound = false;
+    if (!context_bound) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) return PERO_ERR_DRIVER;
+        context_bound = true;
+    }
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems & 7u) || box_rows == 0 || box_rows > 256)
         return PERO_ERR_BAD_ALIGN;
     cuuint64_t dims[2] = {cols, rows};

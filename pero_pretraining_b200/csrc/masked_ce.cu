@@ -44,7 +44,7 @@ constexpr int kMaxLseSplits = 64;
 
 struct CeWsLayout {
     int64_t Dhp, Vp, Mp64, Mpad, S, KS;
-    size_t a_off, at_off, lab_off, inv_off, p_off, pt_off, pm_off, ps_off, zlab_off, rowloss_off, planes_off, total;
+    size_t a_off, at_off, lab_off, inv_off, p_off, pt_off, pm_off, ps_off, zlab_off, rowloss_off, ticket_off, planes_off, total;
 };
 inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     CeWsLayout l;
@@ -73,6 +73,7 @@ inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     l.ps_off = take((size_t)2 * S * l.Mpad * 4);
     l.zlab_off = take((size_t)l.Mpad * 4);
     l.rowloss_off = take((size_t)l.Mpad * 4);
+    l.ticket_off = take(256);
     l.planes_off = take((size_t)KS * M * Dh * 4);
     l.total = off;
     return l;
@@ -105,18 +106,15 @@ head_prepare_kernel(const float* __restrict__ W, const float* __restrict__ bias,
     }
 }
 
-__global__ void ce_inv_init_kernel(int* __restrict__ inv, long long N) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) inv[i] = -1;
-}
-
-// Gather the masked frames into the GEMM operand A [M, Dhp] bf16 (+ A^T [Dh, Mp64] for d_W), their labels,
-// and the inverse frame -> masked-row map.  Tiles of 32 masked rows x 32 channels.
+// Gather the masked frames into the GEMM operand A [M, Dhp] bf16 and A^T [Dh, Mp64] (operand of d_W), their
+// labels, and the inverse frame -> masked-row map inv [N] (-1 for frames that are not selected; `rows` is
+// ascending, so the map is a binary search — no separate initialisation pass).  Tiles of 32 masked rows x 32
+// channels.  Also clears the ticket word that ce_finalize_kernel's last block uses.
 template <typename T>
 __global__ void __launch_bounds__(256)
-ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const long long* __restrict__ labels, int M, int Dh,
-                 int Dhp, int Mp64, int Mpad, __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ at,
-                 int* __restrict__ lab, int* __restrict__ inv) {
+ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const long long* __restrict__ labels, long long N, int M,
+                 int Dh, int Dhp, int Mp64, int Mpad, __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ at,
+                 int* __restrict__ lab, int* __restrict__ inv, unsigned int* __restrict__ ticket) {
     __shared__ float tile[32][33];
     const int m0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -128,25 +126,26 @@ ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const lo
         tile[ty + i * 8][tx] = x;
         if (m < M && d < Dhp) a[(size_t)m * Dhp + d] = __float2bfloat16_rn(x);
     }
-    if (at) {
-        __syncthreads();
+    __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int d = d0 + ty + i * 8, m = m0 + tx;
-            if (d < Dh && m < Mp64) at[(size_t)d * Mp64 + m] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
-        }
+    for (int i = 0; i < 4; ++i) {
+        const int d = d0 + ty + i * 8, m = m0 + tx;
+        if (d < Dh && m < Mp64) at[(size_t)d * Mp64 + m] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
     }
     if (blockIdx.y == 0 && threadIdx.x < 32) {
         const int m = m0 + (int)threadIdx.x;
-        if (m < Mpad) {
-            int l = -1;
-            if (m < M) {
-                const int r = __ldg(rows + m);
-                l = (int)__ldg(labels + r);
-                if (inv) inv[r] = m;
-            }
-            lab[m] = l;
+        if (m < Mpad) lab[m] = m < M ? (int)__ldg(labels + __ldg(rows + m)) : -1;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;
+    // inverse map: frame n -> its position in `rows`, or -1
+    const long long nthreads = (long long)gridDim.x * gridDim.y * blockDim.x;
+    for (long long n = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; n < N; n += nthreads) {
+        int lo = 0, hi = M;                       // first position with rows[pos] >= n
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)__ldg(rows + mid) < n) lo = mid + 1; else hi = mid;
         }
+        inv[n] = (lo < M && (long long)__ldg(rows + lo) == n) ? lo : -1;
     }
 }
 
@@ -300,35 +299,58 @@ struct DlogitsEpi {
 };
 
 // ------------------------------------------------------------------------------------------------ small kernels
-// lse[m] = log-sum-exp combined over the column-split partials, one thread per masked row;
-// rowloss[m] = lse[m] - z[label].  The loss sum is taken by ce_sum_kernel in a fixed order.
+// lse[m] = log-sum-exp combined over the column-split partials; rowloss[m] = lse[m] - z[label].
 // One warp per row, lanes over the partial slots (all loads in flight at once; fixed butterfly order).
+// The block that finishes last (ticket) sums rowloss in a fixed order into loss_sum: no second launch, and the
+// result does not depend on which block that is.
 __global__ void __launch_bounds__(256)
 ce_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ zlab, int M, int Mpad,
-                   int slots, float* __restrict__ lse, float* __restrict__ rowloss) {
+                   int slots, float* __restrict__ lse, float* __restrict__ rowloss, unsigned int* __restrict__ ticket,
+                   float* __restrict__ loss_sum) {
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (m >= M) return;
-    float pmv[4], psv[4];                    // slots <= 2 * kMaxLseSplits = 128 = 4 per lane
-    float mx = -CUDART_INF_F;
+    if (m < M) {
+        float pmv[4], psv[4];                    // slots <= 2 * kMaxLseSplits = 128 = 4 per lane
+        float mx = -CUDART_INF_F;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int s = lane + 32 * i;
-        pmv[i] = s < slots ? __ldg(pm + (size_t)s * Mpad + m) : -CUDART_INF_F;
-        psv[i] = s < slots ? __ldg(ps + (size_t)s * Mpad + m) : 0.f;
-        mx = fmaxf(mx, pmv[i]);
+        for (int i = 0; i < 4; ++i) {
+            const int s = lane + 32 * i;
+            pmv[i] = s < slots ? __ldg(pm + (size_t)s * Mpad + m) : -CUDART_INF_F;
+            psv[i] = s < slots ? __ldg(ps + (size_t)s * Mpad + m) : 0.f;
+            mx = fmaxf(mx, pmv[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sum += psv[i] * exp2f((pmv[i] - mx) * kLog2e);     // exp2(-inf) = 0 on empty slots
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) {
+            const float l = mx + log2f(sum) * kLn2;
+            lse[m] = l;
+            rowloss[m] = l - zlab[m];
+        }
     }
+    __shared__ bool last;
+    __shared__ float sh[8];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    float part = 0.f;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) part += __ldcg(rowloss + i);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sum += psv[i] * exp2f((pmv[i] - mx) * kLog2e);     // exp2(-inf) = 0 on empty slots
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) {
-        const float l = mx + log2f(sum) * kLn2;
-        lse[m] = l;
-        rowloss[m] = l - zlab[m];
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        loss_sum[0] = t;
     }
 }
 
@@ -353,14 +375,34 @@ ce_db_kernel(const __nv_bfloat16* __restrict__ pt, int V, int M, int Mp64, float
 }
 
 // d_h[n, :] = sum over split planes of row inv[n] (zero when the frame is not masked).
+// Blocks [0, gridDim.x - db_blocks) scatter; the last db_blocks blocks (if any) compute d_b exactly as
+// ce_db_kernel does (one warp per label), so that d_b rides in the same launch instead of sitting between the two
+// gradient GEMMs.
 template <typename T>
 __global__ void __launch_bounds__(256)
 ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ inv, long long N, int M, int Dh, int KS,
-                     T* __restrict__ dh) {
+                     T* __restrict__ dh, int db_blocks, const __nv_bfloat16* __restrict__ pt, int V, int Mp64,
+                     float* __restrict__ db) {
+    const int scatter_blocks = (int)gridDim.x - db_blocks;
+    if ((int)blockIdx.x >= scatter_blocks) {
+        const int lane = threadIdx.x & 31;
+        for (int v = ((int)blockIdx.x - scatter_blocks) * 8 + (threadIdx.x >> 5); v < V; v += db_blocks * 8) {
+            const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(pt + (size_t)v * Mp64);
+            float s = 0.f;
+            for (int i = lane; i < Mp64 / 2; i += 32) {
+                const float2 f = __bfloat1622float2(row[i]);
+                s += f.x + f.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) db[v] = s;
+        }
+        return;
+    }
     // one thread per 4 consecutive channels (Dh % 4 == 0): 16-byte plane reads, 16/8-byte stores
     const int g4 = Dh >> 2;
     const long long total = N * g4;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long stride = (long long)scatter_blocks * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const long long n = i / g4;
         const int g = (int)(i - n * g4);
@@ -466,13 +508,14 @@ struct MaskPred {
 };
 
 template <typename T>
-int launch_ce_gather(const void* h, const int32_t* rows, const int64_t* labels, int M, int Dh, const CeWsLayout& l, char* ws,
-                     bool with_t, bool with_inv, cudaStream_t stream) {
+int launch_ce_gather(const void* h, const int32_t* rows, const int64_t* labels, long long N, int M, int Dh, const CeWsLayout& l,
+                     char* ws, cudaStream_t stream) {
     dim3 grid((unsigned)((l.Mpad + 31) / 32), (unsigned)(l.Dhp / 32));
     ce_gather_kernel<T><<<grid, 256, 0, stream>>>(
-        static_cast<const T*>(h), rows, reinterpret_cast<const long long*>(labels), M, Dh, (int)l.Dhp, (int)l.Mp64, (int)l.Mpad,
-        reinterpret_cast<__nv_bfloat16*>(ws + l.a_off), with_t ? reinterpret_cast<__nv_bfloat16*>(ws + l.at_off) : nullptr,
-        reinterpret_cast<int*>(ws + l.lab_off), with_inv ? reinterpret_cast<int*>(ws + l.inv_off) : nullptr);
+        static_cast<const T*>(h), rows, reinterpret_cast<const long long*>(labels), N, M, Dh, (int)l.Dhp, (int)l.Mp64, (int)l.Mpad,
+        reinterpret_cast<__nv_bfloat16*>(ws + l.a_off), reinterpret_cast<__nv_bfloat16*>(ws + l.at_off),
+        reinterpret_cast<int*>(ws + l.lab_off), reinterpret_cast<int*>(ws + l.inv_off),
+        reinterpret_cast<unsigned int*>(ws + l.ticket_off));
     return (int)cudaGetLastError();
 }
 
@@ -509,8 +552,8 @@ size_t pero_masked_ce_workspace_bytes(int64_t N, int64_t M, int64_t V, int64_t D
 }
 
 static int ce_check(const void* h, int64_t N, int64_t Dh, const int32_t* rows, int64_t M, const int64_t* labels,
-                    const void* head, int64_t V, void* workspace, size_t workspace_bytes) {
-    if (!h || !rows || !labels || !head || !workspace) return PERO_ERR_NULL;
+                    const void* head, int64_t V, void* workspace, size_t workspace_bytes, bool h_optional = false) {
+    if ((!h && !h_optional) || !rows || !labels || !head || !workspace) return PERO_ERR_NULL;
     if (N <= 0 || M <= 0 || M > N || V <= 0 || Dh <= 0 || N > (1ll << 31) - 256 || V > (1ll << 24) || Dh > 512)
         return PERO_ERR_BAD_SHAPE;   // Dh <= 512: the masked rows stay resident in shared memory for the sweep
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(head) & 255)) return PERO_ERR_BAD_ALIGN;
@@ -529,8 +572,10 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     const HeadLayout hl = head_layout(V, Dh);
     char* ws = static_cast<char*>(workspace);
     const char* hb = static_cast<const char*>(head);
-    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, (int)M, (int)Dh, l, ws, false, false, stream)
-                   : launch_ce_gather<float>(h, rows, labels, (int)M, (int)Dh, l, ws, false, false, stream);
+    // The gather also leaves A^T and the inverse row map in the workspace: a backward call that is handed the
+    // same workspace (h = NULL) starts directly with its GEMM.
+    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream)
+                   : launch_ce_gather<float>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream);
     if (rc) return rc;
     LseEpi::Params ep;
     ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
@@ -544,8 +589,8 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     if (rc) return rc;
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
     ce_finalize_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
-                                                                rowloss);
-    ce_sum_kernel<<<1, 1024, 0, stream>>>(rowloss, (int)M, loss_sum);
+                                                                rowloss, reinterpret_cast<unsigned int*>(ws + l.ticket_off),
+                                                                loss_sum);
     return (int)cudaGetLastError();
 }
 
@@ -554,8 +599,10 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
                        const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
                        void* workspace, size_t workspace_bytes, pero_stream_t stream) {
     if (M == 0) return PERO_ERR_BAD_SHAPE;
-    int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes);
+    int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes, /*h_optional=*/true);
     if (rc) return rc;
+    // h == NULL: the workspace is the one pero_masked_ce_fwd ran on for the same (h, rows, labels) and still holds
+    // the gathered operands (A, A^T, labels, inverse row map): no second gather.
     // Two-phase use (lets a data-parallel caller all-reduce d_W | d_b while d_h is still being computed):
     //   phase 1: d_W, d_b given (d_h may be NULL)  -> dlogits P / P^T into the workspace, d_W, d_b [, d_h]
     //   phase 2: d_W == d_b == NULL, d_h given     -> d_h from the P left in the SAME workspace by phase 1
@@ -569,11 +616,15 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     int* inv = reinterpret_cast<int*>(ws + l.inv_off);
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + l.p_off);
     __nv_bfloat16* PT = reinterpret_cast<__nv_bfloat16*>(ws + l.pt_off);
+    static int store_pairs = -1;     // PERO_CE_STORE_PAIRS=0: gradient GEMMs on single CTAs (tuning knob)
+    if (store_pairs < 0) { const char* e = getenv("PERO_CE_STORE_PAIRS"); store_pairs = e ? atoi(e) : 1; }
+    const bool db_in_scatter = !phase2_only && d_h != nullptr;
     if (!phase2_only) {
-    ce_inv_init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(inv, N);
-    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, (int)M, (int)Dh, l, ws, true, true, stream)
-                   : launch_ce_gather<float>(h, rows, labels, (int)M, (int)Dh, l, ws, true, true, stream);
-    if (rc) return rc;
+    if (h) {
+        rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream)
+                       : launch_ce_gather<float>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream);
+        if (rc) return rc;
+    }
 
     DlogitsEpi::Params ep;
     ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
@@ -588,10 +639,14 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     // d_W [V, Dh] = P^T [V, Mp64] @ A^T [Dh, Mp64]^T
     StoreEpi::Params sw;
     sw.out = d_W; sw.ld = Dh; sw.split_stride = 0; sw.rows = (int)V; sw.cols = (int)Dh;
-    rc = launch_gemm_tn<1, false, StoreEpi>(PT, (int)V, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1, 0, 1, 0,
-                                            sw, stream);
+    rc = store_pairs
+             ? launch_gemm_tn<2, false, StoreEpi>(PT, (int)V, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1, 0, 1,
+                                                  0, sw, stream)
+             : launch_gemm_tn<1, false, StoreEpi>(PT, (int)V, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1, 0, 1,
+                                                  0, sw, stream);
     if (rc) return rc;
-    ce_db_kernel<<<(unsigned)((V + 7) / 8), 256, 0, stream>>>(PT, (int)V, (int)M, (int)l.Mp64, d_b);
+    // d_b: alone when this call stops after d_W | d_b (they are exchanged next), otherwise inside the scatter launch
+    if (!db_in_scatter) ce_db_kernel<<<(unsigned)((V + 7) / 8), 256, 0, stream>>>(PT, (int)V, (int)M, (int)l.Mp64, d_b);
     }   // !phase2_only
 
     if (d_h) {
@@ -599,22 +654,29 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
         float* planes = reinterpret_cast<float*>(ws + l.planes_off);
         StoreEpi::Params sh;
         sh.out = planes; sh.ld = Dh; sh.split_stride = (long long)M * Dh; sh.rows = (int)M; sh.cols = (int)Dh;
-        rc = launch_gemm_tn<1, false, StoreEpi>(P, (int)M, (int)l.Vp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0, 1,
-                                                0, sh, stream);
+        rc = store_pairs
+                 ? launch_gemm_tn<2, false, StoreEpi>(P, (int)M, (int)l.Vp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
+                                                      1, 0, sh, stream)
+                 : launch_gemm_tn<1, false, StoreEpi>(P, (int)M, (int)l.Vp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
+                                                      1, 0, sh, stream);
         if (rc) return rc;
         const long long total = N * (Dh / 4);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
+        const int db_blocks = db_in_scatter ? (int)((V + 7) / 8) : 0;
+        blocks += db_blocks;
         // the number of planes actually produced is recomputed exactly as launch_gemm_tn does
         const int num_kb = (int)(l.Vp / 64);
         const int kb_per = (num_kb + (int)l.KS - 1) / (int)l.KS;
         const int ks_eff = (num_kb + kb_per - 1) / kb_per;
         if (h_is_bf16)
             ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
-                                                                                     static_cast<__nv_bfloat16*>(d_h));
+                                                                                     static_cast<__nv_bfloat16*>(d_h), db_blocks, PT,
+                                                                                     (int)V, (int)l.Mp64, d_b);
         else
             ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
-                                                                             static_cast<float*>(d_h));
+                                                                             static_cast<float*>(d_h), db_blocks, PT, (int)V,
+                                                                             (int)l.Mp64, d_b);
     }
     return (int)cudaGetLastError();
 }

@@ -12,31 +12,31 @@
 // plain peer loads summed in rank order 0..g-1 and peer stores.  Either way each element is reduced exactly
 // once, by its owner, and the same bits are delivered to every rank, so replicated state stays bit-identical.
 //
-// Barriers are CAS handshakes on flag words in the first PERO_PEER_HEADER_BYTES of each buffer
-// ([block][source rank] u32, 0 when idle); they reset themselves, so the kernels are CUDA-graph replayable.
+// Barriers are one-way release stores of a growing epoch into arrival words in the first
+// PERO_PEER_HEADER_BYTES of each peer's buffer ([block][source rank] u32) polled locally with acquire loads;
+// nothing is ever reset, so the kernels are CUDA-graph replayable.
 // A rank that never arrives makes the waiters trap after ~4 s instead of hanging the GPU.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/pero_b200.h"
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kMaxThreads = 512;
 constexpr int kMaxWorld = PERO_PEER_MAX_WORLD;
 constexpr int kMaxBlocks = PERO_PEER_MAX_BLOCKS;
 constexpr unsigned long long kTimeoutNs = 4000000000ull;
-static_assert(kMaxWorld * kMaxBlocks * 4 <= PERO_PEER_HEADER_BYTES, "flag words must fit the buffer header");
+static_assert(kMaxWorld * kMaxBlocks * 4 <= 8192 && 8192 + kMaxBlocks * 4 <= PERO_PEER_HEADER_BYTES, "flag words must fit the buffer header");
 
-__device__ __forceinline__ uint32_t cas_release_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
-    uint32_t old;
-    asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
-    return old;
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
-    uint32_t old;
-    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
-    return old;
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ unsigned long long now_ns() {
     unsigned long long t;
@@ -44,22 +44,40 @@ __device__ __forceinline__ unsigned long long now_ns() {
     return t;
 }
 
-// All threads of block `blk` on every rank meet here.  Thread t < world raises flag [blk][rank] on rank t and
-// consumes flag [blk][t] on its own rank; release/acquire at system scope order the block's earlier peer
-// stores before the flag and the later peer loads after it.
-__device__ __forceinline__ void rank_barrier(void* const* bufs, int rank, int world, int blk) {
+// Header of a peer buffer: arrival words [block][source rank] (written by the peers, one writer each) and one
+// epoch word per block (local).  Every collective launch advances a block's epoch by 2 (two barriers); arrival
+// words only ever grow, so nothing needs resetting and a CUDA graph can replay the launch.
+constexpr int kEpochOffsetWords = 2048;     // byte 8192
+
+__device__ __forceinline__ uint32_t* arrival_word(void* base, int blk, int src) {
+    return reinterpret_cast<uint32_t*>(base) + blk * kMaxWorld + src;
+}
+__device__ __forceinline__ uint32_t* epoch_word(void* base, int blk) {
+    return reinterpret_cast<uint32_t*>(base) + kEpochOffsetWords + blk;
+}
+
+// All threads of block `blk` on every rank meet here.  Thread t < world publishes `target` in rank t's
+// arrival word [blk][rank] (one-way release store: it orders the block's earlier peer stores before it) and
+// polls its own word [blk][t] until rank t has published the same epoch (acquire).
+__device__ __forceinline__ void rank_barrier(void* const* bufs, int rank, int world, int blk, uint32_t target) {
     __syncthreads();
     const int t = threadIdx.x;
     if (t < world) {
-        uint32_t* remote = reinterpret_cast<uint32_t*>(bufs[t]) + blk * kMaxWorld + rank;
-        uint32_t* local = reinterpret_cast<uint32_t*>(bufs[rank]) + blk * kMaxWorld + t;
+        st_release_sys(arrival_word(bufs[t], blk, rank), target);
+        const uint32_t* mine = arrival_word(bufs[rank], blk, t);
         const unsigned long long t0 = now_ns();
-        while (cas_release_sys(remote, 0u, 1u) != 0u)
-            if (now_ns() - t0 > kTimeoutNs) __trap();
-        while (cas_acquire_sys(local, 1u, 0u) != 1u)
+        while ((int32_t)(ld_acquire_sys(mine) - target) < 0)
             if (now_ns() - t0 > kTimeoutNs) __trap();
     }
     __syncthreads();
+}
+
+// Epoch of this launch for the block (read before the first barrier, advanced after the second).
+__device__ __forceinline__ uint32_t begin_collective(void* const* bufs, int rank, int blk) {
+    return *epoch_word(bufs[rank], blk);
+}
+__device__ __forceinline__ void end_collective(void* const* bufs, int rank, int blk, uint32_t epoch) {
+    if (threadIdx.x == 0) *epoch_word(bufs[rank], blk) = epoch + 2;
 }
 
 __device__ __forceinline__ float4 mc_ld_reduce_add(const char* p) {
@@ -126,14 +144,16 @@ __device__ __forceinline__ Range slice_of(int64_t total, int world, int rank) {
 // kWorld == 0 is the generic loop.  With kEmulate the rank is blockIdx.y: g "ranks" of ONE cooperative launch
 // on one GPU (the single-GPU test of the protocol, never the product path).
 template <class Op, int kWorld, bool kEmulate>
-__global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(void* const* __restrict__ bufs, int rank_arg, int world_arg,
+__global__ void __launch_bounds__(kMaxThreads) peer_allreduce_kernel(void* const* __restrict__ bufs, int rank_arg, int world_arg,
                                                                   int64_t off_bytes, int64_t nvec) {
     using Vec = typename Op::Vec;
     const int world = kWorld > 0 ? kWorld : world_arg;
     const int rank = kEmulate ? (int)blockIdx.y : rank_arg;
-    rank_barrier(bufs, rank, world, blockIdx.x);
+    const uint32_t epoch = begin_collective(bufs, rank, blockIdx.x);
+    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 1);
     const Range r = slice_of(nvec, world, rank);
-    constexpr int U = 2;
+    constexpr int U = kWorld == 2 ? 4 : (kWorld == 8 ? 1 : 2);
+    const int kThreads = blockDim.x;
     const int64_t step = (int64_t)gridDim.x * kThreads * U;
     for (int64_t base = r.lo + (int64_t)blockIdx.x * kThreads * U; base < r.hi; base += step) {
         Vec acc[U];
@@ -174,15 +194,18 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(void* const* _
             }
         }
     }
-    rank_barrier(bufs, rank, world, blockIdx.x);
+    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 2);
+    end_collective(bufs, rank, blockIdx.x, epoch);
 }
 
 // Multicast variant: the switch reduces on load and replicates on store.
-__global__ void __launch_bounds__(kThreads) mc_allreduce_sum_f32_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
+__global__ void __launch_bounds__(kMaxThreads) mc_allreduce_sum_f32_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
                                                                         int world, int64_t off_bytes, int64_t nvec) {
-    rank_barrier(bufs, rank, world, blockIdx.x);
+    const uint32_t epoch = begin_collective(bufs, rank, blockIdx.x);
+    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 1);
     const Range r = slice_of(nvec, world, rank);
     constexpr int U = 8;
+    const int kThreads = blockDim.x;
     char* base_ptr = mc + off_bytes;
     const int64_t step = (int64_t)gridDim.x * kThreads * U;
     for (int64_t base = r.lo + (int64_t)blockIdx.x * kThreads * U; base < r.hi; base += step) {
@@ -198,14 +221,17 @@ __global__ void __launch_bounds__(kThreads) mc_allreduce_sum_f32_kernel(void* co
             if (i < r.hi) mc_st(base_ptr + i * 16, v[u]);
         }
     }
-    rank_barrier(bufs, rank, world, blockIdx.x);
+    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 2);
+    end_collective(bufs, rank, blockIdx.x, epoch);
 }
 
-__global__ void __launch_bounds__(kThreads) mc_allreduce_min_i64_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
+__global__ void __launch_bounds__(kMaxThreads) mc_allreduce_min_i64_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
                                                                         int world, int64_t off_bytes, int64_t n) {
-    rank_barrier(bufs, rank, world, blockIdx.x);
+    const uint32_t epoch = begin_collective(bufs, rank, blockIdx.x);
+    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 1);
     const Range r = slice_of(n, world, rank);
     constexpr int U = 8;
+    const int kThreads = blockDim.x;
     char* base_ptr = mc + off_bytes;
     const int64_t step = (int64_t)gridDim.x * kThreads * U;
     for (int64_t base = r.lo + (int64_t)blockIdx.x * kThreads * U; base < r.hi; base += step) {
@@ -221,7 +247,8 @@ __global__ void __launch_bounds__(kThreads) mc_allreduce_min_i64_kernel(void* co
             if (i < r.hi) mc_st(base_ptr + i * 8, v[u]);
         }
     }
-    rank_barrier(bufs, rank, world, blockIdx.x);
+    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 2);
+    end_collective(bufs, rank, blockIdx.x, epoch);
 }
 
 int check_args(void* const* peer_bufs, int rank, int world, int64_t off_bytes, int64_t n, int64_t per_vec, int n_blocks) {
@@ -230,6 +257,20 @@ int check_args(void* const* peer_bufs, int rank, int world, int64_t off_bytes, i
     if (n_blocks < 1 || n_blocks > kMaxBlocks) return PERO_ERR_BAD_SHAPE;
     if (off_bytes < PERO_PEER_HEADER_BYTES || (off_bytes & 15) || (n % per_vec)) return PERO_ERR_BAD_ALIGN;
     return PERO_OK;
+}
+
+// CTA size of the exchange kernels.  Small CTAs (few registers, no shared memory) slot in beside the resident
+// GEMM CTAs instead of waiting for a whole SM; PERO_PEER_THREADS is a tuning knob.
+int peer_threads() {
+    static int t = 0;
+    if (!t) {
+        const char* e = getenv("PERO_PEER_THREADS");
+        t = e ? atoi(e) : 256;
+        if (t < 32) t = 32;
+        if (t > kMaxThreads) t = kMaxThreads;
+        t = t / 32 * 32;
+    }
+    return t;
 }
 
 template <class Op, bool kEmulate>
@@ -244,8 +285,8 @@ cudaError_t launch_peer(void* const* bufs, int rank, int world, int64_t off, int
         default: fn = (const void*)peer_allreduce_kernel<Op, 0, kEmulate>; break;
     }
     // The emulated ranks spin on one another inside one grid: a cooperative launch guarantees co-residency.
-    return kEmulate ? cudaLaunchCooperativeKernel(fn, grid, dim3(kThreads), args, 0, s)
-                    : cudaLaunchKernel(fn, grid, dim3(kThreads), args, 0, s);
+    return kEmulate ? cudaLaunchCooperativeKernel(fn, grid, dim3(peer_threads()), args, 0, s)
+                    : cudaLaunchKernel(fn, grid, dim3(peer_threads()), args, 0, s);
 }
 
 }  // namespace
@@ -260,7 +301,7 @@ int pero_peer_allreduce_sum_f32(void* const* peer_bufs, void* multicast_base, in
     if (world == 1 || n_elems == 0) return PERO_OK;
     const int64_t nvec = n_elems / 4;
     if (multicast_base) {
-        mc_allreduce_sum_f32_kernel<<<n_blocks, kThreads, 0, s>>>(peer_bufs, static_cast<char*>(multicast_base), rank, world,
+        mc_allreduce_sum_f32_kernel<<<n_blocks, peer_threads(), 0, s>>>(peer_bufs, static_cast<char*>(multicast_base), rank, world,
                                                                  offset_bytes, nvec);
         return (int)cudaGetLastError();
     }
@@ -274,7 +315,7 @@ int pero_peer_allreduce_min_i64(void* const* peer_bufs, void* multicast_base, in
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (world == 1 || n_elems == 0) return PERO_OK;
     if (multicast_base) {
-        mc_allreduce_min_i64_kernel<<<n_blocks, kThreads, 0, s>>>(peer_bufs, static_cast<char*>(multicast_base), rank, world,
+        mc_allreduce_min_i64_kernel<<<n_blocks, peer_threads(), 0, s>>>(peer_bufs, static_cast<char*>(multicast_base), rank, world,
                                                                  offset_bytes, n_elems);
         return (int)cudaGetLastError();
     }

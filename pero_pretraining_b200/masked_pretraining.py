@@ -77,9 +77,9 @@ class _FusedHeadCE(torch.autograd.Function):
             else:
                 m_global = float(m_local)
             if m_local > 0:
-                loss_sum, lse, _ = ops.masked_ce_fwd(h2, rows, lab, head_prep)
+                loss_sum, lse, ws = ops.masked_ce_fwd(h2, rows, lab, head_prep)
             else:
-                loss_sum, lse = torch.zeros(1, device=h2.device), None
+                loss_sum, lse, ws = torch.zeros(1, device=h2.device), None, None
             if dp_group is not None:
                 loss_sum = loss_sum.clone()
                 torch.distributed.all_reduce(loss_sum, group=dp_group)
@@ -87,7 +87,7 @@ class _FusedHeadCE(torch.autograd.Function):
             term = loss_sum[0] / m_global if m_global > 0 else loss_sum[0] * float('nan')
             term = term * weight if weight != 1.0 else term
             loss = term if loss is None else loss + term
-            saved.append((rows, m_local, weight, m_global, lse))
+            saved.append((rows, m_local, weight, m_global, lse, ws))
         ctx.saved = saved
         ctx.h2, ctx.lab, ctx.head_prep, ctx.dp_group = h2, lab, head_prep, dp_group
         ctx.peer_range = peer_range
@@ -103,12 +103,13 @@ class _FusedHeadCE(torch.autograd.Function):
         d_h = d_W = d_b = None
         peer = ctx.peer_range if ctx.dp_group is not None else None
         flat = None
-        for rows, m_local, weight, m_global, lse in ctx.saved:
+        for rows, m_local, weight, m_global, lse, ws in ctx.saved:
             if m_local == 0 or m_global == 0:
                 continue
             first = flat is None
+            # the forward's workspace still holds the gathered operands of this term: no second gather
             dh_t, _, _, flat_t = ops.masked_ce_bwd(h2, rows, lab, head, lse, g, weight / m_global, want_dh=want_dh,
-                                                   return_flat=True,
+                                                   return_flat=True, ws=ws, ws_from_fwd=True,
                                                    flat_out=peer.tensor if (first and peer is not None) else None)
             d_h = dh_t if d_h is None else (d_h + dh_t if dh_t is not None else d_h)
             if first:

@@ -214,8 +214,10 @@ def masked_ce_fwd(h, rows, labels, head, loss_out=None):
 
 
 def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False,
-                  want_dw=True, flat_out=None):
-    """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32[, flat buffer holding d_W|d_b])."""
+                  want_dw=True, flat_out=None, ws_from_fwd=False):
+    """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32[, flat buffer holding d_W|d_b]).
+    ws_from_fwd: `ws` is the workspace masked_ce_fwd returned for the same (h, rows, labels) and has not been
+    touched since: the gathered operands in it are reused instead of gathering again."""
     L = _lib.lib()
     h = _check_h(h)
     N, Dh = h.shape
@@ -227,10 +229,12 @@ def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=Tru
         flat = flat_out if flat_out is not None else torch.empty(head.V * Dh + head.V, dtype=torch.float32, device=h.device)
         d_W, d_b = flat[:head.V * Dh].view(head.V, Dh), flat[head.V * Dh:]
     wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
+    if ws_from_fwd and (ws is None or ws.numel() < wsb):
+        raise ValueError("ws_from_fwd needs the forward call's workspace")
     if ws is None or ws.numel() < wsb:
         ws = _ws(wsb, h.device)
     gs = None if grad_scale is None else _f32c(grad_scale, "grad_scale")
-    check(L.pero_masked_ce_bwd(h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M,
+    check(L.pero_masked_ce_bwd(None if ws_from_fwd else h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M,
                                labels.data_ptr(), head.blob.data_ptr(), head.V, lse.data_ptr(), _p(gs),
                                float(inv_count), _p(d_h), _p(d_W), _p(d_b), ws.data_ptr(), wsb,
                                _stream()), "pero_masked_ce_bwd")
