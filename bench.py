@@ -232,10 +232,18 @@ class DeviceStep:
             from pero_pretraining_b200.peer import PeerBuffer, PeerRange
             blocks = int(os.environ.get("PERO_PEER_BLOCKS", "16"))
             mc = os.environ.get("PERO_PEER_MULTICAST", "auto")
-            self.peer = PeerBuffer(4 * (self.n_ema + self.n_grad) + 4096, dev, n_blocks=blocks,
-                                   use_multicast=None if mc == "auto" else mc != "0")
-            self.ema_x = PeerRange(self.peer, self.n_ema, torch.float32)
+            mc = None if mc == "auto" else mc != "0"
+            # one buffer (= one set of barrier words) per exchange chain: the EMA exchange and the gradient exchange
+            # run on their own streams and may overlap
+            self.peer_ema = PeerBuffer(4 * self.n_ema + 1024, dev, n_blocks=blocks, use_multicast=mc)
+            self.peer = PeerBuffer(4 * self.n_grad + 1024, dev, n_blocks=blocks, use_multicast=mc)
+            self.ema_x = PeerRange(self.peer_ema, self.n_ema, torch.float32)
             self.grad_x = PeerRange(self.peer, self.n_grad + 1, torch.float32)
+            self.s_comm_ema = torch.cuda.Stream(device=dev, priority=-1)
+            # label-axis ranges of the head backward: each range's d_W rows are exchanged while the next is computed
+            chunks = max(1, int(os.environ.get("PERO_DP_CHUNKS", "1")))
+            step = max(256, (c["V"] // chunks + 255) // 256 * 256)
+            self.v_ranges = [(v, min(v + step, c["V"])) for v in range(0, c["V"], step)]
 
     def __call__(self):
         """Three independent chains after the assignment, forked onto side streams (captured as parallel
@@ -262,12 +270,11 @@ class DeviceStep:
             if not self.dp:
                 sums = ops.vq_ema_accumulate(x_rows, idx, c["K"])
             else:
-                # both exchanges run on ONE communication stream, in the same order on every rank
                 sums = ops.vq_ema_accumulate(x_rows, idx, c["K"], out=self.ema_x.tensor)
-                self.s_comm.wait_stream(s_ema)
-                with torch.cuda.stream(self.s_comm):
+                self.s_comm_ema.wait_stream(s_ema)
+                with torch.cuda.stream(self.s_comm_ema):
                     self.ema_x.all_reduce_sum_()
-                s_ema.wait_stream(self.s_comm)
+                s_ema.wait_stream(self.s_comm_ema)
             s_ema.wait_event(gathered)
             ops.vq_ema_apply(sums, self.ema_w, self.cs, self.weight, c["decay"], c["epsilon"], self.cb)
         # --- chain C
@@ -277,21 +284,28 @@ class DeviceStep:
                 d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
                                                         return_flat=True, ws_from_fwd=True)
             else:
-                # loss_sum rides in the same exchange range as d_W | d_b.  Phase 1 produces d_W | d_b, which are
-                # reduced over the ranks on the communication stream while phase 2 computes d_h.
+                # loss_sum rides in the same exchange range as d_W | d_b.  The backward walks the label axis range by
+                # range: each range's rows of d_W are reduced over the ranks on the communication stream while the
+                # next range (and finally d_h) is computed.
                 g = self.grad_x.tensor
+                Dh = c["Dh"]
                 loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head, loss_out=g[self.n_grad:])
-                _, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
-                                                      return_flat=True, want_dh=False, flat_out=g[:self.n_grad], ws_from_fwd=True)
-                self.s_comm.wait_stream(s_ce)
-                with torch.cuda.stream(self.s_comm):
-                    self.grad_x.all_reduce_sum_()
+                for v0, v1 in self.v_ranges:
+                    _, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global,
+                                                          ws=ws, return_flat=True, want_dh=False, flat_out=g[:self.n_grad],
+                                                          ws_from_fwd=True, v_range=(v0, v1))
+                    self.s_comm.wait_stream(s_ce)
+                    with torch.cuda.stream(self.s_comm):
+                        last = v1 == c["V"]         # the last exchange also carries d_b | loss_sum, which follow d_W
+                        numel = (self.grad_x.padded - v0 * Dh) if last else (v1 - v0) * Dh
+                        self.peer.all_reduce_sum_(self.grad_x.offset + 4 * v0 * Dh, numel)
                 d_h, _, _ = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
                                               want_dw=False)
         main.wait_stream(s_ema)
         main.wait_stream(s_ce)
         if self.dp:
             main.wait_stream(self.s_comm)
+            main.wait_stream(self.s_comm_ema)
         self.out = dict(idx=idx, x_rows=x_rows, q=q, loss_c=loss_c, g_x=g_x, sums=sums, loss_sum=loss_sum, lse=lse, ws=ws,
                         d_h=d_h, d_W=d_W, d_b=d_b, flat=flat)
         return self.out
@@ -543,7 +557,8 @@ def our_arm(args):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, **{k: c[k] for k in ("lines", "frames", "K", "D", "Dh", "V", "p")},
                            "masked_frames_per_step": m_total, "frames_per_step": N * world, "parallelism": f"dp{world}" if dp else "single",
-                           "exchange": (f"libpero peer all-reduce ({ds.peer.transport}, {ds.peer.n_blocks} CTAs)" if dp else None),
+                           "exchange": (f"libpero peer all-reduce ({ds.peer.transport}, {ds.peer.n_blocks} CTAs), head backward in "
+                                        f"{len(ds.v_ranges)} label ranges" if dp else None),
                            "l2": "flushed (256 MiB write) between timed steps", "launch": "cuda_graph" if graph is not None else "eager"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": (n_ours if n_ours > 0 else n_kernels) * args.steps, "kernels_per_step": n_kernels, "clocks": clocks}

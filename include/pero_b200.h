@@ -158,6 +158,15 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
                        const int64_t* labels, const void* head, int64_t V, const float* lse,
                        const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
                        void* workspace, size_t workspace_bytes, pero_stream_t stream);
+/* The same backward restricted to the label columns [v_begin, v_end) (v_begin and v_end multiples of 256, or
+ * v_end = V): rows [v_begin, v_end) of d_W and d_b (pointers to the FULL arrays) and the matching columns of the
+ * dlogits kept in the workspace.  A data-parallel caller walks the label axis range by range and exchanges each
+ * range of d_W while the next one is being computed; once all ranges are done, a call with d_W = d_b = NULL and
+ * d_h given produces d_h.  d_h together with d_W/d_b is accepted only for the full range. */
+int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+                             const int64_t* labels, const void* head, int64_t V, const float* lse,
+                             const float* grad_scale, float inv_count, int64_t v_begin, int64_t v_end, void* d_h,
+                             float* d_W, float* d_b, void* workspace, size_t workspace_bytes, pero_stream_t stream);
 /* Logits-in variant for callers that already hold logits [N, V] (fp32 or bf16):
  * MaskedCrossEntropyLoss.forward(output, labels, mask), masked_pretraining/model.py:78-82.
  * workspace: >= 4*M bytes rounded up to 256.  d_logits has the dtype of logits; zero_init != 0 clears it

@@ -48,6 +48,8 @@ SIGNATURES = {
                                    c_sz, c_vp]),
     "pero_masked_ce_bwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32,
                                    c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pero_masked_ce_bwd_range": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32,
+                                         c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pero_ce_logits_fwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pero_ce_logits_bwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_int, c_vp, c_vp]),
     "pero_mask_compact_workspace_bytes": (c_sz, [c_i64]),

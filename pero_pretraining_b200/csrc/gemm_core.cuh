@@ -127,8 +127,11 @@ __device__ __forceinline__ void stamp_cta(const GemmShape& sh, bool on, int slot
     }
 }
 
+// 128 registers per thread (384 threads -> 48 K of the SM's 64 K registers): the remaining 16 K let one CTA of a
+// bandwidth-bound kernel or of the peer-exchange kernel run on the same SM, so those kernels overlap a resident
+// GEMM instead of waiting for it (or, worse, keeping the next GEMM's CTA off the SM).
 template <int kCtaGroup, bool kAResident, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __maxnreg__(128)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmShape sh, const typename Epi::Params ep) {
     extern __shared__ uint8_t smem_raw[];

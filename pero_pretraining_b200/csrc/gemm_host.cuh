@@ -67,12 +67,15 @@ inline int device_sm_count() {
 inline unsigned long long* g_debug_timeline = nullptr;
 
 constexpr size_t kSmemBudget = 227 * 1024;
+// Budget for GEMMs that run beside other chains of the step (masked CE): leaves ~27 KB of shared memory and, with
+// the 128-register cap of the kernel, 16 K registers per SM for a co-resident bandwidth-bound or exchange CTA.
+constexpr size_t kSmemBudgetShared = 200 * 1024;
 constexpr size_t kSmemFloor = 120 * 1024;   // > half an SM: never two TMEM-hungry CTAs on one SM
 
 // Picks the deepest ring that fits; returns 0 when even 2 stages do not fit.
-inline int pick_stages(int cta_group, bool a_resident, int num_kb, int scratch_per_warp) {
+inline int pick_stages(int cta_group, bool a_resident, int num_kb, int scratch_per_warp, size_t budget = kSmemBudget) {
     for (int s = kMaxStages; s >= 2; --s)
-        if (gemm_smem_bytes(cta_group, a_resident, num_kb, s, scratch_per_warp) <= kSmemBudget) return s;
+        if (gemm_smem_bytes(cta_group, a_resident, num_kb, s, scratch_per_warp) <= budget) return s;
     return 0;
 }
 
@@ -81,7 +84,7 @@ inline int pick_stages(int cta_group, bool a_resident, int num_kb, int scratch_p
 template <int kCtaGroup, bool kAResident, class Epi>
 int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int rows_b, int pitch_b, int kd,
                    int num_ks, int split_mode, int fixed_s, int workers, const typename Epi::Params& ep,
-                   cudaStream_t stream, unsigned long long* timeline = nullptr) {
+                   cudaStream_t stream, unsigned long long* timeline = nullptr, size_t smem_budget = kSmemBudget) {
     if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
     GemmShape sh;
     sh.timeline = timeline ? timeline : g_debug_timeline;
@@ -95,7 +98,7 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     sh.num_ks = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;   // no empty splits
     sh.split_mode = split_mode; sh.fixed_s = fixed_s < 1 ? 1 : fixed_s;
     if (kAResident && (sh.num_ks != 1 || sh.num_kb > kMaxAKb)) return PERO_ERR_BAD_SHAPE;
-    sh.num_stages = pick_stages(kCtaGroup, kAResident, sh.num_kb, Epi::kScratchPerWarp);
+    sh.num_stages = pick_stages(kCtaGroup, kAResident, sh.num_kb, Epi::kScratchPerWarp, smem_budget);
     if (sh.num_stages < 2) return PERO_ERR_BAD_SHAPE;
 
     CUtensorMap ta, tb;

@@ -225,9 +225,11 @@ struct DlogitsEpi {
         const float* colvec;  // bias [Vt], -inf beyond V
         const int* lab; const float* lse; const float* grad_scale;
         float inv_count;
-        __nv_bfloat16* p; __nv_bfloat16* pt;
-        int M, V, Vp, Mp64;
-        int debug_skip;       // measurement only: 1 = skip P stores, 2 = skip P^T stores
+        __nv_bfloat16* p; __nv_bfloat16* pt;   // already offset to the first label column / row of the range
+        int M, V, Vp, Mp64;    // V, Vp: number of label columns of the range (exact / rounded up to 64)
+        int p_pitch;           // row pitch of P (the full padded label count)
+        int col_base;          // global index of the range's first label column
+        int debug_skip;        // measurement only: 1 = skip P stores, 2 = skip P^T stores
     };
     struct State { float lse2, scale; int label; };
     static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
@@ -254,7 +256,7 @@ struct DlogitsEpi {
                 g[4 * i + 2] = ex2_fast(fmaf(__uint_as_float(r[4 * i + 2]) + b.z, kLog2e, -st.lse2)) * st.scale;
                 g[4 * i + 3] = ex2_fast(fmaf(__uint_as_float(r[4 * i + 3]) + b.w, kLog2e, -st.lse2)) * st.scale;
             }
-            const unsigned rel = (unsigned)(st.label - col);    // (p - 1) * scale at the label column
+            const unsigned rel = (unsigned)(st.label - ep.col_base - col);    // (p - 1) * scale at the label column
             if (rel < 32u) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) if (rel == (unsigned)j) g[j] -= st.scale;
@@ -273,7 +275,7 @@ struct DlogitsEpi {
                 const int rr = 8 * k + (lane >> 2), piece = lane & 3;
                 const uint4 v = *reinterpret_cast<const uint4*>(cx.scratch + rr * 80 + piece * 16);
                 if (col_ok && row_base + rr < ep.M && !(ep.debug_skip & 1))
-                    *reinterpret_cast<uint4*>(ep.p + (size_t)(row_base + rr) * ep.Vp + col + piece * 8) = v;
+                    *reinterpret_cast<uint4*>(ep.p + (size_t)(row_base + rr) * ep.p_pitch + col + piece * 8) = v;
             }
             __syncwarp();
             // ---- P^T columns: chunk staged column-major in the same buffer; one store instruction = 4 columns
@@ -585,7 +587,8 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     ep.zlab = reinterpret_cast<float*>(ws + l.zlab_off);
     ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S;
     rc = launch_gemm_tn<2, true, LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
-                                         /*split_mode=*/1, (int)l.S, 0, ep, stream);
+                                         /*split_mode=*/1, (int)l.S, 0, ep, reinterpret_cast<cudaStream_t>(stream), nullptr,
+                                         kSmemBudgetShared);
     if (rc) return rc;
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
     ce_finalize_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
@@ -594,60 +597,71 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     return (int)cudaGetLastError();
 }
 
-int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
-                       const int64_t* labels, const void* head, int64_t V, const float* lse,
-                       const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
-                       void* workspace, size_t workspace_bytes, pero_stream_t stream) {
+int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+                             const int64_t* labels, const void* head, int64_t V, const float* lse,
+                             const float* grad_scale, float inv_count, int64_t v_begin, int64_t v_end, void* d_h, float* d_W,
+                             float* d_b, void* workspace, size_t workspace_bytes, pero_stream_t stream) {
     if (M == 0) return PERO_ERR_BAD_SHAPE;
     int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes, /*h_optional=*/true);
     if (rc) return rc;
     // h == NULL: the workspace is the one pero_masked_ce_fwd ran on for the same (h, rows, labels) and still holds
     // the gathered operands (A, A^T, labels, inverse row map): no second gather.
-    // Two-phase use (lets a data-parallel caller all-reduce d_W | d_b while d_h is still being computed):
-    //   phase 1: d_W, d_b given (d_h may be NULL)  -> dlogits P / P^T into the workspace, d_W, d_b [, d_h]
-    //   phase 2: d_W == d_b == NULL, d_h given     -> d_h from the P left in the SAME workspace by phase 1
-    const bool phase2_only = (!d_W && !d_b && d_h);
-    if (!lse || (!phase2_only && (!d_W || !d_b))) return PERO_ERR_NULL;
+    // Phases (a data-parallel caller exchanges d_W | d_b of one label range while the next is being computed):
+    //   d_W, d_b given  -> dlogits P / P^T of label columns [v_begin, v_end) into the workspace, rows [v_begin, v_end)
+    //                      of d_W and d_b; then, if d_h is given too (requires the full range), d_h
+    //   d_W == d_b == NULL, d_h given -> d_h from the P that earlier calls left in the SAME workspace for ALL columns
+    const bool dh_only = (!d_W && !d_b && d_h);
+    if (!lse || (!dh_only && (!d_W || !d_b))) return PERO_ERR_NULL;
     if (Dh % 4 != 0) return PERO_ERR_BAD_SHAPE;
+    if (v_begin < 0 || v_end > V || v_begin >= v_end || (v_begin % 256) != 0 || (v_end != V && (v_end % 256) != 0))
+        return PERO_ERR_BAD_SHAPE;
+    const bool full_range = (v_begin == 0 && v_end == V);
+    if (d_h && !dh_only && !full_range) return PERO_ERR_UNSUPPORTED;
     const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
     const HeadLayout hl = head_layout(V, Dh);
     char* ws = static_cast<char*>(workspace);
     const char* hb = static_cast<const char*>(head);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int* inv = reinterpret_cast<int*>(ws + l.inv_off);
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + l.p_off);
     __nv_bfloat16* PT = reinterpret_cast<__nv_bfloat16*>(ws + l.pt_off);
     static int store_pairs = -1;     // PERO_CE_STORE_PAIRS=0: gradient GEMMs on single CTAs (tuning knob)
     if (store_pairs < 0) { const char* e = getenv("PERO_CE_STORE_PAIRS"); store_pairs = e ? atoi(e) : 1; }
-    const bool db_in_scatter = !phase2_only && d_h != nullptr;
-    if (!phase2_only) {
-    if (h) {
-        rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream)
-                       : launch_ce_gather<float>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream);
+    const bool db_in_scatter = !dh_only && d_h != nullptr;
+    if (!dh_only) {
+        if (h && v_begin == 0) {
+            rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, N, (int)M, (int)Dh, l, ws, st)
+                           : launch_ce_gather<float>(h, rows, labels, N, (int)M, (int)Dh, l, ws, st);
+            if (rc) return rc;
+        }
+        const int64_t vlen = v_end - v_begin;
+        __nv_bfloat16* PTr = PT + (size_t)v_begin * l.Mp64;
+
+        DlogitsEpi::Params ep;
+        ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off) + v_begin;
+        ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
+        ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
+        { const char* e = getenv("PERO_DLOGITS_SKIP"); ep.debug_skip = e ? atoi(e) : 0; }
+        ep.p = P + v_begin; ep.pt = PTr; ep.M = (int)M; ep.V = (int)vlen;
+        ep.Vp = (int)(v_end == V ? l.Vp - v_begin : vlen);      // the last range also writes P's zero padding columns
+        ep.Mp64 = (int)l.Mp64; ep.p_pitch = (int)l.Vp; ep.col_base = (int)v_begin;
+        rc = launch_gemm_tn<2, true, DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off + (size_t)v_begin * l.Dhp * 2,
+                                                 (int)vlen, (int)l.Dhp, (int)l.Dhp, 1, 0, 1, 0, ep, st, nullptr, kSmemBudgetShared);
         if (rc) return rc;
+
+        // d_W [v_begin:v_end, Dh] = P^T [v_begin:v_end, Mp64] @ A^T [Dh, Mp64]^T
+        StoreEpi::Params sw;
+        sw.out = d_W + (size_t)v_begin * Dh; sw.ld = Dh; sw.split_stride = 0; sw.rows = (int)vlen; sw.cols = (int)Dh;
+        rc = store_pairs
+                 ? launch_gemm_tn<2, false, StoreEpi>(PTr, (int)vlen, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1,
+                                                      0, 1, 0, sw, st, nullptr, kSmemBudgetShared)
+                 : launch_gemm_tn<1, false, StoreEpi>(PTr, (int)vlen, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1,
+                                                      0, 1, 0, sw, st, nullptr, kSmemBudgetShared);
+        if (rc) return rc;
+        // d_b: alone when this call stops after d_W | d_b (they are exchanged next), otherwise inside the scatter launch
+        if (!db_in_scatter)
+            ce_db_kernel<<<(unsigned)((vlen + 7) / 8), 256, 0, st>>>(PTr, (int)vlen, (int)M, (int)l.Mp64, d_b + v_begin);
     }
-
-    DlogitsEpi::Params ep;
-    ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
-    ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
-    ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
-    { const char* e = getenv("PERO_DLOGITS_SKIP"); ep.debug_skip = e ? atoi(e) : 0; }
-    ep.p = P; ep.pt = PT; ep.M = (int)M; ep.V = (int)V; ep.Vp = (int)l.Vp; ep.Mp64 = (int)l.Mp64;
-    rc = launch_gemm_tn<2, true, DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
-                                             0, 1, 0, ep, stream);
-    if (rc) return rc;
-
-    // d_W [V, Dh] = P^T [V, Mp64] @ A^T [Dh, Mp64]^T
-    StoreEpi::Params sw;
-    sw.out = d_W; sw.ld = Dh; sw.split_stride = 0; sw.rows = (int)V; sw.cols = (int)Dh;
-    rc = store_pairs
-             ? launch_gemm_tn<2, false, StoreEpi>(PT, (int)V, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1, 0, 1,
-                                                  0, sw, stream)
-             : launch_gemm_tn<1, false, StoreEpi>(PT, (int)V, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1, 0, 1,
-                                                  0, sw, stream);
-    if (rc) return rc;
-    // d_b: alone when this call stops after d_W | d_b (they are exchanged next), otherwise inside the scatter launch
-    if (!db_in_scatter) ce_db_kernel<<<(unsigned)((V + 7) / 8), 256, 0, stream>>>(PT, (int)V, (int)M, (int)l.Mp64, d_b);
-    }   // !phase2_only
 
     if (d_h) {
         // planes[ks] [M, Dh] = P [M, Vp] @ W^T [Dh, Vp]^T over the ks-th slice of the label axis
@@ -656,9 +670,9 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
         sh.out = planes; sh.ld = Dh; sh.split_stride = (long long)M * Dh; sh.rows = (int)M; sh.cols = (int)Dh;
         rc = store_pairs
                  ? launch_gemm_tn<2, false, StoreEpi>(P, (int)M, (int)l.Vp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
-                                                      1, 0, sh, stream)
+                                                      1, 0, sh, st, nullptr, kSmemBudgetShared)
                  : launch_gemm_tn<1, false, StoreEpi>(P, (int)M, (int)l.Vp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
-                                                      1, 0, sh, stream);
+                                                      1, 0, sh, st, nullptr, kSmemBudgetShared);
         if (rc) return rc;
         const long long total = N * (Dh / 4);
         long long blocks = (total + 255) / 256;
@@ -670,15 +684,23 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
         const int kb_per = (num_kb + (int)l.KS - 1) / (int)l.KS;
         const int ks_eff = (num_kb + kb_per - 1) / kb_per;
         if (h_is_bf16)
-            ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
-                                                                                     static_cast<__nv_bfloat16*>(d_h), db_blocks, PT,
-                                                                                     (int)V, (int)l.Mp64, d_b);
+            ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
+                                                                                 static_cast<__nv_bfloat16*>(d_h), db_blocks, PT,
+                                                                                 (int)V, (int)l.Mp64, d_b);
         else
-            ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
-                                                                             static_cast<float*>(d_h), db_blocks, PT, (int)V,
-                                                                             (int)l.Mp64, d_b);
+            ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
+                                                                         static_cast<float*>(d_h), db_blocks, PT, (int)V,
+                                                                         (int)l.Mp64, d_b);
     }
     return (int)cudaGetLastError();
+}
+
+int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+                       const int64_t* labels, const void* head, int64_t V, const float* lse,
+                       const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
+                       void* workspace, size_t workspace_bytes, pero_stream_t stream) {
+    return pero_masked_ce_bwd_range(h, h_is_bf16, N, Dh, rows, M, labels, head, V, lse, grad_scale, inv_count, 0, V, d_h, d_W,
+                                    d_b, workspace, workspace_bytes, stream);
 }
 
 int pero_ce_logits_fwd(const void* logits, int is_bf16, int64_t N, int64_t V, const int32_t* rows, int64_t M,

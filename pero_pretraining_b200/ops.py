@@ -214,10 +214,12 @@ def masked_ce_fwd(h, rows, labels, head, loss_out=None):
 
 
 def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False,
-                  want_dw=True, flat_out=None, ws_from_fwd=False):
+                  want_dw=True, flat_out=None, ws_from_fwd=False, v_range=None):
     """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32[, flat buffer holding d_W|d_b]).
     ws_from_fwd: `ws` is the workspace masked_ce_fwd returned for the same (h, rows, labels) and has not been
-    touched since: the gathered operands in it are reused instead of gathering again."""
+    touched since: the gathered operands in it are reused instead of gathering again.
+    v_range=(v0, v1): only label columns [v0, v1) (multiples of 256 or V): rows v0:v1 of d_W / d_b; needs
+    want_dh=False, and a final call with want_dw=False for d_h once every range is done."""
     L = _lib.lib()
     h = _check_h(h)
     N, Dh = h.shape
@@ -234,10 +236,11 @@ def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=Tru
     if ws is None or ws.numel() < wsb:
         ws = _ws(wsb, h.device)
     gs = None if grad_scale is None else _f32c(grad_scale, "grad_scale")
-    check(L.pero_masked_ce_bwd(None if ws_from_fwd else h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M,
-                               labels.data_ptr(), head.blob.data_ptr(), head.V, lse.data_ptr(), _p(gs),
-                               float(inv_count), _p(d_h), _p(d_W), _p(d_b), ws.data_ptr(), wsb,
-                               _stream()), "pero_masked_ce_bwd")
+    v0, v1 = (0, head.V) if v_range is None else (int(v_range[0]), int(v_range[1]))
+    check(L.pero_masked_ce_bwd_range(None if ws_from_fwd else h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh,
+                                     rows.data_ptr(), M, labels.data_ptr(), head.blob.data_ptr(), head.V, lse.data_ptr(), _p(gs),
+                                     float(inv_count), v0, v1, _p(d_h), _p(d_W), _p(d_b), ws.data_ptr(), wsb,
+                                     _stream()), "pero_masked_ce_bwd_range")
     return (d_h, d_W, d_b, flat) if return_flat else (d_h, d_W, d_b)
 
 

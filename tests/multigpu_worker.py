@@ -82,9 +82,10 @@ def check_peer_allreduce(dev, rank, world):
         got = rng_f.tensor.cpu()
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-5 * float(want.abs().max())), "graph replay"
         # timing of the 8.4 MB EMA exchange and a 16.8 MB gradient exchange (device events, max over ranks)
-        big = PeerBuffer(4 * (8192 * 512 + 8192) + 1024, dev, use_multicast=use_mc)
+        big = PeerBuffer(4 * (8192 * 512 + 8192) + 2048, dev, use_multicast=use_mc)
         rng_g = PeerRange(big, 8192 * 512 + 8192, torch.float32)
-        for name, rg in (("ema 8.4 MB", rng_f), ("grad 16.8 MB", rng_g)):
+        tiny = PeerRange(big, 4, torch.float32)
+        for name, rg in (("16 B (fixed cost)", tiny), ("ema 8.4 MB", rng_f), ("grad 16.8 MB", rng_g)):
             for blocks in (8, 16, 24, 32, 48):
                 rg.tensor.zero_()
                 for _ in range(3):

@@ -162,3 +162,31 @@ def test_mask_compact_matches_nonzero(cuda_dev):
         rows0, count0 = ops.mask_compact(m, labels, 0)
         ref0 = torch.nonzero((m.reshape(-1).long() == 0) & (labels.reshape(-1) >= 0)).flatten()
         assert int(count0) == ref0.numel() and torch.equal(rows0[:ref0.numel()].long(), ref0)
+
+
+def test_backward_by_label_ranges_equals_full_backward(cuda_dev):
+    """pero_masked_ce_bwd_range: walking the label axis range by range (what the data-parallel step does to overlap
+    the exchange of d_W with the next range) gives bit-identical d_W, d_b and d_h."""
+    from pero_pretraining_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    N, Dh, V, M = 1024, 512, 1300, 150
+    h = torch.randn(N, Dh, generator=g).to(cuda_dev)
+    W = (torch.randn(V, Dh, generator=g) * 0.05).to(cuda_dev)
+    b = (torch.randn(V, generator=g) * 0.1).to(cuda_dev)
+    labels = torch.randint(0, V, (N,), generator=g).to(cuda_dev)
+    rows = torch.sort(torch.randperm(N, generator=g)[:M]).values.int().to(cuda_dev)
+    head = ops.PreparedHead(V, Dh, cuda_dev).prepare(W, b)
+    loss_sum, lse, ws = ops.masked_ce_fwd(h, rows, labels, head)
+    d_h, d_W, d_b = ops.masked_ce_bwd(h, rows, labels, head, lse, None, 1.0 / M, ws=ws, ws_from_fwd=True)
+    loss_sum2, lse2, ws2 = ops.masked_ce_fwd(h, rows, labels, head)
+    assert torch.equal(lse, lse2) and torch.equal(loss_sum, loss_sum2)
+    flat = torch.full((V * Dh + V,), float("nan"), device=cuda_dev)
+    for v0, v1 in ((0, 512), (512, 1024), (1024, V)):
+        ops.masked_ce_bwd(h, rows, labels, head, lse2, None, 1.0 / M, ws=ws2, ws_from_fwd=True, want_dh=False, flat_out=flat,
+                          return_flat=True, v_range=(v0, v1))
+    d_h2, _, _ = ops.masked_ce_bwd(h, rows, labels, head, lse2, None, 1.0 / M, ws=ws2, want_dw=False)
+    assert torch.equal(flat[:V * Dh].view(V, Dh), d_W)
+    assert torch.equal(flat[V * Dh:], d_b)
+    assert torch.equal(d_h2, d_h)
+    with pytest.raises(Exception):                    # ranges must start on a multiple of 256
+        ops.masked_ce_bwd(h, rows, labels, head, lse2, None, 1.0 / M, ws=ws2, want_dh=False, v_range=(100, 512))

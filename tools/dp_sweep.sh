@@ -10,10 +10,9 @@ run() {
     grep -o '"ms_per_step": [0-9.]*\|"exchange": "[^"]*"' gpurun_out/sweep_tmp.log | head -3
     grep -i "error\|Traceback\|DEADLINE" gpurun_out/sweep_tmp.log | head -5
 }
-run PERO_X=default
-run PERO_PEER_THREADS=256 PERO_PEER_BLOCKS=8
-run PERO_PEER_THREADS=256 PERO_PEER_BLOCKS=24
-run PERO_PEER_THREADS=512 PERO_PEER_BLOCKS=8
-run PERO_PEER_THREADS=512 PERO_PEER_BLOCKS=16
-run PERO_PEER_THREADS=128 PERO_PEER_BLOCKS=32
-run PERO_PEER_MULTICAST=0 PERO_PEER_THREADS=512 PERO_PEER_BLOCKS=48
+run PERO_DP_CHUNKS=1
+run PERO_DP_CHUNKS=2
+run PERO_DP_CHUNKS=4
+run PERO_DP_CHUNKS=2 PERO_PEER_BLOCKS=24
+run PERO_DP_CHUNKS=2 PERO_PEER_BLOCKS=32 PERO_PEER_THREADS=128
+run PERO_DP_CHUNKS=2 PERO_PEER_MULTICAST=0 PERO_PEER_THREADS=512 PERO_PEER_BLOCKS=48
