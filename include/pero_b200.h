@@ -109,6 +109,18 @@ int pero_vq_ema_apply(const float* sums_counts, int64_t K, int64_t D, double dec
 /* counts[k] = #frames with idx == k as int64 (models/autoencoders.py:165, torch.bincount). */
 int pero_vq_counts(const int64_t* idx, int64_t N, int64_t K, int64_t* counts, pero_stream_t stream);
 
+/* ------------------------------------------------------------------ the whole quantizer forward in one call
+ * Replaces  models/autoencoders.py:204-241  (VectorQuantizer.forward): pero_vq_assign -> pero_vq_gather_st ->
+ * (update_ema != 0: decay > 0 and training) pero_vq_ema_accumulate -> pero_vq_ema_apply, enqueued back to back on
+ * `stream` out of ONE workspace.  quantized [n_lines, D, frames_per_line] (or rows), idx [N] int64.  The
+ * single-process path; data-parallel callers use the stage-level calls with the exchange between accumulate and
+ * apply.  `codebook` is the prepared blob of `weight` (refreshed by the EMA update). */
+size_t pero_vq_forward_workspace_bytes(int64_t N, int64_t K, int64_t D, int update_ema);
+int pero_vq_forward(const float* x, int64_t n_lines, int64_t frames_per_line, int channels_first, int64_t K, int64_t D,
+                    void* codebook, size_t codebook_bytes, float* weight, float* ema_w, float* ema_cluster_size,
+                    double decay, double epsilon, int update_ema, float* quantized, int64_t* idx, void* workspace,
+                    size_t workspace_bytes, pero_stream_t stream);
+
 /* ------------------------------------------------------------------ commitment / latent loss
  * Replaces  models/autoencoders.py:193-202  (VectorQuantizer.calculate_loss = mse_loss terms).
  * pero_mse_fwd: m = mean((a - b)^2); out[0] = scale_a * m + scale_b * m (each product rounded to fp32,

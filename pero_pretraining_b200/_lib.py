@@ -36,6 +36,9 @@ SIGNATURES = {
     "pero_vq_ema_accumulate": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "pero_vq_ema_apply": (c_int, [c_vp, c_i64, c_i64, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_sz,
                                   c_vp]),
+    "pero_vq_forward_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
+    "pero_vq_forward": (c_int, [c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_sz, c_vp, c_vp, c_vp, c_f64, c_f64, c_int,
+                                c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pero_vq_counts": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "pero_mse_workspace_bytes": (c_sz, [c_i64]),
     "pero_mse_fwd": (c_int, [c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_sz, c_vp]),

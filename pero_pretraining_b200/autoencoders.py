@@ -27,11 +27,22 @@ class _QuantizeST(torch.autograd.Function):
         x = inputs.detach()
         if x.dtype != torch.float32:
             x = x.float()
-        x = x.contiguous()
+        if not x.is_contiguous():
+            x = x.contiguous()
         cb = vq._prepared_codebook()
         update = vq.decay > 0.0 and vq.training
-        idx, _, x_rows = ops.vq_assign(x, cb, n_lines, frames, channels_first=True, want_rows=True)
         weight = vq.embedding.weight.data
+        if vq._dp_group is None:
+            # single process: one call of the C ABI for assign -> quantize -> EMA update
+            out, idx = ops.vq_forward(x, cb, weight, vq.ema_w.data if update else None,
+                                      vq.ema_cluster_size if update else None, vq.decay, vq.epsilon, update and x.numel() > 0,
+                                      n_lines, frames, channels_first=True)
+            if update and x.numel() > 0:
+                vq._codebook_tag = vq._weight_tag()
+            ctx.mark_non_differentiable(idx)
+            return out.view(inputs.shape), idx
+        # data parallel: the EMA sums|counts are exchanged between accumulate and apply
+        idx, _, x_rows = ops.vq_assign(x, cb, n_lines, frames, channels_first=True, want_rows=True)
         out = ops.vq_gather_st(x_rows, idx, weight, n_lines, frames, channels_first=True)
         if update and idx.numel() > 0:
             if vq._peer_range is not None:      # [K, D+1] SUM over ranks, in place in the peer-mapped range
@@ -39,8 +50,7 @@ class _QuantizeST(torch.autograd.Function):
                 vq._peer_range.all_reduce_sum_()
             else:
                 sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings)
-                if vq._dp_group is not None:
-                    torch.distributed.all_reduce(sums_counts, group=vq._dp_group)
+                torch.distributed.all_reduce(sums_counts, group=vq._dp_group)
             ops.vq_ema_apply(sums_counts, vq.ema_w.data, vq.ema_cluster_size, weight, vq.decay, vq.epsilon, cb)
             vq._codebook_tag = vq._weight_tag()
         ctx.mark_non_differentiable(idx)
@@ -56,8 +66,15 @@ class _WeightedMse(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tokens, features, w_tokens, w_features):
-        t = tokens.detach().float().contiguous()
-        f = features.detach().float().contiguous()
+        t, f = tokens.detach(), features.detach()
+        if t.dtype != torch.float32:
+            t = t.float()
+        if f.dtype != torch.float32:
+            f = f.float()
+        if not t.is_contiguous():
+            t = t.contiguous()
+        if not f.is_contiguous():
+            f = f.contiguous()
         ctx.save_for_backward(t, f)
         ctx.w = (float(w_tokens), float(w_features))
         ctx.dtypes = (tokens.dtype, features.dtype)
@@ -68,15 +85,19 @@ class _WeightedMse(torch.autograd.Function):
     def backward(ctx, g):
         t, f = ctx.saved_tensors
         w_t, w_f = ctx.w
-        g = g.detach().float().contiguous()
+        g = g.detach()
+        if g.dtype != torch.float32 or not g.is_contiguous():
+            g = g.float().contiguous()
         numel = t.numel()
         g_t = g_f = None
         if ctx.needs_input_grad[0] and w_t != 0.0:
             _, g_t = ops.mse_bwd(t, f, -2.0 * w_t / numel, g, want_a=False, want_b=True)   # w_t*2/n*(t - f)
-            g_t = g_t.to(ctx.dtypes[0])
+            if ctx.dtypes[0] != torch.float32:
+                g_t = g_t.to(ctx.dtypes[0])
         if ctx.needs_input_grad[1] and w_f != 0.0:
             _, g_f = ops.mse_bwd(t, f, 2.0 * w_f / numel, g, want_a=False, want_b=True)    # w_f*2/n*(f - t)
-            g_f = g_f.to(ctx.dtypes[1])
+            if ctx.dtypes[1] != torch.float32:
+                g_f = g_f.to(ctx.dtypes[1])
         return g_t, g_f, None, None
 
 

@@ -31,6 +31,24 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
                           uint32_t box_rows) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return PERO_ERR_DRIVER;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems & 7u) || box_rows == 0 || box_rows > 256)
+        return PERO_ERR_BAD_ALIGN;
+    // The encode is a pure function of its arguments and costs ~3 us of host time per call; a training loop asks
+    // for the same few descriptors every step (the caching allocator hands back the same addresses), so the last
+    // results are memoised per thread.  Nothing here refers to device state: a stale entry cannot exist.
+    struct Key { const void* base; uint64_t rows, cols, pitch; uint32_t box_rows; };
+    struct Entry { Key k; CUtensorMap map; bool valid; };
+    constexpr int kSlots = 32;
+    static thread_local Entry cache[kSlots] = {};
+    const Key key{base, rows, cols, pitch_elems, box_rows};
+    uint64_t hsh = reinterpret_cast<uintptr_t>(base) >> 8;
+    hsh = (hsh ^ (rows * 0x9E3779B97F4A7C15ull) ^ (cols << 17) ^ (pitch_elems << 29) ^ box_rows) * 0xD6E8FEB86659FD93ull;
+    Entry& e = cache[(hsh >> 40) % kSlots];
+    if (e.valid && e.k.base == key.base && e.k.rows == key.rows && e.k.cols == key.cols && e.k.pitch == key.pitch &&
+        e.k.box_rows == key.box_rows) {
+        *out = e.map;
+        return PERO_OK;
+    }
     // The encode is a DRIVER call and needs the primary context current on the calling thread.  A thread whose
     // first CUDA action is this call (e.g. PyTorch's autograd worker entering a backward that starts with a
     // GEMM) has none yet: cudaSetDevice binds it (legal during stream capture, once per thread).
@@ -40,8 +58,6 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
         if (cudaGetDevice(&dev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) return PERO_ERR_DRIVER;
         context_bound = true;
     }
-    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems & 7u) || box_rows == 0 || box_rows > 256)
-        return PERO_ERR_BAD_ALIGN;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {pitch_elems * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
@@ -49,7 +65,9 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? PERO_OK : PERO_ERR_DRIVER;
+    if (r != CUDA_SUCCESS) return PERO_ERR_DRIVER;
+    e.k = key; e.map = *out; e.valid = true;
+    return PERO_OK;
 }
 
 inline int device_sm_count() {

@@ -107,12 +107,12 @@ head_prepare_kernel(const float* __restrict__ W, const float* __restrict__ bias,
 }
 
 // Gather the masked frames into the GEMM operand A [M, Dhp] bf16 and A^T [Dh, Mp64] (operand of d_W), their
-// labels, and the inverse frame -> masked-row map inv [N] (-1 for frames that are not selected; `rows` is
-// ascending, so the map is a binary search — no separate initialisation pass).  Tiles of 32 masked rows x 32
-// channels.  Also clears the ticket word that ce_finalize_kernel's last block uses.
+// labels, and the inverse frame -> masked-row map inv [N] at the selected frames (see masked_row_of: no
+// initialisation pass over the other frames is needed).  Tiles of 32 masked rows x 32 channels.  Also clears the
+// ticket word that ce_finalize_kernel's last block uses.
 template <typename T>
 __global__ void __launch_bounds__(256)
-ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const long long* __restrict__ labels, long long N, int M,
+ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const long long* __restrict__ labels, int M,
                  int Dh, int Dhp, int Mp64, int Mpad, __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ at,
                  int* __restrict__ lab, int* __restrict__ inv, unsigned int* __restrict__ ticket) {
     __shared__ float tile[32][33];
@@ -136,17 +136,19 @@ ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const lo
         const int m = m0 + (int)threadIdx.x;
         if (m < Mpad) lab[m] = m < M ? (int)__ldg(labels + __ldg(rows + m)) : -1;
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;
-    // inverse map: frame n -> its position in `rows`, or -1
-    const long long nthreads = (long long)gridDim.x * gridDim.y * blockDim.x;
-    for (long long n = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; n < N; n += nthreads) {
-        int lo = 0, hi = M;                       // first position with rows[pos] >= n
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((long long)__ldg(rows + mid) < n) lo = mid + 1; else hi = mid;
-        }
-        inv[n] = (lo < M && (long long)__ldg(rows + lo) == n) ? lo : -1;
+    if (blockIdx.y == 0 && threadIdx.x < 32) {
+        const int m = m0 + (int)threadIdx.x;
+        if (m < M) inv[__ldg(rows + m)] = m;
     }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;
+}
+
+// The frame -> masked-row map `inv` is written only at the selected frames; every other entry keeps whatever the
+// workspace held.  A reader validates a candidate m = inv[n] against `rows`: it is n's row iff 0 <= m < M and
+// rows[m] == n (rows are distinct, so a stale or garbage entry can never pass for the wrong frame).
+__device__ __forceinline__ int masked_row_of(const int* __restrict__ inv, const int* __restrict__ rows, long long n, int M) {
+    const int m = __ldg(inv + n);
+    return ((unsigned)m < (unsigned)M && (long long)__ldg(rows + m) == n) ? m : -1;
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
@@ -302,37 +304,40 @@ struct DlogitsEpi {
 
 // ------------------------------------------------------------------------------------------------ small kernels
 // lse[m] = log-sum-exp combined over the column-split partials; rowloss[m] = lse[m] - z[label].
-// One warp per row, lanes over the partial slots (all loads in flight at once; fixed butterfly order).
 // The block that finishes last (ticket) sums rowloss in a fixed order into loss_sum: no second launch, and the
 // result does not depend on which block that is.
 __global__ void __launch_bounds__(256)
 ce_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ zlab, int M, int Mpad,
                    int slots, float* __restrict__ lse, float* __restrict__ rowloss, unsigned int* __restrict__ ticket,
                    float* __restrict__ loss_sum) {
-    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    // 32 rows per block; thread (r = tid % 32, g = tid / 32) combines slots g, g + 8, ... of row r: every load
+    // instruction of a warp reads 32 consecutive rows of one slot (one 128-byte line), then the 8 groups are merged
+    // through shared memory in a fixed order.
+    __shared__ float gm[8][33], gs[8][33];
+    const int r = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int m = blockIdx.x * 32 + r;
+    const int lane = r;
+    float mx = -CUDART_INF_F, sum = 0.f;
     if (m < M) {
-        float pmv[4], psv[4];                    // slots <= 2 * kMaxLseSplits = 128 = 4 per lane
-        float mx = -CUDART_INF_F;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int s = lane + 32 * i;
-            pmv[i] = s < slots ? __ldg(pm + (size_t)s * Mpad + m) : -CUDART_INF_F;
-            psv[i] = s < slots ? __ldg(ps + (size_t)s * Mpad + m) : 0.f;
-            mx = fmaxf(mx, pmv[i]);
+        for (int s = g; s < slots; s += 8) {
+            const float pmv = __ldg(pm + (size_t)s * Mpad + m), psv = __ldg(ps + (size_t)s * Mpad + m);
+            const float nm = fmaxf(mx, pmv);
+            if (nm > -CUDART_INF_F) sum = sum * exp2f((mx - nm) * kLog2e) + psv * exp2f((pmv - nm) * kLog2e);
+            mx = nm;
         }
+    }
+    gm[g][r] = mx; gs[g][r] = sum;
+    __syncthreads();
+    if (g == 0 && m < M) {
+        float tm = gm[0][r];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
+        for (int k = 1; k < 8; ++k) tm = fmaxf(tm, gm[k][r]);
+        float ts = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sum += psv[i] * exp2f((pmv[i] - mx) * kLog2e);     // exp2(-inf) = 0 on empty slots
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) {
-            const float l = mx + log2f(sum) * kLn2;
-            lse[m] = l;
-            rowloss[m] = l - zlab[m];
-        }
+        for (int k = 0; k < 8; ++k) ts += gs[k][r] * exp2f((gm[k][r] - tm) * kLog2e);      // exp2(-inf) = 0 on empty groups
+        const float l = tm + log2f(ts) * kLn2;
+        lse[m] = l;
+        rowloss[m] = l - zlab[m];
     }
     __shared__ bool last;
     __shared__ float sh[8];
@@ -382,8 +387,8 @@ ce_db_kernel(const __nv_bfloat16* __restrict__ pt, int V, int M, int Mp64, float
 // gradient GEMMs.
 template <typename T>
 __global__ void __launch_bounds__(256)
-ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ inv, long long N, int M, int Dh, int KS,
-                     T* __restrict__ dh, int db_blocks, const __nv_bfloat16* __restrict__ pt, int V, int Mp64,
+ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ inv, const int* __restrict__ rows, long long N,
+                     int M, int Dh, int KS, T* __restrict__ dh, int db_blocks, const __nv_bfloat16* __restrict__ pt, int V, int Mp64,
                      float* __restrict__ db) {
     const int scatter_blocks = (int)gridDim.x - db_blocks;
     if ((int)blockIdx.x >= scatter_blocks) {
@@ -408,7 +413,7 @@ ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ i
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const long long n = i / g4;
         const int g = (int)(i - n * g4);
-        const int m = __ldg(inv + n);
+        const int m = masked_row_of(inv, rows, n, M);
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m >= 0) {
             for (int k = 0; k < KS; ++k) {
@@ -514,7 +519,7 @@ int launch_ce_gather(const void* h, const int32_t* rows, const int64_t* labels, 
                      char* ws, cudaStream_t stream) {
     dim3 grid((unsigned)((l.Mpad + 31) / 32), (unsigned)(l.Dhp / 32));
     ce_gather_kernel<T><<<grid, 256, 0, stream>>>(
-        static_cast<const T*>(h), rows, reinterpret_cast<const long long*>(labels), N, M, Dh, (int)l.Dhp, (int)l.Mp64, (int)l.Mpad,
+        static_cast<const T*>(h), rows, reinterpret_cast<const long long*>(labels), M, Dh, (int)l.Dhp, (int)l.Mp64, (int)l.Mpad,
         reinterpret_cast<__nv_bfloat16*>(ws + l.a_off), reinterpret_cast<__nv_bfloat16*>(ws + l.at_off),
         reinterpret_cast<int*>(ws + l.lab_off), reinterpret_cast<int*>(ws + l.inv_off),
         reinterpret_cast<unsigned int*>(ws + l.ticket_off));
@@ -591,7 +596,7 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
                                          kSmemBudgetShared);
     if (rc) return rc;
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
-    ce_finalize_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
+    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
                                                                 rowloss, reinterpret_cast<unsigned int*>(ws + l.ticket_off),
                                                                 loss_sum);
     return (int)cudaGetLastError();
@@ -641,7 +646,9 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off) + v_begin;
         ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
         ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
-        { const char* e = getenv("PERO_DLOGITS_SKIP"); ep.debug_skip = e ? atoi(e) : 0; }
+        static int dlogits_skip = -1;    // PERO_DLOGITS_SKIP: measurement knob, read once
+        if (dlogits_skip < 0) { const char* e = getenv("PERO_DLOGITS_SKIP"); dlogits_skip = e ? atoi(e) : 0; }
+        ep.debug_skip = dlogits_skip;
         ep.p = P + v_begin; ep.pt = PTr; ep.M = (int)M; ep.V = (int)vlen;
         ep.Vp = (int)(v_end == V ? l.Vp - v_begin : vlen);      // the last range also writes P's zero padding columns
         ep.Mp64 = (int)l.Mp64; ep.p_pitch = (int)l.Vp; ep.col_base = (int)v_begin;
@@ -684,11 +691,11 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         const int kb_per = (num_kb + (int)l.KS - 1) / (int)l.KS;
         const int ks_eff = (num_kb + kb_per - 1) / kb_per;
         if (h_is_bf16)
-            ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
+            ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
                                                                                  static_cast<__nv_bfloat16*>(d_h), db_blocks, PT,
                                                                                  (int)V, (int)l.Mp64, d_b);
         else
-            ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, N, (int)M, (int)Dh, ks_eff,
+            ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
                                                                          static_cast<float*>(d_h), db_blocks, PT, (int)V,
                                                                          (int)l.Mp64, d_b);
     }

@@ -56,18 +56,35 @@ __device__ __forceinline__ uint32_t* epoch_word(void* base, int blk) {
     return reinterpret_cast<uint32_t*>(base) + kEpochOffsetWords + blk;
 }
 
-// All threads of block `blk` on every rank meet here.  Thread t < world publishes `target` in rank t's
-// arrival word [blk][rank] (one-way release store: it orders the block's earlier peer stores before it) and
-// polls its own word [blk][t] until rank t has published the same epoch (acquire).
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All threads of block `blk` on every rank meet here.  Thread t < world publishes `target` in rank t's arrival
+// word [blk][rank] with a one-way store and polls its own word [blk][t] (local memory, relaxed loads) until rank t
+// has published the same epoch.
+//   kPublish: the block's earlier peer / multicast stores must be performed before the flag (release store: the
+//             closing barrier).  The opening barrier publishes nothing of its own — what the peers are about to
+//             read was written by earlier kernels of this stream and is already in this GPU's L2 — so a relaxed
+//             store suffices there.
+//   kConsume: the block goes on to read peers' data (opening barrier): one acquire load after the poll.
+template <bool kPublish, bool kConsume>
 __device__ __forceinline__ void rank_barrier(void* const* bufs, int rank, int world, int blk, uint32_t target) {
     __syncthreads();
     const int t = threadIdx.x;
     if (t < world) {
-        st_release_sys(arrival_word(bufs[t], blk, rank), target);
+        uint32_t* theirs = arrival_word(bufs[t], blk, rank);
+        if (kPublish) st_release_sys(theirs, target); else st_relaxed_sys(theirs, target);
         const uint32_t* mine = arrival_word(bufs[rank], blk, t);
         const unsigned long long t0 = now_ns();
-        while ((int32_t)(ld_acquire_sys(mine) - target) < 0)
+        while ((int32_t)(ld_relaxed_sys(mine) - target) < 0)
             if (now_ns() - t0 > kTimeoutNs) __trap();
+        if (kConsume) (void)ld_acquire_sys(mine);
     }
     __syncthreads();
 }
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(kMaxThreads) peer_allreduce_kernel(void* const
     const int world = kWorld > 0 ? kWorld : world_arg;
     const int rank = kEmulate ? (int)blockIdx.y : rank_arg;
     const uint32_t epoch = begin_collective(bufs, rank, blockIdx.x);
-    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 1);
+    rank_barrier<false, true>(bufs, rank, world, blockIdx.x, epoch + 1);
     const Range r = slice_of(nvec, world, rank);
     constexpr int U = kWorld == 2 ? 4 : (kWorld == 8 ? 1 : 2);
     const int kThreads = blockDim.x;
@@ -194,7 +211,7 @@ __global__ void __launch_bounds__(kMaxThreads) peer_allreduce_kernel(void* const
             }
         }
     }
-    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 2);
+    rank_barrier<true, false>(bufs, rank, world, blockIdx.x, epoch + 2);
     end_collective(bufs, rank, blockIdx.x, epoch);
 }
 
@@ -202,7 +219,7 @@ __global__ void __launch_bounds__(kMaxThreads) peer_allreduce_kernel(void* const
 __global__ void __launch_bounds__(kMaxThreads) mc_allreduce_sum_f32_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
                                                                         int world, int64_t off_bytes, int64_t nvec) {
     const uint32_t epoch = begin_collective(bufs, rank, blockIdx.x);
-    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 1);
+    rank_barrier<false, true>(bufs, rank, world, blockIdx.x, epoch + 1);
     const Range r = slice_of(nvec, world, rank);
     constexpr int U = 8;
     const int kThreads = blockDim.x;
@@ -221,14 +238,14 @@ __global__ void __launch_bounds__(kMaxThreads) mc_allreduce_sum_f32_kernel(void*
             if (i < r.hi) mc_st(base_ptr + i * 16, v[u]);
         }
     }
-    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 2);
+    rank_barrier<true, false>(bufs, rank, world, blockIdx.x, epoch + 2);
     end_collective(bufs, rank, blockIdx.x, epoch);
 }
 
 __global__ void __launch_bounds__(kMaxThreads) mc_allreduce_min_i64_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
                                                                         int world, int64_t off_bytes, int64_t n) {
     const uint32_t epoch = begin_collective(bufs, rank, blockIdx.x);
-    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 1);
+    rank_barrier<false, true>(bufs, rank, world, blockIdx.x, epoch + 1);
     const Range r = slice_of(n, world, rank);
     constexpr int U = 8;
     const int kThreads = blockDim.x;
@@ -247,7 +264,7 @@ __global__ void __launch_bounds__(kMaxThreads) mc_allreduce_min_i64_kernel(void*
             if (i < r.hi) mc_st(base_ptr + i * 8, v[u]);
         }
     }
-    rank_barrier(bufs, rank, world, blockIdx.x, epoch + 2);
+    rank_barrier<true, false>(bufs, rank, world, blockIdx.x, epoch + 2);
     end_collective(bufs, rank, blockIdx.x, epoch);
 }
 

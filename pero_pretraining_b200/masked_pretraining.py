@@ -63,11 +63,13 @@ class _FusedHeadCE(torch.autograd.Function):
         h2 = h.detach().reshape(n_frames, h.shape[-1])
         if h2.dtype not in (torch.float32, torch.bfloat16):
             h2 = h2.float()
-        h2 = h2.contiguous()
+        if not h2.is_contiguous():
+            h2 = h2.contiguous()
         lab = labels.detach().reshape(-1)
         if lab.dtype != torch.int64:
             lab = lab.long()
-        lab = lab.contiguous()
+        if not lab.is_contiguous():
+            lab = lab.contiguous()
         saved, loss = [], None
         for rows, m_local, weight in terms:
             if dp_group is not None:
@@ -84,8 +86,7 @@ class _FusedHeadCE(torch.autograd.Function):
                 loss_sum = loss_sum.clone()
                 torch.distributed.all_reduce(loss_sum, group=dp_group)
             # mean over the GLOBAL number of selected frames; an empty selection gives NaN like F.cross_entropy
-            term = loss_sum[0] / m_global if m_global > 0 else loss_sum[0] * float('nan')
-            term = term * weight if weight != 1.0 else term
+            term = loss_sum.view(()) * (weight / m_global if m_global > 0 else float('nan'))
             loss = term if loss is None else loss + term
             saved.append((rows, m_local, weight, m_global, lse, ws))
         ctx.saved = saved
@@ -98,7 +99,9 @@ class _FusedHeadCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         h2, lab, head = ctx.h2, ctx.lab, ctx.head_prep
-        g = g.detach().float().reshape(1).contiguous()
+        g = g.detach().reshape(1)
+        if g.dtype != torch.float32:
+            g = g.float()
         want_dh = ctx.needs_input_grad[0]
         d_h = d_W = d_b = None
         peer = ctx.peer_range if ctx.dp_group is not None else None
@@ -129,8 +132,12 @@ class _FusedHeadCE(torch.autograd.Function):
                 torch.distributed.all_reduce(flat, group=ctx.dp_group)
         d_W, d_b = flat[:head.V * head.Dh].view(head.V, head.Dh), flat[head.V * head.Dh:]
         if d_h is not None:
-            d_h = d_h.reshape(ctx.h_shape).to(ctx.h_dtype)
-        return d_h, d_W.to(ctx.w_dtype), (d_b if ctx.has_bias else None), None, None, None, None, None
+            d_h = d_h.view(ctx.h_shape)
+            if d_h.dtype != ctx.h_dtype:
+                d_h = d_h.to(ctx.h_dtype)
+        if d_W.dtype != ctx.w_dtype:
+            d_W = d_W.to(ctx.w_dtype)
+        return d_h, d_W, (d_b if ctx.has_bias else None), None, None, None, None, None
 
 
 class LinearHead(torch.nn.Module):

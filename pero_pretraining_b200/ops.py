@@ -10,7 +10,14 @@ from . import _lib
 from ._lib import check
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """Raw handle of the current CUDA stream of the current device (the cheap accessor when torch has it:
+    torch.cuda.current_stream() costs several microseconds per call, and every op here needs the handle)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -74,6 +81,28 @@ def vq_assign(x, codebook, n_lines, frames_per_line, channels_first, want_dmin=F
                            codebook.blob.data_ptr(), int(index_offset), _p(idx), _p(dmin), _p(packed), _p(x_rows),
                            ws.data_ptr(), wsb, _stream()), "pero_vq_assign")
     return idx, dmin, x_rows
+
+
+def vq_forward(x, codebook, weight, ema_w, ema_cluster_size, decay, epsilon, update_ema, n_lines, frames_per_line,
+               channels_first=True):
+    """The whole VectorQuantizer.forward in one call of the C ABI (pero_vq_forward): returns (quantized with the
+    layout of x, idx int64 [N]); with update_ema the EMA state, weight and the prepared codebook are updated in place."""
+    L = _lib.lib()
+    N = int(n_lines) * int(frames_per_line)
+    K, D = codebook.K, codebook.D
+    dev = x.device
+    out = torch.empty_like(x)
+    idx = torch.empty(N, dtype=torch.int64, device=dev)
+    if N == 0:
+        return out, idx
+    upd = 1 if update_ema else 0
+    wsb = L.pero_vq_forward_workspace_bytes(N, K, D, upd)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(L.pero_vq_forward(x.data_ptr(), int(n_lines), int(frames_per_line), 1 if channels_first else 0, K, D,
+                            codebook.blob.data_ptr(), codebook.nbytes, weight.data_ptr(), _p(ema_w), _p(ema_cluster_size),
+                            float(decay), float(epsilon), upd, out.data_ptr(), idx.data_ptr(), ws.data_ptr(), wsb, _stream()),
+          "pero_vq_forward")
+    return out, idx
 
 
 def vq_packed_init(N, device, out=None):
