@@ -109,6 +109,15 @@ int pero_vq_ema_apply(const float* sums_counts, int64_t K, int64_t D, double dec
 /* counts[k] = #frames with idx == k as int64 (models/autoencoders.py:165, torch.bincount). */
 int pero_vq_counts(const int64_t* idx, int64_t N, int64_t K, int64_t* counts, pero_stream_t stream);
 
+/* ------------------------------------------------------------------ mini-batch k-means centre update (codebook FIT)
+ * The step of scikit-learn's MiniBatchKMeans (sklearn/cluster/_k_means_minibatch.pyx, update_center_dense — the
+ * fitter behind  scripts/fit_kmeans.py:20-32 ; scikit-learn is an unpinned dependency of the reference, 1.9.0 here)
+ * after the batch has been assigned (pero_vq_assign) and summed per centre (pero_vq_ema_accumulate):
+ *     for centres with n > 0 members:  c <- (c * w + sum) * (1 / (w + n)),  w <- w + n
+ * centers [K, D] and weight_sums [K] are updated in place; `codebook` (or NULL) is the prepared blob to refresh. */
+int pero_kmeans_update(const float* sums_counts, int64_t K, int64_t D, float* centers, float* weight_sums, void* codebook,
+                       size_t codebook_bytes, pero_stream_t stream);
+
 /* ------------------------------------------------------------------ the whole quantizer forward in one call
  * Replaces  models/autoencoders.py:204-241  (VectorQuantizer.forward): pero_vq_assign -> pero_vq_gather_st ->
  * (update_ema != 0: decay > 0 and training) pero_vq_ema_accumulate -> pero_vq_ema_apply, enqueued back to back on
@@ -170,6 +179,17 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
                        const int64_t* labels, const void* head, int64_t V, const float* lse,
                        const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
                        void* workspace, size_t workspace_bytes, pero_stream_t stream);
+/* Evaluation of the head on the masked frames without materialising logits
+ * (replaces  masked_pretraining/tester.py:70-93  Tester._update_errors + the loss of :57-64): one sweep of the logits
+ * GEMM yields the loss terms AND, per masked frame, the number of labels whose logit is strictly larger than the
+ * frame's own label's (its 0-based rank); errors[i] = #frames with rank >= topk_host[i] ("label not among the
+ * top-k predictions"; exact logit ties are broken in favour of the label).
+ *   topk_host  HOST array of num_topk (1..8) values k >= 1, e.g. {1, 3, 10}
+ *   rank  [M] int32 or NULL;  errors [num_topk] int64 (device).  Workspace: pero_masked_ce_workspace_bytes(). */
+int pero_masked_ce_eval(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+                        const int64_t* labels, const void* head, int64_t V, const int32_t* topk_host, int num_topk,
+                        float* loss_sum, float* lse, int32_t* rank, int64_t* errors, void* workspace,
+                        size_t workspace_bytes, pero_stream_t stream);
 /* The same backward restricted to the label columns [v_begin, v_end) (v_begin and v_end multiples of 256, or
  * v_end = V): rows [v_begin, v_end) of d_W and d_b (pointers to the FULL arrays) and the matching columns of the
  * dlogits kept in the workspace.  A data-parallel caller walks the label axis range by range and exchanges each

@@ -208,3 +208,26 @@ def topk_errors(logits, labels, mask, ks=(1, 3, 10)):
         hit = (order[:, :k] == y[:, None]).any(1)
         out[f"errors_{k}"] = int((~hit).sum())
     return out
+
+
+def minibatch_kmeans_step(X, centers, weight_sums):
+    """One step of scikit-learn's MiniBatchKMeans without reassignment (the fitter of scripts/fit_kmeans.py:20-32;
+    scikit-learn is an unpinned dependency of the reference — 1.9.0 in the build container).  Restates
+    sklearn/cluster/_kmeans.py _mini_batch_step + _k_means_minibatch.pyx update_center_dense in fp32:
+        labels = nearest centre (squared Euclidean);  inertia = sum of squared distances BEFORE the update
+        for centres with members: c <- (c * w + sum_{members, in sample order} x) * (1 / (w + n));  w <- w + n
+    Returns (labels int64 [n], inertia float, centers_new [K, D] fp32, weight_sums_new [K] fp32)."""
+    X = np.asarray(X, dtype=np.float32)
+    c = np.asarray(centers, dtype=np.float32).copy()
+    w = np.asarray(weight_sums, dtype=np.float32).copy()
+    d = (X.astype(np.float64) ** 2).sum(1)[:, None] - 2.0 * X.astype(np.float64) @ c.astype(np.float64).T + (c.astype(np.float64) ** 2).sum(1)[None]
+    labels = d.argmin(1)
+    inertia = float(d[np.arange(len(X)), labels].sum())
+    for k in np.unique(labels):
+        members = X[labels == k]
+        acc = c[k] * w[k]
+        for row in members:                       # sample order, fp32 adds: what the Cython loop does
+            acc = acc + row
+        w[k] = w[k] + np.float32(len(members))
+        c[k] = acc * (np.float32(1.0) / w[k])
+    return labels.astype(np.int64), inertia, c, w

@@ -7,11 +7,15 @@ raises unless the shared library is built and a B200 is the current device.
     from pero_pretraining_b200 import VectorQuantizer, VQVAE                     # models/autoencoders.py
     from pero_pretraining_b200 import LinearHead, MaskedCrossEntropyLoss, MaskedTransformerEncoder
     from pero_pretraining_b200 import KMeansLabeller, kmeans_assign              # scripts/produce_kmeans_labels.py
+    from pero_pretraining_b200 import MiniBatchKMeans                            # scripts/fit_kmeans.py (GPU fit)
+    from pero_pretraining_b200 import produce_kmeans_labels, save_labels         # label wire format + production loop
     pero_pretraining_b200.install()   # swap the classes into an importable `pero_pretraining` package
 """
 from ._lib import PeroError, build, lib  # noqa: F401
 from .autoencoders import VQVAE, VectorQuantizer  # noqa: F401
+from .kmeans_fit import MiniBatchKMeans  # noqa: F401
 from .kmeans_labels import KMeansLabeller, kmeans_assign  # noqa: F401
+from .labels_io import LabelWriter, compute_labels, load_labels, produce_kmeans_labels, save_labels  # noqa: F401
 from .masked_pretraining import LinearHead, MaskedCrossEntropyLoss, MaskedTransformerEncoder  # noqa: F401
 from .sharding import ShardedCodebook, merge_packed, shard_bounds  # noqa: F401
 

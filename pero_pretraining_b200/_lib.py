@@ -36,6 +36,7 @@ SIGNATURES = {
     "pero_vq_ema_accumulate": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "pero_vq_ema_apply": (c_int, [c_vp, c_i64, c_i64, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_sz,
                                   c_vp]),
+    "pero_kmeans_update": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pero_vq_forward_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "pero_vq_forward": (c_int, [c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_sz, c_vp, c_vp, c_vp, c_f64, c_f64, c_int,
                                 c_vp, c_vp, c_vp, c_sz, c_vp]),
@@ -51,6 +52,8 @@ SIGNATURES = {
                                    c_sz, c_vp]),
     "pero_masked_ce_bwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32,
                                    c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pero_masked_ce_eval": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp,
+                                    c_vp, c_vp, c_sz, c_vp]),
     "pero_masked_ce_bwd_range": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32,
                                          c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pero_ce_logits_fwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -44,7 +44,8 @@ constexpr int kMaxLseSplits = 64;
 
 struct CeWsLayout {
     int64_t Dhp, Vp, Mp64, Mpad, S, KS;
-    size_t a_off, at_off, lab_off, inv_off, p_off, pt_off, pm_off, ps_off, zlab_off, rowloss_off, ticket_off, planes_off, total;
+    size_t a_off, at_off, lab_off, inv_off, p_off, pt_off, pm_off, ps_off, zlab_off, rowloss_off, ticket_off, zlin_off, pcnt_off,
+        planes_off, total;
 };
 inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     CeWsLayout l;
@@ -74,6 +75,8 @@ inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     l.zlab_off = take((size_t)l.Mpad * 4);
     l.rowloss_off = take((size_t)l.Mpad * 4);
     l.ticket_off = take(256);
+    l.zlin_off = take((size_t)l.Mpad * 4);              // evaluation: label logit known before the sweep
+    l.pcnt_off = take((size_t)2 * S * l.Mpad * 4);      // evaluation: per-split counts of logits above the label's
     l.planes_off = take((size_t)KS * M * Dh * 4);
     l.total = off;
     return l;
@@ -153,7 +156,11 @@ __device__ __forceinline__ int masked_row_of(const int* __restrict__ inv, const 
 
 // ------------------------------------------------------------------------------------------------ epilogues
 // Online log-sum-exp over the label axis; one partial (max, sum) per row, column split and column half.
-struct LseEpi {
+// kRank (evaluation, masked_pretraining/tester.py:70-93): the label's logit is known before the sweep (zl_in) and
+// the epilogue also counts the labels whose logit is strictly larger — the label's 0-based rank, from which the
+// top-k errors follow without the [M, V] logits ever existing.
+template <bool kRank>
+struct LseEpiT {
     static constexpr bool kColVec = true;
     static constexpr int kScratchPerWarp = 0;
     struct Params {
@@ -161,12 +168,16 @@ struct LseEpi {
         const int* lab;       // [Mpad]
         float* pm; float* ps; // [2 * S, Mpad] partial max / sum(exp(z - max))
         float* zlab;          // [Mpad] logit at the label
+        const float* zl_in;   // kRank: [Mpad] label logit computed ahead of the sweep
+        int* pcnt;            // kRank: [2 * S, Mpad] partial counts of logits above zl_in
         int M, Mpad, S;
     };
-    struct State { float m, s, zl; int label; bool has; };
+    struct State { float m, s, zl, zin; int label, cnt; bool has; };
     static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
         st.m = -CUDART_INF_F; st.s = 0.f; st.zl = 0.f; st.has = false;
         st.label = cx.row < ep.M ? __ldg(ep.lab + cx.row) : -1;
+        st.cnt = 0;
+        st.zin = (kRank && cx.row < ep.M) ? __ldg(ep.zl_in + cx.row) : CUDART_INF_F;
     }
     static __device__ __forceinline__ void tile(State& st, const Params&, const TileCtx& cx, uint32_t taddr) {
         const float4* cv = reinterpret_cast<const float4*>(cx.cv);
@@ -193,6 +204,14 @@ struct LseEpi {
                 for (int j = 0; j < 32; ++j) if (rel == (unsigned)j) st.zl = z[j];
                 st.has = true;
             }
+            if constexpr (kRank) {
+                int above = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) above += (z[j] > st.zin) ? 1 : 0;
+                // the label's own column is never counted, however its two evaluations round
+                if (rel < 32u && st.zl > st.zin) above -= 1;
+                st.cnt += above;
+            }
             if (cmax > -CUDART_INF_F) {
                 const float mn = fmaxf(st.m, cmax);
                 const float mn2 = mn * kLog2e;
@@ -214,8 +233,11 @@ struct LseEpi {
         ep.pm[(size_t)slot * ep.Mpad + cx.row] = st.m;
         ep.ps[(size_t)slot * ep.Mpad + cx.row] = st.s;
         if (st.has) ep.zlab[cx.row] = st.zl;
+        if constexpr (kRank) ep.pcnt[(size_t)slot * ep.Mpad + cx.row] = st.cnt;
     }
 };
+using LseEpi = LseEpiT<false>;
+using EvalEpi = LseEpiT<true>;
 
 // dlogits tile = (exp(z - lse) - [col == label]) * scale, written bf16 as P [M, Vp] (16-byte stores) and
 // P^T [V, Mp64]: neighbouring lanes (= neighbouring rows) swap one value per column pair so that every
@@ -358,6 +380,46 @@ ce_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps, c
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += sh[w];
         loss_sum[0] = t;
+    }
+}
+
+// Evaluation: zl[m] = <A[m, :], W[label_m, :]> + bias[label_m] from the same bf16 operands the GEMM reads
+// (fp32 accumulation); one warp per masked row.
+__global__ void __launch_bounds__(256)
+ce_label_logit_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ wb, const float* __restrict__ bias,
+                      const int* __restrict__ lab, int M, int Dhp, float* __restrict__ zl) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const int label = __ldg(lab + m);
+    const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(a + (size_t)m * Dhp);
+    const __nv_bfloat162* w = reinterpret_cast<const __nv_bfloat162*>(wb + (size_t)label * Dhp);
+    float acc = 0.f;
+    for (int i = lane; i < Dhp / 2; i += 32) {
+        const float2 xv = __bfloat1622float2(x[i]), wv = __bfloat1622float2(w[i]);
+        acc = fmaf(xv.x, wv.x, acc);
+        acc = fmaf(xv.y, wv.y, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) zl[m] = acc + __ldg(bias + label);
+}
+
+struct TopKs { int k[8]; int n; };
+// rank[m] = number of labels with a larger logit than the frame's own label (sum of the per-split counts);
+// errors[i] += [rank[m] >= k_i]  (integer atomics: exact, order-free).
+__global__ void __launch_bounds__(256)
+ce_rank_finalize_kernel(const int* __restrict__ pcnt, int M, int Mpad, int slots, TopKs ks, int* __restrict__ rank,
+                        unsigned long long* __restrict__ errors) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = 0;
+    if (m < M) {
+        for (int s = 0; s < slots; ++s) r += __ldg(pcnt + (size_t)s * Mpad + m);
+        if (rank) rank[m] = r;
+    }
+    for (int i = 0; i < ks.n; ++i) {
+        const unsigned ballot = __ballot_sync(0xffffffffu, m < M && r >= ks.k[i]);
+        if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(errors + i, (unsigned long long)__popc(ballot));
     }
 }
 
@@ -599,6 +661,53 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
                                                                 rowloss, reinterpret_cast<unsigned int*>(ws + l.ticket_off),
                                                                 loss_sum);
+    return (int)cudaGetLastError();
+}
+
+int pero_masked_ce_eval(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+                        const int64_t* labels, const void* head, int64_t V, const int32_t* topk_host, int num_topk,
+                        float* loss_sum, float* lse, int32_t* rank, int64_t* errors, void* workspace, size_t workspace_bytes,
+                        pero_stream_t stream) {
+    if (M == 0) return PERO_ERR_BAD_SHAPE;
+    int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (!loss_sum || !lse || !errors || !topk_host) return PERO_ERR_NULL;
+    if (num_topk < 1 || num_topk > 8) return PERO_ERR_BAD_SHAPE;
+    TopKs ks;
+    ks.n = num_topk;
+    for (int i = 0; i < 8; ++i) ks.k[i] = i < num_topk ? topk_host[i] : 0;
+    for (int i = 0; i < num_topk; ++i) if (ks.k[i] < 1) return PERO_ERR_BAD_SHAPE;
+    const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
+    const HeadLayout hl = head_layout(V, Dh);
+    char* ws = static_cast<char*>(workspace);
+    const char* hb = static_cast<const char*>(head);
+    cudaError_t e = cudaMemsetAsync(errors, 0, (size_t)num_topk * 8, stream);
+    if (e != cudaSuccess) return (int)e;
+    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream)
+                   : launch_ce_gather<float>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream);
+    if (rc) return rc;
+    EvalEpi::Params ep;
+    ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
+    ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
+    ep.pm = reinterpret_cast<float*>(ws + l.pm_off);
+    ep.ps = reinterpret_cast<float*>(ws + l.ps_off);
+    ep.zlab = reinterpret_cast<float*>(ws + l.zlab_off);
+    float* zl_in = reinterpret_cast<float*>(ws + l.zlin_off);
+    ep.zl_in = zl_in;
+    ep.pcnt = reinterpret_cast<int*>(ws + l.pcnt_off);
+    ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S;
+    ce_label_logit_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(ws + l.a_off), reinterpret_cast<const __nv_bfloat16*>(hb + hl.w_off), ep.colvec,
+        ep.lab, (int)M, (int)l.Dhp, zl_in);
+    rc = launch_gemm_tn<2, true, EvalEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
+                                          /*split_mode=*/1, (int)l.S, 0, ep, stream, nullptr, kSmemBudgetShared);
+    if (rc) return rc;
+    float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
+    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
+                                                                  rowloss, reinterpret_cast<unsigned int*>(ws + l.ticket_off),
+                                                                  loss_sum);
+    ce_rank_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(ep.pcnt, (int)M, (int)l.Mpad, 2 * (int)l.S, ks, rank,
+                                                                         reinterpret_cast<unsigned long long*>(errors));
     return (int)cudaGetLastError();
 }
 

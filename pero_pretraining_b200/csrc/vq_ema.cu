@@ -277,6 +277,42 @@ ema_apply_rows_kernel(const float* __restrict__ sums, const float* __restrict__ 
     if (cnorm && lane == 0) cnorm[k] = s;
 }
 
+// Mini-batch k-means centre update (scikit-learn MiniBatchKMeans, _k_means_minibatch.pyx update_center_dense, the
+// fitter behind scripts/fit_kmeans.py:20-32): for every centre with members in the batch
+//     c <- (c * w + sum of members) * (1 / (w + n)),   w <- w + n
+// and untouched otherwise.  One warp per centre; also refreshes the bf16 GEMM operand and |c|^2 for the next assign.
+__global__ void __launch_bounds__(256)
+kmeans_update_rows_kernel(const float* __restrict__ sums, const float* __restrict__ counts, int K, int D, int Dp, int Kp,
+                          float* __restrict__ centers, float* __restrict__ weight_sums, __nv_bfloat16* __restrict__ cb,
+                          float* __restrict__ cnorm) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= Kp) return;
+    if (k >= K) { if (cnorm && lane == 0) cnorm[k] = CUDART_INF_F; return; }
+    const float n = counts[k], w = weight_sums[k];
+    const float w_new = __fadd_rn(w, n);
+    const float alpha = __fdiv_rn(1.0f, w_new);
+    __syncwarp();
+    if (lane == 0 && n > 0.f) weight_sums[k] = w_new;
+    float s = 0.f;
+    for (int d = lane; d < Dp; d += 32) {
+        float c = 0.f;
+        if (d < D) {
+            const size_t o = (size_t)k * D + d;
+            c = centers[o];
+            if (n > 0.f) {
+                c = __fmul_rn(__fadd_rn(__fmul_rn(c, w), sums[o]), alpha);
+                centers[o] = c;
+            }
+        }
+        s = fmaf(c, c, s);
+        if (cb) cb[(size_t)k * Dp + d] = __float2bfloat16_rn(c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (cnorm && lane == 0) cnorm[k] = s;
+}
+
 }  // namespace pero
 
 using namespace pero;
@@ -359,6 +395,26 @@ int pero_vq_ema_apply(const float* sums_counts, int64_t K, int64_t D, double dec
     ema_apply_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(sums, counts, cluster_partial, nblocks, (int)K, (int)D,
                                                                          (int)cl.Dp, rows, decay_f, omd_f, eps_f, keps_f,
                                                                          ema_cluster_size, ema_w, weight, cb, cnorm);
+    return (int)cudaGetLastError();
+}
+
+int pero_kmeans_update(const float* sums_counts, int64_t K, int64_t D, float* centers, float* weight_sums, void* codebook,
+                       size_t codebook_bytes, pero_stream_t stream) {
+    if (!sums_counts || !centers || !weight_sums) return PERO_ERR_NULL;
+    if (K <= 0 || D <= 0 || K > (1ll << 24)) return PERO_ERR_BAD_SHAPE;
+    const CodebookLayout cl = codebook_layout(K, D);
+    __nv_bfloat16* cb = nullptr;
+    float* cnorm = nullptr;
+    if (codebook) {
+        if (codebook_bytes < cl.total) return PERO_ERR_WORKSPACE;
+        if (reinterpret_cast<uintptr_t>(codebook) & 255) return PERO_ERR_BAD_ALIGN;
+        cb = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(codebook) + cl.cb_off);
+        cnorm = reinterpret_cast<float*>(static_cast<char*>(codebook) + cl.cnorm_off);
+    }
+    const int rows = (int)(codebook ? cl.Kp : K);
+    kmeans_update_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(sums_counts, sums_counts + (size_t)K * D, (int)K,
+                                                                             (int)D, (int)cl.Dp, rows, centers, weight_sums, cb,
+                                                                             cnorm);
     return (int)cudaGetLastError();
 }
 

@@ -189,6 +189,39 @@ class LinearHead(torch.nn.Module):
                                   self._peer_range if dp_group is not None else None)
 
 
+    def masked_errors(self, hidden, labels, mask, ks=(1, 3, 10)):
+        """Evaluation on the masked frames without materialising logits: what Tester.test_step + _update_errors
+        compute from result['output'] (masked_pretraining/tester.py:57-93).  Returns a dict with the mean masked loss
+        (0-dim tensor), 'length' (number of masked frames) and 'errors_<k>' (int tensors, still on the device: a
+        caller accumulates them over batches and reads them back once)."""
+        dev = hidden.device
+        rows, m = _rows_from_mask(mask, labels, 1, False, dev)
+        out = {'length': m}
+        if m == 0:
+            out['loss'] = torch.full((), float('nan'), device=dev)
+            for k in ks:
+                out[f'errors_{k}'] = torch.zeros((), dtype=torch.int64, device=dev)
+            return out
+        h2 = hidden.detach().reshape(-1, hidden.shape[-1])
+        if h2.dtype not in (torch.float32, torch.bfloat16):
+            h2 = h2.float()
+        lab = labels.detach().reshape(-1).long().contiguous()
+        loss_sum, _, _, errors = ops.masked_ce_eval(h2.contiguous(), rows, lab, self._prepared(), ks)
+        out['loss'] = loss_sum.view(()) / m
+        for i, k in enumerate(ks):
+            out[f'errors_{k}'] = errors[i]
+        return out
+
+
+def update_errors(errors, result):
+    """Accumulate LinearHead.masked_errors results the way Tester._update_errors does (tester.py:70-93):
+    errors['errors_<k>'] += count, errors['length'] += number of masked frames.  Counts stay device tensors."""
+    for key, value in result.items():
+        if key.startswith('errors_') or key == 'length':
+            errors[key] = errors.get(key, 0) + value
+    return errors
+
+
 class MaskedCrossEntropyLoss(torch.nn.Module):
     """masked_pretraining/model.py:72-95: logits-in interface kept for callers that already hold logits."""
 

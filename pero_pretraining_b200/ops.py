@@ -160,6 +160,17 @@ def vq_ema_apply(sums_counts, ema_w, ema_cluster_size, weight, decay, epsilon, c
           "pero_vq_ema_apply")
 
 
+def kmeans_update(sums_counts, centers, weight_sums, codebook=None):
+    """In-place mini-batch k-means centre update (pero_kmeans_update) from the [K*D + K] sums|counts buffer."""
+    K, D = centers.shape
+    for t, n in ((centers, "centers"), (weight_sums, "weight_sums")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError(f"{n} must be a contiguous CUDA float32 tensor")
+    check(_lib.lib().pero_kmeans_update(sums_counts.data_ptr(), K, D, centers.data_ptr(), weight_sums.data_ptr(),
+                                        None if codebook is None else codebook.blob.data_ptr(),
+                                        0 if codebook is None else codebook.nbytes, _stream()), "pero_kmeans_update")
+
+
 def vq_counts(idx, K):
     counts = torch.empty(int(K), dtype=torch.int64, device=idx.device)
     check(_lib.lib().pero_vq_counts(idx.data_ptr(), idx.numel(), int(K), counts.data_ptr(), _stream()), "pero_vq_counts")
@@ -240,6 +251,29 @@ def masked_ce_fwd(h, rows, labels, head, loss_out=None):
                                labels.data_ptr(), head.blob.data_ptr(), head.V, loss_sum.data_ptr(), lse.data_ptr(),
                                ws.data_ptr(), wsb, _stream()), "pero_masked_ce_fwd")
     return loss_sum, lse, ws
+
+
+def masked_ce_eval(h, rows, labels, head, ks=(1, 3, 10), want_rank=False):
+    """Loss terms and top-k errors of the head on the masked frames, logits never materialised
+    (pero_masked_ce_eval).  Returns (loss_sum [1], lse [M], rank int32 [M] or None, errors int64 [len(ks)])."""
+    import ctypes
+    L = _lib.lib()
+    h = _check_h(h)
+    N, Dh = h.shape
+    M = rows.numel()
+    dev = h.device
+    loss_sum = torch.empty(1, dtype=torch.float32, device=dev)
+    lse = torch.empty(M, dtype=torch.float32, device=dev)
+    rank = torch.empty(M, dtype=torch.int32, device=dev) if want_rank else None
+    errors = torch.empty(len(ks), dtype=torch.int64, device=dev)
+    wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
+    ws = _ws(wsb, dev)
+    karr = (ctypes.c_int32 * len(ks))(*[int(k) for k in ks])
+    check(L.pero_masked_ce_eval(h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M,
+                                labels.data_ptr(), head.blob.data_ptr(), head.V, ctypes.addressof(karr), len(ks),
+                                loss_sum.data_ptr(), lse.data_ptr(), _p(rank), errors.data_ptr(), ws.data_ptr(), wsb,
+                                _stream()), "pero_masked_ce_eval")
+    return loss_sum, lse, rank, errors
 
 
 def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False,

@@ -1,3 +1,4 @@
+"""One masked-CE forward + backward at the bench shape, for an ncu capture of its GEMMs."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 from pero_pretraining_b200 import ops
@@ -7,7 +8,8 @@ h = torch.randn(N, Dh, device=dev); W = torch.randn(V, Dh, device=dev) * 0.04; b
 labels = torch.randint(0, V, (N,), device=dev)
 rows = torch.from_numpy(np.flatnonzero(np.random.default_rng(0).random(N) < 0.15).astype(np.int32)).to(dev)
 head = ops.PreparedHead(V, Dh, dev).prepare(W, b)
-for rep in range(2):
+for _ in range(2):
     loss_sum, lse, ws = ops.masked_ce_fwd(h, rows, labels, head)
-    ops.masked_ce_bwd(h, rows, labels, head, lse, None, 1.0 / rows.numel(), ws=ws)
-torch.cuda.synchronize(); print("done")
+    ops.masked_ce_bwd(h, rows, labels, head, lse, None, 1.0 / rows.numel(), ws=ws, ws_from_fwd=True)
+torch.cuda.synchronize()
+print("done")

@@ -178,7 +178,32 @@ def gen_masked_ce(name, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
 
 
+def gen_kmeans_minibatch(name, seed):
+    """Third-party arithmetic of the codebook fit (scripts/fit_kmeans.py:20-32): scikit-learn's own
+    MiniBatchKMeans.partial_fit, from given centres, on three given batches, reassignment off
+    (reassignment_ratio=0 — the random part is not parity material).  Well separated blobs: no near-tie labels."""
+    import sklearn
+    from sklearn.cluster import MiniBatchKMeans
+    rng = np.random.RandomState(seed)
+    K, D, nb = 24, 20, 160
+    true = rng.randn(K, D).astype(np.float32) * 4.0
+    init = (true + 0.3 * rng.randn(K, D)).astype(np.float32)
+    batches = [(true[rng.randint(0, K, nb)] + 0.4 * rng.randn(nb, D)).astype(np.float32) for _ in range(3)]
+    km = MiniBatchKMeans(n_clusters=K, init=init, n_init=1, batch_size=nb, reassignment_ratio=0.0, compute_labels=True,
+                         random_state=0)
+    rec = {"init": init, "sklearn_version": np.array(sklearn.__version__)}
+    for i, b in enumerate(batches):
+        km.partial_fit(b)
+        rec[f"batch{i}"] = b
+        rec[f"centers{i}"] = km.cluster_centers_.astype(np.float32).copy()
+        rec[f"counts{i}"] = km._counts.astype(np.float32).copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "kmeans_minibatch":       # only the scikit-learn fixture
+        gen_kmeans_minibatch("kmeans_minibatch", seed=61)
+        sys.exit(0)
     gen_vq("vq_cold_3steps", K=64, D=16, nl=4, H=1, W=12, decay=0.99, steps=3, seed=11)
     gen_vq("vq_warm_3steps", K=48, D=32, nl=3, H=2, W=20, decay=0.99, steps=3, seed=12, spread=True)
     gen_vq("vq_nodecay", K=32, D=8, nl=2, H=1, W=16, decay=0.0, steps=1, seed=13)
@@ -187,6 +212,7 @@ if __name__ == "__main__":
     gen_vqvae("vqvae_forward", seed=31)
     gen_kmeans("kmeans_assign", seed=41)
     gen_masked_ce("masked_ce", seed=51)
+    gen_kmeans_minibatch("kmeans_minibatch", seed=61)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):

@@ -143,3 +143,21 @@ def test_packed_distance_index_order():
     assert [(p[0] + 0.0, p[1]) for p in pairs if p[0] != 0.0] == [(p[0] + 0.0, p[1]) for p in ref if p[0] != 0.0]
     assert torch.equal(unpack_index_reference(packed), idx)
     assert int(packed.max()) < 0x7FFFFFFFFFFFFFFF           # INT64_MAX is reserved for "empty"
+
+
+def test_label_wire_format_roundtrip(tmp_path):
+    """"<line_id> l0 l1 ...\\n" with frames filtered by image_mask == 1 (produce_kmeans_labels.py:83-85,
+    scripts/common.py:51-54) — host-side code, no device involved."""
+    import os
+    import numpy as np
+    from pero_pretraining_b200.labels_io import LabelWriter, format_label_line, load_labels, save_labels
+    assert format_label_line("a.jpg", [3, 0, 12]) == "a.jpg 3 0 12\n"
+    assert format_label_line("empty.jpg", []) == "empty.jpg \n"           # what the reference's f-string writes
+    p = os.path.join(tmp_path, "l.txt")
+    with LabelWriter(p) as w:
+        w.write_batch(["x", "y"], np.array([[1, 1, 0, 0], [1, 0, 1, 1]]), np.array([[5, 6, 7, 8], [9, 10, 11, 12]]))
+    assert open(p).read() == "x 5 6\ny 9 11 12\n"
+    assert load_labels(p) == {"x": [5, 6], "y": [9, 11, 12]}
+    q = os.path.join(tmp_path, "m.txt")
+    save_labels({"x": [5, 6], "y": [9, 11, 12]}, q)
+    assert open(q).read() == open(p).read()

@@ -190,3 +190,52 @@ def test_backward_by_label_ranges_equals_full_backward(cuda_dev):
     assert torch.equal(d_h2, d_h)
     with pytest.raises(Exception):                    # ranges must start on a multiple of 256
         ops.masked_ce_bwd(h, rows, labels, head, lse2, None, 1.0 / M, ws=ws2, want_dh=False, v_range=(100, 512))
+
+
+@pytest.mark.parametrize("Nl,T_,Dh,V,p", [(8, 128, 512, 4096, 0.15), (5, 37, 96, 1000, 0.5), (3, 50, 512, 257, 0.3)])
+def test_masked_errors_match_tester(cuda_dev, Nl, T_, Dh, V, p):
+    """Fused evaluation (label rank counted in the logits GEMM's epilogue) vs Tester._update_errors restated in the
+    oracle on full logits (masked_pretraining/tester.py:70-93).  A frame may differ only where the label's logit is
+    within bf16 noise of the k-th largest logit."""
+    from pero_pretraining_b200 import LinearHead, ops
+    from pero_pretraining_b200.masked_pretraining import update_errors
+    rng = np.random.default_rng(V)
+    g = torch.Generator(device="cpu").manual_seed(V + 3)
+    h = torch.randn(Nl, T_, Dh, generator=g)
+    W = torch.randn(V, Dh, generator=g) * (2.0 / np.sqrt(Dh))
+    b = torch.randn(V, generator=g) * 0.1
+    labels = torch.from_numpy(rng.integers(0, V, size=(Nl, T_))).long()
+    # make the task non-trivial: every frame is pulled towards its label's weight row by a random amount, so the
+    # label's rank ranges from 0 to the hundreds
+    pull = torch.from_numpy(rng.random((Nl, T_))).float()[..., None] * 4.5
+    h = h + pull * torch.nn.functional.normalize(W[labels], dim=-1)
+    mask = (rng.random((Nl, T_)) < p).astype(int)
+    head = LinearHead(Dh, V).to(cuda_dev)
+    with torch.no_grad():
+        head.linear.weight.copy_(W); head.linear.bias.copy_(b)
+    res = head.masked_errors(h.to(cuda_dev), labels.to(cuda_dev), mask, ks=(1, 3, 10))
+    logits = O.linear_head(h.bfloat16().float(), W.bfloat16().float(), b)         # same operand rounding as the device
+    ref = O.topk_errors(logits.numpy(), labels.numpy(), mask, ks=(1, 3, 10))
+    assert res["length"] == ref["length"]
+    # frames whose label logit is within 1e-3 (relative to the logit scale) of the k-th largest may flip
+    z = logits.numpy()[mask == 1]; y = labels.numpy()[mask == 1]
+    zl = z[np.arange(len(y)), y]
+    srt = -np.sort(-z, axis=1)
+    for k in (1, 3, 10):
+        near = int((np.abs(zl - srt[:, k - 1]) < 1e-3 * np.abs(srt[:, 0])).sum()) + int((np.abs(zl - srt[:, k]) < 1e-3 * np.abs(srt[:, 0])).sum())
+        assert abs(int(res[f"errors_{k}"]) - ref[f"errors_{k}"]) <= near, (k, int(res[f"errors_{k}"]), ref[f"errors_{k}"], near)
+    ref_loss = O.masked_ce(logits, labels, T(mask))
+    assert abs(res["loss"].item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item())
+    assert 0 < ref["errors_10"] <= ref["errors_3"] <= ref["errors_1"] < ref["length"]
+    if V >= 1000:
+        assert ref["errors_10"] < ref["errors_1"]                                   # the case separates the three counts
+    # rank itself: exact where the logit gaps are clear
+    rows = torch.from_numpy(np.flatnonzero(mask.reshape(-1) == 1).astype(np.int32)).to(cuda_dev)
+    _, _, rank, _ = ops.masked_ce_eval(h.to(cuda_dev).reshape(-1, Dh), rows, labels.to(cuda_dev).reshape(-1), head._prepared(),
+                                       ks=(1,), want_rank=True)
+    ref_rank = (z > zl[:, None]).sum(1)
+    margin = np.abs(z - zl[:, None]); margin[np.arange(len(y)), y] = np.inf
+    clear = margin.min(1) > 1e-3 * np.abs(srt[:, 0])
+    assert np.array_equal(rank.cpu().numpy()[clear], ref_rank[clear])
+    acc = update_errors(update_errors({}, res), res)
+    assert acc["length"] == 2 * res["length"] and int(acc["errors_3"]) == 2 * int(res["errors_3"])

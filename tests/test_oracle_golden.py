@@ -139,3 +139,14 @@ def test_create_mask_and_topk():
     logits = rng.standard_normal((3, 20, 10))
     errs = O.topk_errors(logits, labels, mask, ks=(1, 3, 10))
     assert errs["errors_10"] == 0 and errs["errors_1"] >= errs["errors_3"] and errs["length"] == mask.sum()
+
+
+def test_minibatch_kmeans_step_matches_sklearn_golden():
+    """oracle.minibatch_kmeans_step restates scikit-learn's MiniBatchKMeans step (the fitter behind
+    scripts/fit_kmeans.py:20-32); pinned on centres/counts that scikit-learn itself produced (make_golden.py)."""
+    g = load_golden("kmeans_minibatch")
+    c, w = g["init"], np.zeros(g["init"].shape[0], dtype=np.float32)
+    for i in range(3):
+        _, _, c, w = O.minibatch_kmeans_step(g[f"batch{i}"], c, w)
+        np.testing.assert_allclose(w, g[f"counts{i}"], rtol=0, atol=0)
+        np.testing.assert_allclose(c, g[f"centers{i}"], rtol=2e-6, atol=2e-6)
