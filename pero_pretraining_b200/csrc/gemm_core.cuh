@@ -130,10 +130,14 @@ __device__ __forceinline__ void stamp_cta(const GemmShape& sh, bool on, int slot
 // 128 registers per thread (384 threads -> 48 K of the SM's 64 K registers): the remaining 16 K let one CTA of a
 // bandwidth-bound kernel or of the peer-exchange kernel run on the same SM, so those kernels overlap a resident
 // GEMM instead of waiting for it (or, worse, keeping the next GEMM's CTA off the SM).
-template <int kCtaGroup, bool kAResident, class Epi>
+// kMnMajor: both operands are read "transposed" — A is stored [k][rows_a] and B [k][rows_b] (the contraction index
+// runs over the rows of the stored matrices), i.e. C = A^T B without a transposed copy of either in HBM.  TMA
+// fetches boxes of {64 contiguous MN-elements, 64 k-rows}; the UMMA descriptors are MN-major.
+template <int kCtaGroup, bool kAResident, class Epi, bool kMnMajor = false>
 __global__ void __maxnreg__(128)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmShape sh, const typename Epi::Params ep) {
+    static_assert(!(kMnMajor && kAResident), "MN-major operands are streamed through the ring");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     stamp_cta(sh, threadIdx.x == 0, 0);
@@ -213,7 +217,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sbase = ring + stage * kStageBytes;
-                    if constexpr (kCtaGroup == 1) {
+                    if constexpr (kMnMajor) {
+                        // boxes of {64 MN-elements, 64 k-rows} = 8 KiB each: 2 for A, kBRows / 64 for B
+                        constexpr uint32_t kBox = 64u * kBlockK * 2u;
+                        if constexpr (kCtaGroup == 1) {
+                            mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+#pragma unroll
+                            for (int j = 0; j < kBlockM / 64; ++j)
+                                tma_load_2d(sbase + kBBlockBytes + j * kBox, &tmap_a, full_bar(stage), row0 + 64 * j, kb * kBlockK);
+#pragma unroll
+                            for (int j = 0; j < (int)kBRows / 64; ++j)
+                                tma_load_2d(sbase + j * kBox, &tmap_b, full_bar(stage), brow0 + 64 * j, kb * kBlockK);
+                        } else {
+                            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);
+                            else mbar_arrive_remote(full_bar(stage), 0);
+#pragma unroll
+                            for (int j = 0; j < kBlockM / 64; ++j)
+                                tma_load_2d_pair(sbase + kBBlockBytes + j * kBox, &tmap_a, full_bar(stage), row0 + 64 * j, kb * kBlockK);
+#pragma unroll
+                            for (int j = 0; j < (int)kBRows / 64; ++j)
+                                tma_load_2d_pair(sbase + j * kBox, &tmap_b, full_bar(stage), brow0 + 64 * j, kb * kBlockK);
+                        }
+                    } else if constexpr (kCtaGroup == 1) {
                         mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
                         if constexpr (!kAResident) tma_load_2d(sbase + kBBlockBytes, &tmap_a, full_bar(stage), kb * kBlockK, row0);
                         tma_load_2d(sbase, &tmap_b, full_bar(stage), kb * kBlockK, brow0);
@@ -242,7 +267,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // barrier probe of the NEXT stage is issued before the MMAs of the current one, so its latency
         // hides behind the issue instead of adding ~100 cycles per k-block.
         if (leader && u0 < u1) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, kBlockN);
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, kBlockN, kMnMajor);
             int stage = 0; uint32_t phase = 0;
             int prev_rb = -1, rbi = -1, it = 0;
             uint32_t ready = 0;
@@ -268,13 +293,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     ready = (kb + 1 < kb1 || ui.u + 1 < u1) ? mbar_test_wait(full_bar(nstage), nphase) : 0u;
                     const uint32_t sbase = ring + stage * kStageBytes;
                     const uint32_t a_addr = kAResident ? (a_res + kb * kABlockBytes) : (sbase + kBBlockBytes);
-                    const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(sbase);
+                    constexpr uint32_t kMnBox = 64u * kBlockK * 2u;
+                    const uint64_t adesc = kMnMajor ? make_mnmajor_sw128_desc(a_addr, kMnBox) : make_kmajor_sw128_desc(a_addr);
+                    const uint64_t bdesc = kMnMajor ? make_mnmajor_sw128_desc(sbase, kMnBox) : make_kmajor_sw128_desc(sbase);
+                    // address-field step per UMMA_K (16 contraction elements): K-major +32 B inside the 128-byte
+                    // swizzle row (+2 in the >>4 field); MN-major +16 k-rows = two 1024-byte atoms (+128)
+                    constexpr uint64_t kDescStep = kMnMajor ? (2048u >> 4) : 2u;
                     if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                            // +32 B per UMMA_K step inside the 128-byte swizzle row: +2 in the >>4 address field
-                            umma_bf16<kCtaGroup>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16<kCtaGroup>(tmem_d, adesc + kDescStep * k, bdesc + kDescStep * k, idesc,
+                                                 (kb > kb0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit<kCtaGroup>(empty_bar(stage));
                         if (kAResident && last_of_rb) umma_commit<kCtaGroup>(aempty_bar(kb));

@@ -99,10 +99,13 @@ inline int pick_stages(int cta_group, bool a_resident, int num_kb, int scratch_p
 
 // A: [rows_a, kd] bf16, pitch_a elements; B: [rows_b, kd] bf16, pitch_b elements; kd % 64 == 0.
 // `workers` = number of CTAs (kCtaGroup == 1) or CTA pairs (== 2); 0 = fill the machine.
-template <int kCtaGroup, bool kAResident, class Epi>
+// kMnMajor: A is stored [k_rows, rows_a] and B [k_rows, rows_b] (row pitches pitch_a / pitch_b), C = A^T B; kd is the
+// contraction length rounded up to 64 and k_rows (<= kd, 0 = kd) the rows that exist (TMA zero-fills the rest).
+template <int kCtaGroup, bool kAResident, class Epi, bool kMnMajor = false>
 int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int rows_b, int pitch_b, int kd,
                    int num_ks, int split_mode, int fixed_s, int workers, const typename Epi::Params& ep,
-                   cudaStream_t stream, unsigned long long* timeline = nullptr, size_t smem_budget = kSmemBudget) {
+                   cudaStream_t stream, unsigned long long* timeline = nullptr, size_t smem_budget = kSmemBudget,
+                   int k_rows = 0) {
     if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
     GemmShape sh;
     sh.timeline = timeline ? timeline : g_debug_timeline;
@@ -120,9 +123,17 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     if (sh.num_stages < 2) return PERO_ERR_BAD_SHAPE;
 
     CUtensorMap ta, tb;
-    int rc = make_tmap_bf16(&ta, a, (uint64_t)rows_a, (uint64_t)kd, (uint64_t)pitch_a, kBlockM);
-    if (rc) return rc;
-    rc = make_tmap_bf16(&tb, b, (uint64_t)rows_b, (uint64_t)kd, (uint64_t)pitch_b, kBlockN / kCtaGroup);
+    int rc;
+    if constexpr (kMnMajor) {
+        const uint64_t kr = (uint64_t)(k_rows > 0 ? k_rows : kd);
+        rc = make_tmap_bf16(&ta, a, kr, (uint64_t)rows_a, (uint64_t)pitch_a, 64);
+        if (rc) return rc;
+        rc = make_tmap_bf16(&tb, b, kr, (uint64_t)rows_b, (uint64_t)pitch_b, 64);
+    } else {
+        rc = make_tmap_bf16(&ta, a, (uint64_t)rows_a, (uint64_t)kd, (uint64_t)pitch_a, kBlockM);
+        if (rc) return rc;
+        rc = make_tmap_bf16(&tb, b, (uint64_t)rows_b, (uint64_t)kd, (uint64_t)pitch_b, kBlockN / kCtaGroup);
+    }
     if (rc) return rc;
 
     const long long units = (long long)sh.num_rb * sh.num_ct * sh.num_ks;
@@ -138,7 +149,7 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
 
     size_t smem = gemm_smem_bytes(kCtaGroup, kAResident, sh.num_kb, sh.num_stages, Epi::kScratchPerWarp);
     if (smem < kSmemFloor) smem = kSmemFloor;
-    auto kern = gemm_tn_kernel<kCtaGroup, kAResident, Epi>;
+    auto kern = gemm_tn_kernel<kCtaGroup, kAResident, Epi, kMnMajor>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);

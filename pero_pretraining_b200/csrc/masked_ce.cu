@@ -44,8 +44,7 @@ constexpr int kMaxLseSplits = 64;
 
 struct CeWsLayout {
     int64_t Dhp, Vp, Mp64, Mpad, S, KS;
-    size_t a_off, at_off, lab_off, inv_off, p_off, pt_off, pm_off, ps_off, zlab_off, rowloss_off, ticket_off, zlin_off, pcnt_off,
-        planes_off, total;
+    size_t a_off, lab_off, inv_off, p_off, pm_off, ps_off, zlab_off, rowloss_off, ticket_off, zlin_off, pcnt_off, planes_off, total;
 };
 inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     CeWsLayout l;
@@ -65,11 +64,9 @@ inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
     l.a_off = take((size_t)M * l.Dhp * 2);
-    l.at_off = take((size_t)Dh * l.Mp64 * 2);
     l.lab_off = take((size_t)l.Mpad * 4);
     l.inv_off = take((size_t)N * 4);
     l.p_off = take((size_t)M * l.Vp * 2);
-    l.pt_off = take((size_t)V * l.Mp64 * 2);
     l.pm_off = take((size_t)2 * S * l.Mpad * 4);
     l.ps_off = take((size_t)2 * S * l.Mpad * 4);
     l.zlab_off = take((size_t)l.Mpad * 4);
@@ -109,41 +106,31 @@ head_prepare_kernel(const float* __restrict__ W, const float* __restrict__ bias,
     }
 }
 
-// Gather the masked frames into the GEMM operand A [M, Dhp] bf16 and A^T [Dh, Mp64] (operand of d_W), their
-// labels, and the inverse frame -> masked-row map inv [N] at the selected frames (see masked_row_of: no
-// initialisation pass over the other frames is needed).  Tiles of 32 masked rows x 32 channels.  Also clears the
-// ticket word that ce_finalize_kernel's last block uses.
+// Gather the masked frames into the GEMM operand A [M, Dhp] bf16 (rows = masked frames: the K-major operand of the
+// logits GEMMs and, read through MN-major descriptors, the operand of d_W = dlogits^T A), their labels, and the
+// inverse frame -> masked-row map inv [N] at the selected frames (see masked_row_of).  One warp per masked row.
+// Also clears the ticket word that ce_finalize_kernel's last block uses.
 template <typename T>
 __global__ void __launch_bounds__(256)
 ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const long long* __restrict__ labels, int M,
-                 int Dh, int Dhp, int Mp64, int Mpad, __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ at,
-                 int* __restrict__ lab, int* __restrict__ inv, unsigned int* __restrict__ ticket) {
-    __shared__ float tile[32][33];
-    const int m0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty + i * 8, d = d0 + tx;
-        float x = 0.f;
-        if (m < M && d < Dh) x = (float)h[(size_t)__ldg(rows + m) * Dh + d];
-        tile[ty + i * 8][tx] = x;
-        if (m < M && d < Dhp) a[(size_t)m * Dhp + d] = __float2bfloat16_rn(x);
+                 int Dh, int Dhp, int Mpad, __nv_bfloat16* __restrict__ a, int* __restrict__ lab, int* __restrict__ inv,
+                 unsigned int* __restrict__ ticket) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;
+    if (m >= Mpad) return;
+    if (m >= M) { if (lane == 0) lab[m] = -1; return; }
+    const int r = __ldg(rows + m);
+    const T* src = h + (size_t)r * Dh;
+    __nv_bfloat16* dst = a + (size_t)m * Dhp;
+    for (int d = 2 * lane; d < Dhp; d += 64) {          // Dhp is a multiple of 64: every lane writes whole pairs
+        const float x0 = d < Dh ? (float)src[d] : 0.f, x1 = d + 1 < Dh ? (float)src[d + 1] : 0.f;
+        *reinterpret_cast<__nv_bfloat162*>(dst + d) = __floats2bfloat162_rn(x0, x1);
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int d = d0 + ty + i * 8, m = m0 + tx;
-        if (d < Dh && m < Mp64) at[(size_t)d * Mp64 + m] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+    if (lane == 0) {
+        lab[m] = (int)__ldg(labels + r);
+        inv[r] = m;
     }
-    if (blockIdx.y == 0 && threadIdx.x < 32) {
-        const int m = m0 + (int)threadIdx.x;
-        if (m < Mpad) lab[m] = m < M ? (int)__ldg(labels + __ldg(rows + m)) : -1;
-    }
-    if (blockIdx.y == 0 && threadIdx.x < 32) {
-        const int m = m0 + (int)threadIdx.x;
-        if (m < M) inv[__ldg(rows + m)] = m;
-    }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;
 }
 
 // The frame -> masked-row map `inv` is written only at the selected frames; every other entry keeps whatever the
@@ -239,27 +226,25 @@ struct LseEpiT {
 using LseEpi = LseEpiT<false>;
 using EvalEpi = LseEpiT<true>;
 
-// dlogits tile = (exp(z - lse) - [col == label]) * scale, written bf16 as P [M, Vp] (16-byte stores) and
-// P^T [V, Mp64]: neighbouring lanes (= neighbouring rows) swap one value per column pair so that every
-// lane writes a packed bf16 pair, i.e. 4-byte stores that coalesce to 64 B per column.
+// dlogits tile = (exp(z - lse) - [col == label]) * scale, written bf16 as P [M, Vp] only: 32 x 32 chunks are staged
+// row-major in a warp-private shared-memory tile so that one store instruction writes 8 rows x 64 B.  Both gradient
+// GEMMs read this one copy: d_h = P W consumes it K-major, d_W = P^T A through MN-major descriptors.
 struct DlogitsEpi {
     static constexpr bool kColVec = true;
     static constexpr int kScratchPerWarp = 32 * 80;      // 32 rows x 32 bf16, 80-byte pitch
     struct Params {
-        const float* colvec;  // bias [Vt], -inf beyond V
+        const float* colvec;  // bias [Vt], -inf beyond V (already offset to the range's first column)
         const int* lab; const float* lse; const float* grad_scale;
         float inv_count;
-        __nv_bfloat16* p; __nv_bfloat16* pt;   // already offset to the first label column / row of the range
-        int M, V, Vp, Mp64;    // V, Vp: number of label columns of the range (exact / rounded up to 64)
+        __nv_bfloat16* p;      // already offset to the first label column of the range
+        int M, Vp;             // Vp: label columns of the range to write (multiple of 32)
         int p_pitch;           // row pitch of P (the full padded label count)
         int col_base;          // global index of the range's first label column
-        int debug_skip;        // measurement only: 1 = skip P stores, 2 = skip P^T stores
     };
     struct State { float lse2, scale; int label; };
     static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
         const bool ok = cx.row < ep.M;
         st.label = ok ? __ldg(ep.lab + cx.row) : -1;
-        // rows in [M, Mp64) are the zero padding of P^T: lse = +inf makes exp2(z - lse) exactly 0, no select needed
         st.lse2 = ok ? __ldg(ep.lse + cx.row) * kLog2e : CUDART_INF_F;
         st.scale = ok ? ep.inv_count * (ep.grad_scale ? __ldg(ep.grad_scale) : 1.0f) : 0.f;
     }
@@ -267,10 +252,9 @@ struct DlogitsEpi {
         const float4* cv = reinterpret_cast<const float4*>(cx.cv);
         const int lane = threadIdx.x & 31;
         const int row_base = cx.row - lane;
-        const bool rows_in_pt = row_base < ep.Mp64;            // warp-uniform: Mp64 is a multiple of 64
         for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
             const int col = cx.col0 + c * 32;
-            const bool col_ok = col < ep.Vp;                    // warp-uniform: Vp is a multiple of 64
+            if (col >= ep.Vp) return;                           // warp-uniform: Vp is a multiple of 32
             float g[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -288,8 +272,6 @@ struct DlogitsEpi {
             __nv_bfloat162 o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = __floats2bfloat162_rn(g[2 * j], g[2 * j + 1]);
-
-            // ---- P rows: chunk staged row-major (80-byte pitch); one store instruction = 8 rows x 64 B
             uint4* srow = reinterpret_cast<uint4*>(cx.scratch + lane * 80);
 #pragma unroll
             for (int i = 0; i < 4; ++i) srow[i] = *reinterpret_cast<uint4*>(&o[4 * i]);
@@ -298,25 +280,8 @@ struct DlogitsEpi {
             for (int k = 0; k < 4; ++k) {
                 const int rr = 8 * k + (lane >> 2), piece = lane & 3;
                 const uint4 v = *reinterpret_cast<const uint4*>(cx.scratch + rr * 80 + piece * 16);
-                if (col_ok && row_base + rr < ep.M && !(ep.debug_skip & 1))
+                if (row_base + rr < ep.M)
                     *reinterpret_cast<uint4*>(ep.p + (size_t)(row_base + rr) * ep.p_pitch + col + piece * 8) = v;
-            }
-            __syncwarp();
-            // ---- P^T columns: chunk staged column-major in the same buffer; one store instruction = 4 columns
-            //      x 64 B (the warp's 32 rows are contiguous in P^T)
-            __nv_bfloat16* tcol = reinterpret_cast<__nv_bfloat16*>(cx.scratch) + lane;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                tcol[(2 * j) * 40] = o[j].x;                     // 40 bf16 = 80-byte pitch
-                tcol[(2 * j + 1) * 40] = o[j].y;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int cc = 4 * k + (lane >> 3), piece = lane & 7;     // column cc, rows 4*piece .. 4*piece+3
-                const uint2 v = *reinterpret_cast<const uint2*>(cx.scratch + cc * 80 + piece * 8);
-                if (rows_in_pt && col + cc < ep.V && !(ep.debug_skip & 2))
-                    *reinterpret_cast<uint2*>(ep.pt + (size_t)(col + cc) * ep.Mp64 + row_base + piece * 4) = v;
             }
             __syncwarp();
         });
@@ -425,47 +390,47 @@ ce_rank_finalize_kernel(const int* __restrict__ pcnt, int M, int Mpad, int slots
 
 __global__ void ce_sum_kernel(const float* __restrict__ v, int M, float* __restrict__ out);
 
-// d_b[v] = sum_m P^T[v, m]: one warp per label, fixed lane-strided order.
-__global__ void __launch_bounds__(256)
-ce_db_kernel(const __nv_bfloat16* __restrict__ pt, int V, int M, int Mp64, float* __restrict__ db) {
-    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (v >= V) return;
-    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(pt + (size_t)v * Mp64);
-    float s = 0.f;
-    for (int i = lane; i < Mp64 / 2; i += 32) {      // columns >= M are zero by construction
-        const float2 f = __bfloat1622float2(row[i]);
-        s += f.x + f.y;
+// d_b[v] = sum_m P[m, v]: a block owns 64 consecutive labels; thread (c = tid % 32, g = tid / 32) adds the rows
+// g, g + 8, ... of its column pair (128-byte coalesced row reads), then the 8 partial sums are added in a fixed order.
+__device__ __forceinline__ void ce_db_block(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, int v0, int V,
+                                            float* __restrict__ db) {
+    __shared__ float2 part[8][33];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int v = v0 + 2 * c;
+    float2 s = make_float2(0.f, 0.f);
+    if (v < V) {                                           // P is padded to a multiple of 64 columns: the pair exists
+        for (int m = g; m < M; m += 8) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + (size_t)m * p_pitch + v));
+            s.x += f.x; s.y += f.y;
+        }
     }
+    part[g][c] = s;
+    __syncthreads();
+    if (g == 0 && v < V) {
+        float2 t = part[0][c];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) db[v] = s;
-    (void)M;
+        for (int k = 1; k < 8; ++k) { t.x += part[k][c].x; t.y += part[k][c].y; }
+        db[v] = t.x;
+        if (v + 1 < V) db[v + 1] = t.y;
+    }
+    __syncthreads();
 }
 
-// d_h[n, :] = sum over split planes of row inv[n] (zero when the frame is not masked).
+__global__ void __launch_bounds__(256)
+ce_db_kernel(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, int v_begin, int v_end, float* __restrict__ db) {
+    ce_db_block(p, M, p_pitch, v_begin + (int)blockIdx.x * 64, v_end, db);
+}
+
 // Blocks [0, gridDim.x - db_blocks) scatter; the last db_blocks blocks (if any) compute d_b exactly as
-// ce_db_kernel does (one warp per label), so that d_b rides in the same launch instead of sitting between the two
-// gradient GEMMs.
+// ce_db_kernel does, so that d_b rides in the same launch instead of sitting between the two gradient GEMMs.
 template <typename T>
 __global__ void __launch_bounds__(256)
 ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ inv, const int* __restrict__ rows, long long N,
-                     int M, int Dh, int KS, T* __restrict__ dh, int db_blocks, const __nv_bfloat16* __restrict__ pt, int V, int Mp64,
-                     float* __restrict__ db) {
+                     int M, int Dh, int KS, T* __restrict__ dh, int db_blocks, const __nv_bfloat16* __restrict__ p, int V,
+                     int p_pitch, float* __restrict__ db) {
     const int scatter_blocks = (int)gridDim.x - db_blocks;
     if ((int)blockIdx.x >= scatter_blocks) {
-        const int lane = threadIdx.x & 31;
-        for (int v = ((int)blockIdx.x - scatter_blocks) * 8 + (threadIdx.x >> 5); v < V; v += db_blocks * 8) {
-            const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(pt + (size_t)v * Mp64);
-            float s = 0.f;
-            for (int i = lane; i < Mp64 / 2; i += 32) {
-                const float2 f = __bfloat1622float2(row[i]);
-                s += f.x + f.y;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) db[v] = s;
-        }
+        ce_db_block(p, M, p_pitch, ((int)blockIdx.x - scatter_blocks) * 64, V, db);
         return;
     }
     // one thread per 4 consecutive channels (Dh % 4 == 0): 16-byte plane reads, 16/8-byte stores
@@ -579,12 +544,11 @@ struct MaskPred {
 template <typename T>
 int launch_ce_gather(const void* h, const int32_t* rows, const int64_t* labels, long long N, int M, int Dh, const CeWsLayout& l,
                      char* ws, cudaStream_t stream) {
-    dim3 grid((unsigned)((l.Mpad + 31) / 32), (unsigned)(l.Dhp / 32));
-    ce_gather_kernel<T><<<grid, 256, 0, stream>>>(
-        static_cast<const T*>(h), rows, reinterpret_cast<const long long*>(labels), M, Dh, (int)l.Dhp, (int)l.Mp64, (int)l.Mpad,
-        reinterpret_cast<__nv_bfloat16*>(ws + l.a_off), reinterpret_cast<__nv_bfloat16*>(ws + l.at_off),
-        reinterpret_cast<int*>(ws + l.lab_off), reinterpret_cast<int*>(ws + l.inv_off),
-        reinterpret_cast<unsigned int*>(ws + l.ticket_off));
+    (void)N;
+    ce_gather_kernel<T><<<(unsigned)((l.Mpad + 7) / 8), 256, 0, stream>>>(
+        static_cast<const T*>(h), rows, reinterpret_cast<const long long*>(labels), M, Dh, (int)l.Dhp, (int)l.Mpad,
+        reinterpret_cast<__nv_bfloat16*>(ws + l.a_off), reinterpret_cast<int*>(ws + l.lab_off),
+        reinterpret_cast<int*>(ws + l.inv_off), reinterpret_cast<unsigned int*>(ws + l.ticket_off));
     return (int)cudaGetLastError();
 }
 
@@ -738,7 +702,6 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int* inv = reinterpret_cast<int*>(ws + l.inv_off);
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + l.p_off);
-    __nv_bfloat16* PT = reinterpret_cast<__nv_bfloat16*>(ws + l.pt_off);
     static int store_pairs = -1;     // PERO_CE_STORE_PAIRS=0: gradient GEMMs on single CTAs (tuning knob)
     if (store_pairs < 0) { const char* e = getenv("PERO_CE_STORE_PAIRS"); store_pairs = e ? atoi(e) : 1; }
     const bool db_in_scatter = !dh_only && d_h != nullptr;
@@ -749,34 +712,30 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
             if (rc) return rc;
         }
         const int64_t vlen = v_end - v_begin;
-        __nv_bfloat16* PTr = PT + (size_t)v_begin * l.Mp64;
-
         DlogitsEpi::Params ep;
         ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off) + v_begin;
         ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
         ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
-        static int dlogits_skip = -1;    // PERO_DLOGITS_SKIP: measurement knob, read once
-        if (dlogits_skip < 0) { const char* e = getenv("PERO_DLOGITS_SKIP"); dlogits_skip = e ? atoi(e) : 0; }
-        ep.debug_skip = dlogits_skip;
-        ep.p = P + v_begin; ep.pt = PTr; ep.M = (int)M; ep.V = (int)vlen;
+        ep.p = P + v_begin; ep.M = (int)M;
         ep.Vp = (int)(v_end == V ? l.Vp - v_begin : vlen);      // the last range also writes P's zero padding columns
-        ep.Mp64 = (int)l.Mp64; ep.p_pitch = (int)l.Vp; ep.col_base = (int)v_begin;
+        ep.p_pitch = (int)l.Vp; ep.col_base = (int)v_begin;
         rc = launch_gemm_tn<2, true, DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off + (size_t)v_begin * l.Dhp * 2,
                                                  (int)vlen, (int)l.Dhp, (int)l.Dhp, 1, 0, 1, 0, ep, st, nullptr, kSmemBudgetShared);
         if (rc) return rc;
 
-        // d_W [v_begin:v_end, Dh] = P^T [v_begin:v_end, Mp64] @ A^T [Dh, Mp64]^T
+        // d_W [v_begin:v_end, Dh] = P[:, v_begin:v_end]^T @ A: both operands are read as stored (rows = masked
+        // frames = the contraction index) through MN-major descriptors; no transposed copy of either exists.
         StoreEpi::Params sw;
         sw.out = d_W + (size_t)v_begin * Dh; sw.ld = Dh; sw.split_stride = 0; sw.rows = (int)vlen; sw.cols = (int)Dh;
         rc = store_pairs
-                 ? launch_gemm_tn<2, false, StoreEpi>(PTr, (int)vlen, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1,
-                                                      0, 1, 0, sw, st, nullptr, kSmemBudgetShared)
-                 : launch_gemm_tn<1, false, StoreEpi>(PTr, (int)vlen, (int)l.Mp64, ws + l.at_off, (int)Dh, (int)l.Mp64, (int)l.Mp64, 1,
-                                                      0, 1, 0, sw, st, nullptr, kSmemBudgetShared);
+                 ? launch_gemm_tn<2, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Vp, ws + l.a_off, (int)Dh, (int)l.Dhp,
+                                                            (int)l.Mp64, 1, 0, 1, 0, sw, st, nullptr, kSmemBudgetShared, (int)M)
+                 : launch_gemm_tn<1, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Vp, ws + l.a_off, (int)Dh, (int)l.Dhp,
+                                                            (int)l.Mp64, 1, 0, 1, 0, sw, st, nullptr, kSmemBudgetShared, (int)M);
         if (rc) return rc;
         // d_b: alone when this call stops after d_W | d_b (they are exchanged next), otherwise inside the scatter launch
         if (!db_in_scatter)
-            ce_db_kernel<<<(unsigned)((vlen + 7) / 8), 256, 0, st>>>(PTr, (int)vlen, (int)M, (int)l.Mp64, d_b + v_begin);
+            ce_db_kernel<<<(unsigned)((vlen + 63) / 64), 256, 0, st>>>(P, (int)M, (int)l.Vp, (int)v_begin, (int)v_end, d_b);
     }
 
     if (d_h) {
@@ -793,7 +752,7 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         const long long total = N * (Dh / 4);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        const int db_blocks = db_in_scatter ? (int)((V + 7) / 8) : 0;
+        const int db_blocks = db_in_scatter ? (int)((V + 63) / 64) : 0;
         blocks += db_blocks;
         // the number of planes actually produced is recomputed exactly as launch_gemm_tn does
         const int num_kb = (int)(l.Vp / 64);
@@ -801,12 +760,12 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         const int ks_eff = (num_kb + kb_per - 1) / kb_per;
         if (h_is_bf16)
             ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
-                                                                                 static_cast<__nv_bfloat16*>(d_h), db_blocks, PT,
-                                                                                 (int)V, (int)l.Mp64, d_b);
+                                                                                 static_cast<__nv_bfloat16*>(d_h), db_blocks, P,
+                                                                                 (int)V, (int)l.Vp, d_b);
         else
             ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
-                                                                         static_cast<float*>(d_h), db_blocks, PT, (int)V,
-                                                                         (int)l.Mp64, d_b);
+                                                                         static_cast<float*>(d_h), db_blocks, P, (int)V,
+                                                                         (int)l.Vp, d_b);
     }
     return (int)cudaGetLastError();
 }

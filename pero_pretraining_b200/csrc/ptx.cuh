@@ -191,10 +191,25 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= 2ull << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D fp32 (bit 4), A/B bf16 (bits 7, 10), both K-major,
-// N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// MN-major operand tile (the contraction index runs over ROWS of the source matrix, the M/N index is contiguous),
+// 128-byte swizzle: what TMA boxes {64 MN-elements, 64 k-rows} with CU_TENSOR_MAP_SWIZZLE_128B deposit — one box
+// = 64 k-rows of 128 B = eight 1024-byte swizzle atoms (8 k-rows each) stacked along k.  Canonical layout in
+// 16-byte units ((8, n), (8, k)) : ((1, LBO), (8, SBO)): SBO = 1024 B between 8-row k-groups, LBO = distance
+// between the boxes that hold successive groups of 64 MN-elements.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(1024u >> 4) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32 (bit 4), A/B bf16 (bits 7, 10), A/B major (bits 15, 16: 0 = K-major,
+// 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, bool mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) | ((n >> 3) << 17) |
+           ((m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- misc

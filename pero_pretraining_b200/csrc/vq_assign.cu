@@ -264,6 +264,14 @@ int pero_debug_gemm_tn(const void* a_bf16, int64_t rows_a, const void* b_bf16, i
         if (res) return launch_gemm_tn<1, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
         return launch_gemm_tn<1, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
     }
+    if (variant & 32) {          // MN-major operands: a is [kd, rows_a], b is [kd, rows_b]; out = a^T b
+        const int kp = (k + 63) / 64 * 64;
+        if (variant & 1)
+            return launch_gemm_tn<2, false, StoreEpi, true>(a_bf16, ra, ra, b_bf16, rb, rb, kp, num_splits, 0, 1, 0, ep, stream,
+                                                            nullptr, kSmemBudget, k);
+        return launch_gemm_tn<1, false, StoreEpi, true>(a_bf16, ra, ra, b_bf16, rb, rb, kp, num_splits, 0, 1, 0, ep, stream, nullptr,
+                                                        kSmemBudget, k);
+    }
     switch (variant & 3) {
         case 0: return launch_gemm_tn<1, false, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, num_splits, 0, 1, 0, ep, stream);
         case 1: return launch_gemm_tn<2, false, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, num_splits, 0, 1, 0, ep, stream);

@@ -37,6 +37,24 @@ def test_gemm_core_matches_matmul(cuda_dev, variant, shape):
     assert (got.double() - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("pairs", [0, 1])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (304, 520, 200), (1000, 512, 1245), (8192, 512, 150)])
+def test_gemm_core_mn_major_operands(cuda_dev, pairs, shape):
+    """C = A^T B with A stored [k, rows_a] and B [k, rows_b] (MN-major UMMA descriptors fed by {64 x 64} TMA boxes):
+    how d_W = dlogits^T h is computed without a transposed copy of either operand."""
+    ops = _ops()
+    ra, rb, kd = shape
+    g = torch.Generator(device="cpu").manual_seed(ra + rb + kd)
+    a = torch.randn(kd, ra, generator=g).to(cuda_dev).bfloat16()
+    b = torch.randn(kd, rb, generator=g).to(cuda_dev).bfloat16()
+    out = torch.zeros(1, ra, rb, dtype=torch.float32, device=cuda_dev)
+    from pero_pretraining_b200 import _lib
+    _lib.check(_lib.lib().pero_debug_gemm_tn(a.data_ptr(), ra, b.data_ptr(), rb, kd, 32 + pairs, 1, out.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "pero_debug_gemm_tn")
+    ref = a.double().t() @ b.double()
+    assert (out[0].double() - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_gemm_core_streamed_long_k_and_splits(cuda_dev, variant):
     ops = _ops()
