@@ -253,12 +253,17 @@ class DeviceStep:
         ops, c = self.ops, CFG
         main = torch.cuda.current_stream()
         s_ema, s_ce = self.s_ema, self.s_ce
-        s_ce.wait_stream(main)
-        with torch.cuda.stream(s_ce):
-            self.head.prepare(self.W, self.b)        # head weights change every optimizer step in training
+        s_ema.wait_stream(main)
         idx, _, x_rows = ops.vq_assign(self.x, self.cb, c["lines"], c["frames"], True, want_rows=True)
+        with torch.cuda.stream(s_ema):
+            # Launched AFTER the distance GEMM and on the low-priority stream: the GEMM's CTAs are placed first and
+            # this bandwidth-bound kernel fills in beside them (it does not depend on the assignment).
+            self.head.prepare(self.W, self.b)        # head weights change every optimizer step in training
+            prepared = torch.cuda.Event()
+            prepared.record(s_ema)
         s_ema.wait_stream(main)
         s_ce.wait_stream(main)
+        s_ce.wait_event(prepared)
         # --- chain A (main stream)
         q = ops.vq_gather_st(x_rows, idx, self.weight, c["lines"], c["frames"], True)
         gathered = torch.cuda.Event()

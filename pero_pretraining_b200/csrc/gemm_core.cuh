@@ -56,6 +56,9 @@ struct GemmShape {
     int split_mode;    // 0: balanced contiguous unit ranges; 1: worker = rb * fixed_s + s
     int fixed_s;
     int num_stages;    // ring depth chosen by the host from the shared-memory budget
+    int pdl;           // programmatic dependent launch: bit 0 = release the next kernel of the stream at once (it does
+                       // not read this kernel's output), bit 1 = before exiting, wait for the previous kernel (this
+                       // kernel was released early by it and must not be seen to finish first)
     unsigned long long* timeline;   // debug: per-unit clock64 stamps of worker 0 ([unit][8]); NULL in production
 };
 
@@ -138,6 +141,7 @@ __global__ void __maxnreg__(128)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmShape sh, const typename Epi::Params ep) {
     static_assert(!(kMnMajor && kAResident), "MN-major operands are streamed through the ring");
+    if (sh.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     stamp_cta(sh, threadIdx.x == 0, 0);
@@ -360,6 +364,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_before();
     if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 10) tmem_dealloc<kCtaGroup>(tmem_base, 512);
+    if (sh.pdl & 2) asm volatile("griddepcontrol.wait;" ::: "memory");
     stamp_cta(sh, threadIdx.x == 0, 3);
 }
 

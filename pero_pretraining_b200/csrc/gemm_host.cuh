@@ -105,7 +105,7 @@ template <int kCtaGroup, bool kAResident, class Epi, bool kMnMajor = false>
 int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int rows_b, int pitch_b, int kd,
                    int num_ks, int split_mode, int fixed_s, int workers, const typename Epi::Params& ep,
                    cudaStream_t stream, unsigned long long* timeline = nullptr, size_t smem_budget = kSmemBudget,
-                   int k_rows = 0) {
+                   int k_rows = 0, int pdl = 0) {
     if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
     GemmShape sh;
     sh.timeline = timeline ? timeline : g_debug_timeline;
@@ -118,6 +118,7 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     sh.kb_per_split = (sh.num_kb + sh.num_ks - 1) / sh.num_ks;
     sh.num_ks = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;   // no empty splits
     sh.split_mode = split_mode; sh.fixed_s = fixed_s < 1 ? 1 : fixed_s;
+    sh.pdl = pdl;
     if (kAResident && (sh.num_ks != 1 || sh.num_kb > kMaxAKb)) return PERO_ERR_BAD_SHAPE;
     sh.num_stages = pick_stages(kCtaGroup, kAResident, sh.num_kb, Epi::kScratchPerWarp, smem_budget);
     if (sh.num_stages < 2) return PERO_ERR_BAD_SHAPE;
@@ -161,10 +162,15 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCtaGroup; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (pdl & 2) {      // may start while the previous kernel of the stream is still running (see GemmShape::pdl)
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, sh, ep);
     return e == cudaSuccess ? PERO_OK : (int)e;
 }

@@ -43,13 +43,17 @@ inline HeadLayout head_layout(int64_t V, int64_t Dh) {
 constexpr int kMaxLseSplits = 64;
 
 struct CeWsLayout {
-    int64_t Dhp, Vp, Mp64, Mpad, S, KS;
+    int64_t Dhp, Vp, Pp, Mp64, Mpad, S, KS;
     size_t a_off, lab_off, inv_off, p_off, pm_off, ps_off, zlab_off, rowloss_off, ticket_off, zlin_off, pcnt_off, planes_off, total;
 };
 inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     CeWsLayout l;
     // The logits GEMMs (forward LSE, backward dlogits) run on CTA pairs: 256-row blocks, 74 workers.
     l.Dhp = round_up(Dh, 64); l.Vp = round_up(V, 64); l.Mp64 = round_up(M, 64); l.Mpad = round_up(M, 256);
+    // Row pitch of the dlogits matrix P: a pitch that is a multiple of 4 KiB would put the same 128-byte column
+    // stripe of every row into the same few L2 sets (column sums and 8-rows-per-instruction stores walk exactly
+    // that pattern); 64 extra elements stagger the rows.
+    l.Pp = ((l.Vp * 2) % 4096 == 0) ? l.Vp + 64 : l.Vp;
     const int64_t num_rb_pair = l.Mpad / 256, num_rb = (M + 127) / 128, num_ct = (V + 255) / 256, num_ct_dh = (Dh + 255) / 256;
     int64_t S = 74 / num_rb_pair;
     if (S < 1) S = 1;
@@ -66,7 +70,7 @@ inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     l.a_off = take((size_t)M * l.Dhp * 2);
     l.lab_off = take((size_t)l.Mpad * 4);
     l.inv_off = take((size_t)N * 4);
-    l.p_off = take((size_t)M * l.Vp * 2);
+    l.p_off = take((size_t)M * l.Pp * 2);
     l.pm_off = take((size_t)2 * S * l.Mpad * 4);
     l.ps_off = take((size_t)2 * S * l.Mpad * 4);
     l.zlab_off = take((size_t)l.Mpad * 4);
@@ -390,54 +394,62 @@ ce_rank_finalize_kernel(const int* __restrict__ pcnt, int M, int Mpad, int slots
 
 __global__ void ce_sum_kernel(const float* __restrict__ v, int M, float* __restrict__ out);
 
-// d_b[v] = sum_m P[m, v]: a block owns 64 consecutive labels; thread (c = tid % 32, g = tid / 32) adds the rows
-// g, g + 8, ... of its column pair (128-byte coalesced row reads), then the 8 partial sums are added in a fixed order.
+// d_b[v] = sum_m P[m, v]: a block owns 64 consecutive labels; thread (c = tid % 8, g = tid / 8) adds rows
+// g, g + 32, ... of its 8 columns (16-byte loads, four in flight), then the 32 partial sums are added in a fixed
+// order through shared memory.
 __device__ __forceinline__ void ce_db_block(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, int v0, int V,
                                             float* __restrict__ db) {
-    __shared__ float2 part[8][33];
-    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int v = v0 + 2 * c;
-    float2 s = make_float2(0.f, 0.f);
-    if (v < V) {                                           // P is padded to a multiple of 64 columns: the pair exists
-        for (int m = g; m < M; m += 8) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + (size_t)m * p_pitch + v));
-            s.x += f.x; s.y += f.y;
+    __shared__ float part[32][8][9];
+    const int c = threadIdx.x & 7, g = threadIdx.x >> 3;
+    const int v = v0 + 8 * c;                              // P is padded to a multiple of 64 columns: the 8 exist
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (v < V) {
+        const __nv_bfloat16* col = p + v;
+#pragma unroll 4
+        for (int m = g; m < M; m += 32) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(col + (size_t)m * p_pitch));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+            }
         }
     }
-    part[g][c] = s;
-    __syncthreads();
-    if (g == 0 && v < V) {
-        float2 t = part[0][c];
 #pragma unroll
-        for (int k = 1; k < 8; ++k) { t.x += part[k][c].x; t.y += part[k][c].y; }
-        db[v] = t.x;
-        if (v + 1 < V) db[v + 1] = t.y;
+    for (int j = 0; j < 8; ++j) part[g][c][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int cc = threadIdx.x >> 3, jj = threadIdx.x & 7, vv = v0 + threadIdx.x;
+        float t = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) t += part[k][cc][jj];
+        if (vv < V) db[vv] = t;
     }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(256)
 ce_db_kernel(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, int v_begin, int v_end, float* __restrict__ db) {
+    // the d_W GEMM that follows in the stream does not read d_b: it may start at once (no-op unless that launch
+    // carries the programmatic-serialization attribute)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     ce_db_block(p, M, p_pitch, v_begin + (int)blockIdx.x * 64, v_end, db);
 }
 
-// Blocks [0, gridDim.x - db_blocks) scatter; the last db_blocks blocks (if any) compute d_b exactly as
-// ce_db_kernel does, so that d_b rides in the same launch instead of sitting between the two gradient GEMMs.
 template <typename T>
 __global__ void __launch_bounds__(256)
 ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ inv, const int* __restrict__ rows, long long N,
-                     int M, int Dh, int KS, T* __restrict__ dh, int db_blocks, const __nv_bfloat16* __restrict__ p, int V,
-                     int p_pitch, float* __restrict__ db) {
-    const int scatter_blocks = (int)gridDim.x - db_blocks;
-    if ((int)blockIdx.x >= scatter_blocks) {
-        ce_db_block(p, M, p_pitch, ((int)blockIdx.x - scatter_blocks) * 64, V, db);
-        return;
-    }
+                     int M, int Dh, int KS, T* __restrict__ dh) {
+    const int scatter_blocks = (int)gridDim.x;
+    const int sblock = (int)blockIdx.x;
     // one thread per 4 consecutive channels (Dh % 4 == 0): 16-byte plane reads, 16/8-byte stores
     const int g4 = Dh >> 2;
     const long long total = N * g4;
     const long long stride = (long long)scatter_blocks * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    for (long long i = (long long)sblock * blockDim.x + threadIdx.x; i < total; i += stride) {
         const long long n = i / g4;
         const int g = (int)(i - n * g4);
         const int m = masked_row_of(inv, rows, n, M);
@@ -704,7 +716,14 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + l.p_off);
     static int store_pairs = -1;     // PERO_CE_STORE_PAIRS=0: gradient GEMMs on single CTAs (tuning knob)
     if (store_pairs < 0) { const char* e = getenv("PERO_CE_STORE_PAIRS"); store_pairs = e ? atoi(e) : 1; }
-    const bool db_in_scatter = !dh_only && d_h != nullptr;
+    // When one call produces both gradients, the d_W and d_h GEMMs each get half of the SM pairs and run side by
+    // side: d_h does not read d_W, so the d_W kernel releases it at once (programmatic dependent launch) and the
+    // d_h kernel, before it exits, waits for d_W so that stream order still implies "both are done".  Each CTA then
+    // walks two tiles, and the store of one overlaps the loads of the next.
+    static int pdl_on = -1;          // PERO_CE_PDL=0: the two gradient GEMMs run one after the other
+    if (pdl_on < 0) { const char* e = getenv("PERO_CE_PDL"); pdl_on = e ? atoi(e) : 1; }
+    const bool side_by_side = pdl_on && store_pairs && !dh_only && d_h != nullptr && full_range;
+    const int half_workers = device_sm_count() / 4;
     if (!dh_only) {
         if (h && v_begin == 0) {
             rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, N, (int)M, (int)Dh, l, ws, st)
@@ -718,24 +737,27 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
         ep.p = P + v_begin; ep.M = (int)M;
         ep.Vp = (int)(v_end == V ? l.Vp - v_begin : vlen);      // the last range also writes P's zero padding columns
-        ep.p_pitch = (int)l.Vp; ep.col_base = (int)v_begin;
+        ep.p_pitch = (int)l.Pp; ep.col_base = (int)v_begin;
         rc = launch_gemm_tn<2, true, DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off + (size_t)v_begin * l.Dhp * 2,
                                                  (int)vlen, (int)l.Dhp, (int)l.Dhp, 1, 0, 1, 0, ep, st, nullptr, kSmemBudgetShared);
         if (rc) return rc;
+
+        // d_b right behind the kernel that wrote P (the columns are still in L2).  In the side-by-side schedule it
+        // releases the d_W GEMM at once, which in turn releases the d_h GEMM; each waits for its predecessor
+        // before it exits, so stream order still means "all three are done".
+        ce_db_kernel<<<(unsigned)((vlen + 63) / 64), 256, 0, st>>>(P, (int)M, (int)l.Pp, (int)v_begin, (int)v_end, d_b);
 
         // d_W [v_begin:v_end, Dh] = P[:, v_begin:v_end]^T @ A: both operands are read as stored (rows = masked
         // frames = the contraction index) through MN-major descriptors; no transposed copy of either exists.
         StoreEpi::Params sw;
         sw.out = d_W + (size_t)v_begin * Dh; sw.ld = Dh; sw.split_stride = 0; sw.rows = (int)vlen; sw.cols = (int)Dh;
         rc = store_pairs
-                 ? launch_gemm_tn<2, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Vp, ws + l.a_off, (int)Dh, (int)l.Dhp,
-                                                            (int)l.Mp64, 1, 0, 1, 0, sw, st, nullptr, kSmemBudgetShared, (int)M)
-                 : launch_gemm_tn<1, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Vp, ws + l.a_off, (int)Dh, (int)l.Dhp,
+                 ? launch_gemm_tn<2, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp,
+                                                            (int)l.Mp64, 1, 0, 1, side_by_side ? half_workers : 0, sw, st, nullptr,
+                                                            kSmemBudgetShared, (int)M, side_by_side ? 3 : 0)
+                 : launch_gemm_tn<1, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp,
                                                             (int)l.Mp64, 1, 0, 1, 0, sw, st, nullptr, kSmemBudgetShared, (int)M);
         if (rc) return rc;
-        // d_b: alone when this call stops after d_W | d_b (they are exchanged next), otherwise inside the scatter launch
-        if (!db_in_scatter)
-            ce_db_kernel<<<(unsigned)((vlen + 63) / 64), 256, 0, st>>>(P, (int)M, (int)l.Vp, (int)v_begin, (int)v_end, d_b);
     }
 
     if (d_h) {
@@ -744,28 +766,25 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         StoreEpi::Params sh;
         sh.out = planes; sh.ld = Dh; sh.split_stride = (long long)M * Dh; sh.rows = (int)M; sh.cols = (int)Dh;
         rc = store_pairs
-                 ? launch_gemm_tn<2, false, StoreEpi>(P, (int)M, (int)l.Vp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
-                                                      1, 0, sh, st, nullptr, kSmemBudgetShared)
-                 : launch_gemm_tn<1, false, StoreEpi>(P, (int)M, (int)l.Vp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
+                 ? launch_gemm_tn<2, false, StoreEpi>(P, (int)M, (int)l.Pp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
+                                                      1, side_by_side ? half_workers : 0, sh, st, nullptr, kSmemBudgetShared, 0,
+                                                      side_by_side ? 2 : 0)
+                 : launch_gemm_tn<1, false, StoreEpi>(P, (int)M, (int)l.Pp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
                                                       1, 0, sh, st, nullptr, kSmemBudgetShared);
         if (rc) return rc;
         const long long total = N * (Dh / 4);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        const int db_blocks = db_in_scatter ? (int)((V + 63) / 64) : 0;
-        blocks += db_blocks;
         // the number of planes actually produced is recomputed exactly as launch_gemm_tn does
         const int num_kb = (int)(l.Vp / 64);
         const int kb_per = (num_kb + (int)l.KS - 1) / (int)l.KS;
         const int ks_eff = (num_kb + kb_per - 1) / kb_per;
         if (h_is_bf16)
             ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
-                                                                                 static_cast<__nv_bfloat16*>(d_h), db_blocks, P,
-                                                                                 (int)V, (int)l.Vp, d_b);
+                                                                                 static_cast<__nv_bfloat16*>(d_h));
         else
             ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
-                                                                         static_cast<float*>(d_h), db_blocks, P, (int)V,
-                                                                         (int)l.Vp, d_b);
+                                                                         static_cast<float*>(d_h));
     }
     return (int)cudaGetLastError();
 }
