@@ -41,10 +41,12 @@ inline HeadLayout head_layout(int64_t V, int64_t Dh) {
 }
 
 constexpr int kMaxLseSplits = 64;
+constexpr int kDbRows = 8;          // masked frames per partial row of the d_b column sums
 
 struct CeWsLayout {
     int64_t Dhp, Vp, Pp, Mp64, Mpad, S, KS;
-    size_t a_off, lab_off, inv_off, p_off, pm_off, ps_off, zlab_off, rowloss_off, ticket_off, zlin_off, pcnt_off, planes_off, total;
+    size_t a_off, lab_off, inv_off, p_off, pm_off, ps_off, zlab_off, rowloss_off, ticket_off, zlin_off, pcnt_off, dbpart_off,
+        planes_off, total;
 };
 inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     CeWsLayout l;
@@ -78,6 +80,7 @@ inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     l.ticket_off = take(256);
     l.zlin_off = take((size_t)l.Mpad * 4);              // evaluation: label logit known before the sweep
     l.pcnt_off = take((size_t)2 * S * l.Mpad * 4);      // evaluation: per-split counts of logits above the label's
+    l.dbpart_off = take((size_t)((M + kDbRows - 1) / kDbRows) * l.Vp * 4);   // d_b partial column sums, one row per 8 masked frames
     l.planes_off = take((size_t)KS * M * Dh * 4);
     l.total = off;
     return l;
@@ -394,57 +397,80 @@ ce_rank_finalize_kernel(const int* __restrict__ pcnt, int M, int Mpad, int slots
 
 __global__ void ce_sum_kernel(const float* __restrict__ v, int M, float* __restrict__ out);
 
-// d_b[v] = sum_m P[m, v]: a block owns 64 consecutive labels; thread (c = tid % 8, g = tid / 8) adds rows
-// g, g + 32, ... of its 8 columns (16-byte loads, four in flight), then the 32 partial sums are added in a fixed
-// order through shared memory.
-__device__ __forceinline__ void ce_db_block(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, int v0, int V,
-                                            float* __restrict__ db) {
-    __shared__ float part[32][8][9];
-    const int c = threadIdx.x & 7, g = threadIdx.x >> 3;
-    const int v = v0 + 8 * c;                              // P is padded to a multiple of 64 columns: the 8 exist
-    float acc[8];
+// d_b[v] = sum_m P[m, v] in two passes that both stream contiguous memory:
+//   ce_db_partial_kernel   block r adds the kDbRows consecutive rows r*8 .. r*8+7 of P (whole rows: 16-byte loads,
+//                          every warp instruction reads 512 contiguous bytes) into part[r, :]
+//   ce_db_reduce_block     d_b[v] = sum_r part[r, v] in a fixed order, 32 labels per block
+// Fixed orders: bit-identical from run to run.
+__global__ void __launch_bounds__(256)
+ce_db_partial_kernel(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, int v_begin, int v_len8, int vp,
+                     float* __restrict__ part, int wait_for_previous) {
+    const int m0 = blockIdx.x * kDbRows;
+    float* dst = part + (size_t)blockIdx.x * vp + v_begin;
+    for (int c = threadIdx.x; c < v_len8; c += blockDim.x) {        // 8 columns per thread
+        float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (v < V) {
-        const __nv_bfloat16* col = p + v;
-#pragma unroll 4
-        for (int m = g; m < M; m += 32) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(col + (size_t)m * p_pitch));
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(h2[j]);
-                acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+        for (int r = 0; r < kDbRows; ++r) {
+            if (m0 + r < M) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p + (size_t)(m0 + r) * p_pitch + v_begin) + c);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h2[j]);
+                    acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+                }
             }
         }
+        float4* o = reinterpret_cast<float4*>(dst + 8 * c);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) part[g][c][j] = acc[j];
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        const int cc = threadIdx.x >> 3, jj = threadIdx.x & 7, vv = v0 + threadIdx.x;
-        float t = 0.f;
+    // side-by-side schedule: this kernel was released early by the d_h GEMM in front of it and must not be seen to
+    // finish before that one (see pero_masked_ce_bwd_range)
+    if (wait_for_previous) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// One block finishes 32 labels: thread (c = tid % 32, g = tid / 32) adds the partial rows g, g + 8, ... of label
+// v0 + c (all loads independent: one round trip), then the 8 group sums are added in ascending g.
+__device__ __forceinline__ void ce_db_reduce_block(const float* __restrict__ part, int nparts, int vp, int v0, int v_end,
+                                                   float* __restrict__ db) {
+    __shared__ float grp[8][33];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int v = v0 + c;
+    float t = 0.f;
+    if (v < v_end) {
 #pragma unroll 8
-        for (int k = 0; k < 32; ++k) t += part[k][cc][jj];
-        if (vv < V) db[vv] = t;
+        for (int r = g; r < nparts; r += 8) t += __ldg(part + (size_t)r * vp + v);
     }
+    grp[g][c] = t;
     __syncthreads();
+    if (g == 0 && v < v_end) {
+        float sum = grp[0][c];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) sum += grp[k][c];
+        db[v] = sum;
+    }
 }
 
 __global__ void __launch_bounds__(256)
-ce_db_kernel(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, int v_begin, int v_end, float* __restrict__ db) {
-    // the d_W GEMM that follows in the stream does not read d_b: it may start at once (no-op unless that launch
-    // carries the programmatic-serialization attribute)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    ce_db_block(p, M, p_pitch, v_begin + (int)blockIdx.x * 64, v_end, db);
+ce_db_reduce_kernel(const float* __restrict__ part, int nparts, int vp, int v_begin, int v_end, float* __restrict__ db) {
+    ce_db_reduce_block(part, nparts, vp, v_begin + (int)blockIdx.x * 32, v_end, db);
 }
 
+// The first db_blocks blocks (if any) finish d_b from its partial sums (ce_db_reduce_block), the others scatter.
 template <typename T>
 __global__ void __launch_bounds__(256)
 ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ inv, const int* __restrict__ rows, long long N,
-                     int M, int Dh, int KS, T* __restrict__ dh) {
-    const int scatter_blocks = (int)gridDim.x;
-    const int sblock = (int)blockIdx.x;
+                     int M, int Dh, int KS, T* __restrict__ dh, int db_blocks, const float* __restrict__ dbpart, int nparts,
+                     int vp, int V, float* __restrict__ db) {
+    if ((int)blockIdx.x < db_blocks) {
+        ce_db_reduce_block(dbpart, nparts, vp, (int)blockIdx.x * 32, V, db);
+        return;
+    }
+    const int scatter_blocks = (int)gridDim.x - db_blocks;
+    const int sblock = (int)blockIdx.x - db_blocks;
     // one thread per 4 consecutive channels (Dh % 4 == 0): 16-byte plane reads, 16/8-byte stores
     const int g4 = Dh >> 2;
     const long long total = N * g4;
@@ -714,12 +740,15 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int* inv = reinterpret_cast<int*>(ws + l.inv_off);
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + l.p_off);
+    float* dbpart = reinterpret_cast<float*>(ws + l.dbpart_off);
+    const int db_nparts = (int)((M + kDbRows - 1) / kDbRows);
     static int store_pairs = -1;     // PERO_CE_STORE_PAIRS=0: gradient GEMMs on single CTAs (tuning knob)
     if (store_pairs < 0) { const char* e = getenv("PERO_CE_STORE_PAIRS"); store_pairs = e ? atoi(e) : 1; }
     // When one call produces both gradients, the d_W and d_h GEMMs each get half of the SM pairs and run side by
-    // side: d_h does not read d_W, so the d_W kernel releases it at once (programmatic dependent launch) and the
-    // d_h kernel, before it exits, waits for d_W so that stream order still implies "both are done".  Each CTA then
-    // walks two tiles, and the store of one overlaps the loads of the next.
+    // side, with the d_b column sums filling in beside them: none of the three reads another's output, so each
+    // kernel releases its successor at once (programmatic dependent launch) and every successor, before it exits,
+    // waits for its predecessor, so that stream order still implies "all three are done".  Each GEMM CTA then walks
+    // two tiles, and the store of one overlaps the loads of the next.
     static int pdl_on = -1;          // PERO_CE_PDL=0: the two gradient GEMMs run one after the other
     if (pdl_on < 0) { const char* e = getenv("PERO_CE_PDL"); pdl_on = e ? atoi(e) : 1; }
     const bool side_by_side = pdl_on && store_pairs && !dh_only && d_h != nullptr && full_range;
@@ -742,10 +771,6 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
                                                  (int)vlen, (int)l.Dhp, (int)l.Dhp, 1, 0, 1, 0, ep, st, nullptr, kSmemBudgetShared);
         if (rc) return rc;
 
-        // d_b right behind the kernel that wrote P (the columns are still in L2).  In the side-by-side schedule it
-        // releases the d_W GEMM at once, which in turn releases the d_h GEMM; each waits for its predecessor
-        // before it exits, so stream order still means "all three are done".
-        ce_db_kernel<<<(unsigned)((vlen + 63) / 64), 256, 0, st>>>(P, (int)M, (int)l.Pp, (int)v_begin, (int)v_end, d_b);
 
         // d_W [v_begin:v_end, Dh] = P[:, v_begin:v_end]^T @ A: both operands are read as stored (rows = masked
         // frames = the contraction index) through MN-major descriptors; no transposed copy of either exists.
@@ -754,10 +779,20 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         rc = store_pairs
                  ? launch_gemm_tn<2, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp,
                                                             (int)l.Mp64, 1, 0, 1, side_by_side ? half_workers : 0, sw, st, nullptr,
-                                                            kSmemBudgetShared, (int)M, side_by_side ? 3 : 0)
+                                                            kSmemBudgetShared, (int)M, side_by_side ? 1 : 0)
                  : launch_gemm_tn<1, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp,
                                                             (int)l.Mp64, 1, 0, 1, 0, sw, st, nullptr, kSmemBudgetShared, (int)M);
         if (rc) return rc;
+        // d_b: partial column sums of P now, unless the side-by-side schedule below runs them beside the GEMMs; the
+        // final sums on their own when this call stops after d_W | d_b (they are exchanged next), otherwise by the
+        // leading blocks of the scatter launch
+        if (!side_by_side) {
+            const int vlen8 = (int)((v_end == V ? l.Vp - v_begin : vlen) / 8);      // P's padding columns are zeros
+            ce_db_partial_kernel<<<db_nparts, 256, 0, st>>>(P, (int)M, (int)l.Pp, (int)v_begin, vlen8, (int)l.Vp, dbpart, 0);
+        }
+        if (!d_h)
+            ce_db_reduce_kernel<<<(unsigned)((vlen + 31) / 32), 256, 0, st>>>(dbpart, db_nparts, (int)l.Vp, (int)v_begin,
+                                                                              (int)v_end, d_b);
     }
 
     if (d_h) {
@@ -768,23 +803,39 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         rc = store_pairs
                  ? launch_gemm_tn<2, false, StoreEpi>(P, (int)M, (int)l.Pp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
                                                       1, side_by_side ? half_workers : 0, sh, st, nullptr, kSmemBudgetShared, 0,
-                                                      side_by_side ? 2 : 0)
+                                                      side_by_side ? 3 : 0)
                  : launch_gemm_tn<1, false, StoreEpi>(P, (int)M, (int)l.Pp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
                                                       1, 0, sh, st, nullptr, kSmemBudgetShared);
         if (rc) return rc;
+        if (side_by_side) {
+            // third member of the side-by-side group: released by the d_h GEMM as soon as that one has started
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)db_nparts); cfg.blockDim = dim3(256); cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, ce_db_partial_kernel, (const __nv_bfloat16*)P, (int)M, (int)l.Pp, 0,
+                                               (int)(l.Vp / 8), (int)l.Vp, dbpart, 1);
+            if (e != cudaSuccess) return (int)e;
+        }
         const long long total = N * (Dh / 4);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
+        const int db_blocks = dh_only ? 0 : (int)((V + 31) / 32);
+        blocks += db_blocks;
         // the number of planes actually produced is recomputed exactly as launch_gemm_tn does
         const int num_kb = (int)(l.Vp / 64);
         const int kb_per = (num_kb + (int)l.KS - 1) / (int)l.KS;
         const int ks_eff = (num_kb + kb_per - 1) / kb_per;
         if (h_is_bf16)
             ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
-                                                                                 static_cast<__nv_bfloat16*>(d_h));
+                                                                                 static_cast<__nv_bfloat16*>(d_h), db_blocks, dbpart,
+                                                                                 db_nparts, (int)l.Vp, (int)V, d_b);
         else
             ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
-                                                                         static_cast<float*>(d_h));
+                                                                         static_cast<float*>(d_h), db_blocks, dbpart, db_nparts,
+                                                                         (int)l.Vp, (int)V, d_b);
     }
     return (int)cudaGetLastError();
 }

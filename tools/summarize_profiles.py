@@ -19,13 +19,12 @@ def launches(src, dst):
     H, data = rows[hdr], rows[hdr + 1:]
     ki, vi = H.index("Kernel Name"), H.index("Metric Value")
     names = [(d[ki], float(d[vi].replace(",", ""))) for d in data]
+    # one step = the launches between two successive frames_prepare kernels; take the last COMPLETE one
     starts = [i for i, (n, _) in enumerate(names) if "frames_prepare" in n]
-    s = starts[-1]
-    out, tot, i = [], 0.0, s
-    while i < len(names) and "packed_init" not in names[i][0]:
-        n, v = names[i]
-        i += 1
-        if "FillFunctor" in n or "direct_copy" in n or "bfloat16_copy" in n:
+    s, e = starts[-2], starts[-1]
+    out, tot = [], 0.0
+    for n, v in names[s:e]:
+        if "FillFunctor" in n or "direct_copy" in n or "bfloat16_copy" in n or "packed_init" in n:
             continue
         out.append((n.split("(")[0].replace("void ", "").replace("pero::", ""), v / 1000.0))
         tot += v / 1000.0
