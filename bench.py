@@ -230,7 +230,7 @@ class DeviceStep:
         self.n_grad = c["V"] * c["Dh"] + c["V"]
         if dp:
             from pero_pretraining_b200.peer import PeerBuffer, PeerRange
-            blocks = int(os.environ.get("PERO_PEER_BLOCKS", "16"))
+            blocks = int(os.environ.get("PERO_PEER_BLOCKS", "24"))
             mc = os.environ.get("PERO_PEER_MULTICAST", "auto")
             mc = None if mc == "auto" else mc != "0"
             # one buffer (= one set of barrier words) per exchange chain: the EMA exchange and the gradient exchange

@@ -779,7 +779,7 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         rc = store_pairs
                  ? launch_gemm_tn<2, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp,
                                                             (int)l.Mp64, 1, 0, 1, side_by_side ? half_workers : 0, sw, st, nullptr,
-                                                            kSmemBudgetShared, (int)M, side_by_side ? 1 : 0)
+                                                            kSmemBudgetShared, (int)M, (side_by_side || pdl_on) ? 1 : 0)
                  : launch_gemm_tn<1, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp,
                                                             (int)l.Mp64, 1, 0, 1, 0, sw, st, nullptr, kSmemBudgetShared, (int)M);
         if (rc) return rc;
@@ -787,8 +787,17 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         // final sums on their own when this call stops after d_W | d_b (they are exchanged next), otherwise by the
         // leading blocks of the scatter launch
         if (!side_by_side) {
+            // beside the d_W GEMM (released by it at once, waits for it before exiting) when PDL is on
             const int vlen8 = (int)((v_end == V ? l.Vp - v_begin : vlen) / 8);      // P's padding columns are zeros
-            ce_db_partial_kernel<<<db_nparts, 256, 0, st>>>(P, (int)M, (int)l.Pp, (int)v_begin, vlen8, (int)l.Vp, dbpart, 0);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)db_nparts); cfg.blockDim = dim3(256); cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = pdl_on ? 1 : 0;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, ce_db_partial_kernel, (const __nv_bfloat16*)P, (int)M, (int)l.Pp, (int)v_begin,
+                                               vlen8, (int)l.Vp, dbpart, pdl_on ? 1 : 0);
+            if (e != cudaSuccess) return (int)e;
         }
         if (!d_h)
             ce_db_reduce_kernel<<<(unsigned)((vlen + 31) / 32), 256, 0, st>>>(dbpart, db_nparts, (int)l.Vp, (int)v_begin,

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import check
 
 HEADER_BYTES = 16384          # PERO_PEER_HEADER_BYTES
-DEFAULT_BLOCKS = 16
+DEFAULT_BLOCKS = 24
 
 
 def _round_up(a, b):
