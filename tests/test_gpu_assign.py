@@ -164,6 +164,37 @@ def test_assign_fixed_point_and_full_size_properties(cuda_dev):
     assert (dmin4.double() - d).abs().max().item() < 2e-2 * d.abs().max().item()
 
 
+def test_config5_codebook_sharded_stress_full_size(cuda_dev):
+    """BASELINE config 5 at full size on one GPU: 2**20 frames, 65536 x 512 codebook walked as 8 shards of 8192
+    codewords whose packed winners are min-merged (what the 8-rank MIN exchange does).  Frames generated around
+    codewords recover the generating index, and the merge is bit-identical to one call on the whole codebook."""
+    import time
+    ops = _ops()
+    g = torch.Generator(device=cuda_dev).manual_seed(5)
+    K, D, N, world = 65536, 512, 1 << 20, 8
+    C = torch.randn(K, D, device=cuda_dev, generator=g)
+    j = torch.randint(0, K, (N,), device=cuda_dev, generator=g)
+    X = C[j]
+    X += 0.5 * torch.randn(N, D, device=cuda_dev, generator=g)
+    packed = ops.vq_packed_init(N, cuda_dev)
+    shards = [ops.PreparedCodebook(K // world, D, cuda_dev).prepare(C[r * (K // world):(r + 1) * (K // world)].contiguous())
+              for r in range(world)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for r in range(world):
+        ops.vq_assign(X, shards[r], N, 1, False, index_offset=r * (K // world), packed=packed)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    idx, _ = ops.vq_unpack(packed)
+    assert (idx == j).float().mean().item() > 0.999
+    full = ops.PreparedCodebook(K, D, cuda_dev).prepare(C)
+    packed_full = ops.vq_packed_init(N, cuda_dev)
+    ops.vq_assign(X, full, N, 1, False, packed=packed_full)
+    assert torch.equal(packed_full, packed)
+    print(f"config 5 on one GPU: {dt * 1e3:.1f} ms for {2.0 * N * K * D / 1e12:.1f} TFLOP "
+          f"({2.0 * N * K * D / dt / 1e12:.0f} TFLOP/s incl. frame preparation)")
+
+
 def test_codebook_sharded_merge_equals_full_assign(cuda_dev):
     """SURVEY §8e codebook-sharded mode on one GPU: g shards packed into the same int64 buffer by atomicMin
     (what the MIN all-reduce does across ranks) == assignment against the whole codebook."""
