@@ -58,7 +58,9 @@ struct GemmShape {
     int num_stages;    // ring depth chosen by the host from the shared-memory budget
     int pdl;           // programmatic dependent launch: bit 0 = release the next kernel of the stream at once (it does
                        // not read this kernel's output), bit 1 = before exiting, wait for the previous kernel (this
-                       // kernel was released early by it and must not be seen to finish first)
+                       // kernel was released early by it, does not read its output, and must not be seen to finish
+                       // first), bit 2 = wait for the previous kernel after the set-up (barriers, TMEM, descriptor
+                       // prefetch), before the first global access: the set-up overlaps the producer kernel's tail
     unsigned long long* timeline;   // debug: per-unit clock64 stamps of worker 0 ([unit][8]); NULL in production
 };
 
@@ -188,6 +190,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (sh.pdl & 4) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     stamp_cta(sh, threadIdx.x == 0, 1);
     int u0, u1;

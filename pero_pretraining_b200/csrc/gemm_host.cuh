@@ -166,7 +166,7 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCtaGroup; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (pdl & 2) {      // may start while the previous kernel of the stream is still running (see GemmShape::pdl)
+    if (pdl & 6) {      // may start while the previous kernel of the stream is still running (see GemmShape::pdl)
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.numAttrs = 2;

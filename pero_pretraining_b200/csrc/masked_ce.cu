@@ -7,6 +7,7 @@
 // tcgen05 GEMMs for d_W = dlogits^T @ h and d_h = dlogits @ W (split over the label axis, fixed-order
 // reduction), then scatters d_h back to the frame positions.  No atomics anywhere: deterministic.
 #include <cub/device/device_select.cuh>
+#include <algorithm>
 #include <cuda_bf16.h>
 #include <thrust/iterator/counting_iterator.h>
 #include "../../include/pero_b200.h"
@@ -122,6 +123,8 @@ __global__ void __launch_bounds__(256)
 ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const long long* __restrict__ labels, int M,
                  int Dh, int Dhp, int Mpad, __nv_bfloat16* __restrict__ a, int* __restrict__ lab, int* __restrict__ inv,
                  unsigned int* __restrict__ ticket) {
+    // the logits GEMM behind this kernel sets itself up meanwhile and waits for this grid before its first load
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;
@@ -243,6 +246,8 @@ struct DlogitsEpi {
         const float* colvec;  // bias [Vt], -inf beyond V (already offset to the range's first column)
         const int* lab; const float* lse; const float* grad_scale;
         float inv_count;
+        const float* pm; const float* ps;   // when not NULL: the forward's LSE partials [slots, Mpad]; the log-sum-exp
+        int slots, Mpad;                    // is rebuilt from them instead of being read from `lse`
         __nv_bfloat16* p;      // already offset to the first label column of the range
         int M, Vp;             // Vp: label columns of the range to write (multiple of 32)
         int p_pitch;           // row pitch of P (the full padded label count)
@@ -252,7 +257,17 @@ struct DlogitsEpi {
     static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
         const bool ok = cx.row < ep.M;
         st.label = ok ? __ldg(ep.lab + cx.row) : -1;
-        st.lse2 = ok ? __ldg(ep.lse + cx.row) * kLog2e : CUDART_INF_F;
+        if (ok && ep.pm) {
+            // same combination as ce_finalize_kernel, in slot order (coalesced: neighbouring lanes own neighbouring rows)
+            float mx = -CUDART_INF_F;
+            for (int s = 0; s < ep.slots; ++s) mx = fmaxf(mx, __ldg(ep.pm + (size_t)s * ep.Mpad + cx.row));
+            float sum = 0.f;
+            for (int s = 0; s < ep.slots; ++s)
+                sum += __ldg(ep.ps + (size_t)s * ep.Mpad + cx.row) * exp2f((__ldg(ep.pm + (size_t)s * ep.Mpad + cx.row) - mx) * kLog2e);
+            st.lse2 = fmaf(mx, kLog2e, log2f(sum));
+        } else {
+            st.lse2 = ok ? __ldg(ep.lse + cx.row) * kLog2e : CUDART_INF_F;
+        }
         st.scale = ok ? ep.inv_count * (ep.grad_scale ? __ldg(ep.grad_scale) : 1.0f) : 0.f;
     }
     static __device__ __forceinline__ void tile(State& st, const Params& ep, const TileCtx& cx, uint32_t taddr) {
@@ -307,6 +322,9 @@ ce_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps, c
     // 32 rows per block; thread (r = tid % 32, g = tid / 32) combines slots g, g + 8, ... of row r: every load
     // instruction of a warp reads 32 consecutive rows of one slot (one 128-byte line), then the 8 groups are merged
     // through shared memory in a fixed order.
+    // a dlogits GEMM launched right behind (backward on the forward's workspace) recomputes the log-sum-exp from the
+    // same partials and never reads this kernel's output: it may start at once
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ float gm[8][33], gs[8][33];
     const int r = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int m = blockIdx.x * 32 + r;
@@ -657,7 +675,7 @@ int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
     ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S;
     rc = launch_gemm_tn<2, true, LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
                                          /*split_mode=*/1, (int)l.S, 0, ep, reinterpret_cast<cudaStream_t>(stream), nullptr,
-                                         kSmemBudgetShared);
+                                         kSmemBudgetShared, 0, /*pdl=*/4);
     if (rc) return rc;
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
     ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
@@ -702,7 +720,7 @@ int pero_masked_ce_eval(const void* h, int h_is_bf16, int64_t N, int64_t Dh, con
         reinterpret_cast<const __nv_bfloat16*>(ws + l.a_off), reinterpret_cast<const __nv_bfloat16*>(hb + hl.w_off), ep.colvec,
         ep.lab, (int)M, (int)l.Dhp, zl_in);
     rc = launch_gemm_tn<2, true, EvalEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
-                                          /*split_mode=*/1, (int)l.S, 0, ep, stream, nullptr, kSmemBudgetShared);
+                                          /*split_mode=*/1, (int)l.S, 0, ep, stream, nullptr, kSmemBudgetShared, 0, /*pdl=*/0);
     if (rc) return rc;
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
     ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
@@ -764,11 +782,22 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off) + v_begin;
         ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
         ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
+        // Directly behind the forward on the same workspace (h == NULL, first range): the log-sum-exp comes from the
+        // forward's partials, so this GEMM need not wait for ce_finalize_kernel (released by it at once; waits for it
+        // before exiting).  Behind its own gather: set-up overlaps the gather, then waits for it.
+        // (every label range of a backward on the forward's workspace uses the partials, so that walking the label
+        // axis range by range gives the same bits as one call)
+        const bool from_partials = (h == nullptr);
+        ep.pm = from_partials ? reinterpret_cast<const float*>(ws + l.pm_off) : nullptr;
+        ep.ps = from_partials ? reinterpret_cast<const float*>(ws + l.ps_off) : nullptr;
+        ep.slots = 2 * (int)l.S; ep.Mpad = (int)l.Mpad;
+        const int dl_pdl = (!pdl_on || v_begin != 0) ? 0 : (from_partials ? 2 : 4);
         ep.p = P + v_begin; ep.M = (int)M;
         ep.Vp = (int)(v_end == V ? l.Vp - v_begin : vlen);      // the last range also writes P's zero padding columns
         ep.p_pitch = (int)l.Pp; ep.col_base = (int)v_begin;
         rc = launch_gemm_tn<2, true, DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off + (size_t)v_begin * l.Dhp * 2,
-                                                 (int)vlen, (int)l.Dhp, (int)l.Dhp, 1, 0, 1, 0, ep, st, nullptr, kSmemBudgetShared);
+                                                 (int)vlen, (int)l.Dhp, (int)l.Dhp, 1, 0, 1, 0, ep, st, nullptr, kSmemBudgetShared,
+                                                 0, dl_pdl);
         if (rc) return rc;
 
 

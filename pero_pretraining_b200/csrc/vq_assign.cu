@@ -37,6 +37,8 @@ __global__ void codebook_prepare_kernel(const float* __restrict__ w, int K, int 
 __global__ void __launch_bounds__(256)
 frames_prepare_cf_kernel(const float* __restrict__ x, int D, int Dp, int HW, long long N,
                          __nv_bfloat16* __restrict__ xb, float* __restrict__ xr, long long* __restrict__ packed) {
+    // the distance GEMM behind this kernel sets itself up meanwhile and waits for this grid before its first load
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ float tile[64][33];
     const int nl = blockIdx.z, hw0 = blockIdx.x * 32, d0 = blockIdx.y * 64;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -70,6 +72,7 @@ frames_prepare_cf_kernel(const float* __restrict__ x, int D, int Dp, int HW, lon
 __global__ void __launch_bounds__(256)
 frames_prepare_rows_kernel(const float* __restrict__ x, int D, int Dp, long long N,
                            __nv_bfloat16* __restrict__ xb, float* __restrict__ xr, long long* __restrict__ packed) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long pairs = N * (Dp / 2);
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,17 +114,24 @@ int assign_variant_default(int num_kb) {
 }
 
 int run_assign_gemm(const __nv_bfloat16* xb, long long N, int Dp, const CodebookLayout& cl, const void* codebook,
-                    long long K, int index_offset, long long* packed, cudaStream_t stream) {
+                    long long K, int index_offset, long long* packed, cudaStream_t stream, int pdl = 0) {
     ArgminEpi::Params ep;
     ep.colvec = reinterpret_cast<const float*>(static_cast<const char*>(codebook) + cl.cnorm_off);
     ep.packed = packed; ep.rows = (int)N; ep.index_offset = index_offset;
     const void* cb = static_cast<const char*>(codebook) + cl.cb_off;
     const int v = assign_variant_default(Dp / kBlockK);
+    // Short contractions (D <= 256) leave room for a 7-deep ring inside the budget that keeps 27 KB of shared memory
+    // free for a co-resident bandwidth-bound CTA of another chain; long ones take the whole SM.
+    const size_t budget = (Dp / kBlockK <= 4) ? kSmemBudgetShared : kSmemBudget;
     switch (v & 3) {
-        case 0: return launch_gemm_tn<1, false, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream);
-        case 1: return launch_gemm_tn<2, false, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream);
-        case 2: return launch_gemm_tn<1, true, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream);
-        default: return launch_gemm_tn<2, true, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream);
+        case 0: return launch_gemm_tn<1, false, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
+                                                                budget, 0, pdl);
+        case 1: return launch_gemm_tn<2, false, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
+                                                                budget, 0, pdl);
+        case 2: return launch_gemm_tn<1, true, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
+                                                                budget, 0, pdl);
+        default: return launch_gemm_tn<2, true, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
+                                                                budget, 0, pdl);
     }
 }
 
@@ -207,7 +217,7 @@ int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
-    int rc = run_assign_gemm(xb, N, Dp, cl, codebook, K, (int)index_offset, packed, (cudaStream_t)stream);
+    int rc = run_assign_gemm(xb, N, Dp, cl, codebook, K, (int)index_offset, packed, (cudaStream_t)stream, /*pdl=*/4);
     if (rc) return rc;
     if (!packed_io && (idx || dmin)) {
         unpack_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(packed, N, reinterpret_cast<long long*>(idx), dmin);
