@@ -487,14 +487,16 @@ def our_arm(args):
     graph = None
     if not args.no_graph:
         try:
-            s = torch.cuda.Stream()
+            # The capture stream carries the quantize chain and the distance GEMM: high priority, like the masked-CE
+            # stream; only the EMA chain (and the head operand preparation) run at low priority and fill in beside.
+            s = torch.cuda.Stream(priority=-1)
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 ds()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=s):
                 ds()
             for _ in range(2):
                 graph.replay()

@@ -118,6 +118,11 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     sh.kb_per_split = (sh.num_kb + sh.num_ks - 1) / sh.num_ks;
     sh.num_ks = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;   // no empty splits
     sh.split_mode = split_mode; sh.fixed_s = fixed_s < 1 ? 1 : fixed_s;
+    {
+        static int pdl_off = -1;       // PERO_PDL=0: no programmatic dependent launches at all (diagnostic knob)
+        if (pdl_off < 0) { const char* e = getenv("PERO_PDL"); pdl_off = (e && atoi(e) == 0) ? 1 : 0; }
+        if (pdl_off) pdl = 0;
+    }
     sh.pdl = pdl;
     if (kAResident && (sh.num_ks != 1 || sh.num_kb > kMaxAKb)) return PERO_ERR_BAD_SHAPE;
     sh.num_stages = pick_stages(kCtaGroup, kAResident, sh.num_kb, Epi::kScratchPerWarp, smem_budget);
