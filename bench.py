@@ -220,7 +220,10 @@ class DeviceStep:
         self.out = {}
         # The masked-CE chain is the critical path: its stream (and the exchange stream) outrank the EMA chain, so
         # that pending GEMM CTAs are scheduled ahead of the EMA chain's bandwidth-bound kernels.
-        self.s_ema = torch.cuda.Stream(device=dev, priority=0)
+        # (data parallel: the EMA chain feeds an exchange that should be out of the way before the gradient exchange
+        # needs the links, so there it runs at high priority too)
+        ema_prio = int(os.environ.get("PERO_EMA_PRIO", "-1" if dp else "0"))
+        self.s_ema = torch.cuda.Stream(device=dev, priority=ema_prio)
         self.s_ce = torch.cuda.Stream(device=dev, priority=-1)
         self.s_comm = torch.cuda.Stream(device=dev, priority=-1)
         # Data-parallel exchange ranges (EMA sums|counts and d_W|d_b|loss_sum) live in a peer-mapped buffer and
