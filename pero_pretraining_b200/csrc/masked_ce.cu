@@ -422,7 +422,14 @@ __global__ void ce_sum_kernel(const float* __restrict__ v, int M, float* __restr
 // Fixed orders: bit-identical from run to run.
 __global__ void __launch_bounds__(256)
 ce_db_partial_kernel(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, int v_begin, int v_len8, int vp,
-                     float* __restrict__ part, int wait_for_previous) {
+                     float* __restrict__ part, int wait_for_previous, uint4* __restrict__ zero_fill, long long zero_vec) {
+    // side-by-side schedule: this kernel also clears d_h (zero_vec 16-byte words) while the gradient GEMMs run, so
+    // that the scatter behind them only has to write the masked frames
+    if (zero_fill) {
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < zero_vec; i += stride)
+            zero_fill[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     const int m0 = blockIdx.x * kDbRows;
     float* dst = part + (size_t)blockIdx.x * vp + v_begin;
     for (int c = threadIdx.x; c < v_len8; c += blockDim.x) {        // 8 columns per thread
@@ -482,7 +489,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ inv, const int* __restrict__ rows, long long N,
                      int M, int Dh, int KS, T* __restrict__ dh, int db_blocks, const float* __restrict__ dbpart, int nparts,
-                     int vp, int V, float* __restrict__ db) {
+                     int vp, int V, float* __restrict__ db, int masked_only) {
     if ((int)blockIdx.x < db_blocks) {
         ce_db_reduce_block(dbpart, nparts, vp, (int)blockIdx.x * 32, V, db);
         return;
@@ -491,12 +498,15 @@ ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ i
     const int sblock = (int)blockIdx.x - db_blocks;
     // one thread per 4 consecutive channels (Dh % 4 == 0): 16-byte plane reads, 16/8-byte stores
     const int g4 = Dh >> 2;
-    const long long total = N * g4;
+    const long long total = (masked_only ? (long long)M : N) * g4;
     const long long stride = (long long)scatter_blocks * blockDim.x;
-    for (long long i = (long long)sblock * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const long long n = i / g4;
-        const int g = (int)(i - n * g4);
-        const int m = masked_row_of(inv, rows, n, M);
+    for (long long j = (long long)sblock * blockDim.x + threadIdx.x; j < total; j += stride) {
+        // masked_only: d_h was cleared beforehand and only the rows of the masked frames are written
+        long long n = j / g4;
+        const int g = (int)(j - n * g4);
+        int m;
+        if (masked_only) { m = (int)n; n = __ldg(rows + m); } else { m = masked_row_of(inv, rows, n, M); }
+        const long long i = n * g4 + g;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m >= 0) {
             for (int k = 0; k < KS; ++k) {
@@ -825,7 +835,7 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
             at[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = pdl_on ? 1 : 0;
             cudaError_t e = cudaLaunchKernelEx(&cfg, ce_db_partial_kernel, (const __nv_bfloat16*)P, (int)M, (int)l.Pp, (int)v_begin,
-                                               vlen8, (int)l.Vp, dbpart, pdl_on ? 1 : 0);
+                                               vlen8, (int)l.Vp, dbpart, pdl_on ? 1 : 0, (uint4*)nullptr, 0ll);
             if (e != cudaSuccess) return (int)e;
         }
         if (!d_h)
@@ -833,6 +843,7 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
                                                                               (int)v_end, d_b);
     }
 
+    bool scatter_masked_only = false;
     if (d_h) {
         // planes[ks] [M, Dh] = P [M, Vp] @ W^T [Dh, Vp]^T over the ks-th slice of the label axis
         float* planes = reinterpret_cast<float*>(ws + l.planes_off);
@@ -853,11 +864,16 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
+            const long long zero_vec = (long long)N * Dh * (h_is_bf16 ? 2 : 4) / 16;       // Dh % 4 == 0 and, for bf16,
+            const bool can_zero = (((long long)N * Dh * (h_is_bf16 ? 2 : 4)) % 16 == 0) &&    // whole 16-byte words
+                                  ((reinterpret_cast<uintptr_t>(d_h) & 15) == 0);
+            scatter_masked_only = can_zero;
             cudaError_t e = cudaLaunchKernelEx(&cfg, ce_db_partial_kernel, (const __nv_bfloat16*)P, (int)M, (int)l.Pp, 0,
-                                               (int)(l.Vp / 8), (int)l.Vp, dbpart, 1);
+                                               (int)(l.Vp / 8), (int)l.Vp, dbpart, 1,
+                                               can_zero ? static_cast<uint4*>(d_h) : (uint4*)nullptr, can_zero ? zero_vec : 0ll);
             if (e != cudaSuccess) return (int)e;
         }
-        const long long total = N * (Dh / 4);
+        const long long total = (scatter_masked_only ? M : N) * (Dh / 4);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         const int db_blocks = dh_only ? 0 : (int)((V + 31) / 32);
@@ -869,11 +885,12 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         if (h_is_bf16)
             ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
                                                                                  static_cast<__nv_bfloat16*>(d_h), db_blocks, dbpart,
-                                                                                 db_nparts, (int)l.Vp, (int)V, d_b);
+                                                                                 db_nparts, (int)l.Vp, (int)V, d_b,
+                                                                                 scatter_masked_only ? 1 : 0);
         else
             ce_dh_scatter_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
                                                                          static_cast<float*>(d_h), db_blocks, dbpart, db_nparts,
-                                                                         (int)l.Vp, (int)V, d_b);
+                                                                         (int)l.Vp, (int)V, d_b, scatter_masked_only ? 1 : 0);
     }
     return (int)cudaGetLastError();
 }
