@@ -72,23 +72,27 @@ class _FusedHeadCE(torch.autograd.Function):
             lab = lab.contiguous()
         saved, loss = [], None
         for rows, m_local, weight in terms:
-            if dp_group is not None:
-                cnt = torch.tensor([float(m_local)], device=h2.device)
-                torch.distributed.all_reduce(cnt, group=dp_group)
-                m_global = float(cnt.item())
-            else:
-                m_global = float(m_local)
             if m_local > 0:
                 loss_sum, lse, ws = ops.masked_ce_fwd(h2, rows, lab, head_prep)
             else:
                 loss_sum, lse, ws = torch.zeros(1, device=h2.device), None, None
             if dp_group is not None:
-                loss_sum = loss_sum.clone()
-                torch.distributed.all_reduce(loss_sum, group=dp_group)
-            # mean over the GLOBAL number of selected frames; an empty selection gives NaN like F.cross_entropy
-            term = loss_sum.view(()) * (weight / m_global if m_global > 0 else float('nan'))
+                # (loss_sum, M) summed over the ranks in ONE small collective; the global count stays on the device
+                # (scale = weight / M_global is applied by the kernels through their device-scalar argument), so the
+                # step has no host synchronisation here.  Empty global selection: 0 * (w / 0) = NaN, like the reference.
+                stats = torch.empty(2, dtype=torch.float32, device=h2.device)
+                stats[0:1].copy_(loss_sum)
+                stats[1].fill_(float(m_local))
+                torch.distributed.all_reduce(stats, group=dp_group)
+                scale = weight / stats[1:2]                                  # [1] device tensor
+                term = (stats[0:1] * scale).view(())
+            else:
+                m_global = float(m_local)
+                scale = weight / m_global if m_global > 0 else float('nan')   # host float
+                # mean over the number of selected frames; an empty selection gives NaN like F.cross_entropy
+                term = loss_sum.view(()) * scale
             loss = term if loss is None else loss + term
-            saved.append((rows, m_local, weight, m_global, lse, ws))
+            saved.append((rows, m_local, scale, lse, ws))
         ctx.saved = saved
         ctx.h2, ctx.lab, ctx.head_prep, ctx.dp_group = h2, lab, head_prep, dp_group
         ctx.peer_range = peer_range
@@ -106,12 +110,16 @@ class _FusedHeadCE(torch.autograd.Function):
         d_h = d_W = d_b = None
         peer = ctx.peer_range if ctx.dp_group is not None else None
         flat = None
-        for rows, m_local, weight, m_global, lse, ws in ctx.saved:
-            if m_local == 0 or m_global == 0:
+        for rows, m_local, scale, lse, ws in ctx.saved:
+            if m_local == 0:
                 continue
             first = flat is None
+            if isinstance(scale, torch.Tensor):          # data parallel: device scalar weight / M_global
+                gs, inv = g * scale, 1.0
+            else:
+                gs, inv = g, scale
             # the forward's workspace still holds the gathered operands of this term: no second gather
-            dh_t, _, _, flat_t = ops.masked_ce_bwd(h2, rows, lab, head, lse, g, weight / m_global, want_dh=want_dh,
+            dh_t, _, _, flat_t = ops.masked_ce_bwd(h2, rows, lab, head, lse, gs, inv, want_dh=want_dh,
                                                    return_flat=True, ws=ws, ws_from_fwd=True,
                                                    flat_out=peer.tensor if (first and peer is not None) else None)
             d_h = dh_t if d_h is None else (d_h + dh_t if dh_t is not None else d_h)
