@@ -463,6 +463,30 @@ def _log(msg):
         sys.stderr.flush()
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer exists: pinned
+    memory is placed on the NUMA node of the allocating thread, and a far node roughly halves the H2D bandwidth the
+    e2e leg depends on (and adds latency to every launch).  Returns (all cpus, bound cpus) or (all, None)."""
+    all_cpus = sorted(os.sched_getaffinity(0))
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local_rank)
+        try:
+            bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(all_cpus) // 64) + 1)
+        local = [c for c in all_cpus if (int(words[c // 64]) >> (c % 64)) & 1]
+        if local and len(local) < len(all_cpus):
+            os.sched_setaffinity(0, local)
+            return all_cpus, local
+    except Exception:
+        pass
+    return all_cpus, None
+
+
 def our_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -470,6 +494,7 @@ def our_arm(args):
     dp = world > 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus, bound_cpus = bind_to_gpu_numa_node(local_rank)
     if dp:
         torch.distributed.init_process_group("nccl", device_id=dev)
     from pero_pretraining_b200 import ops
@@ -570,6 +595,7 @@ def our_arm(args):
     _log("e2e leg done")
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
+        os.sched_setaffinity(0, all_cpus)              # the CPU arm gets every host core again
         mean_s, min_s = run_cpu(make_batch(0), 3, 1)
         cpu = {"value": ds.M / mean_s, "unit": "masked frames/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "3 full-size steps of one 64-line batch after 1 warm-up", "ms_per_step": mean_s * 1e3}
@@ -582,7 +608,8 @@ def our_arm(args):
                            "masked_frames_per_step": m_total, "frames_per_step": N * world, "parallelism": f"dp{world}" if dp else "single",
                            "exchange": (f"libpero peer all-reduce ({ds.peer.transport}, {ds.peer.n_blocks} CTAs), head backward in "
                                         f"{len(ds.v_ranges)} label ranges" if dp else None),
-                           "l2": "flushed (256 MiB write) between timed steps", "launch": "cuda_graph" if graph is not None else "eager"},
+                           "l2": "flushed (256 MiB write) between timed steps", "launch": "cuda_graph" if graph is not None else "eager",
+                           "host_affinity": (f"{len(bound_cpus)} CPUs local to the GPU (NVML)" if bound_cpus else "unchanged")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": (n_ours if n_ours > 0 else n_kernels) * args.steps, "kernels_per_step": n_kernels, "clocks": clocks}
         print(json.dumps(line), flush=True)
