@@ -319,15 +319,21 @@ class DeviceStep:
         return self.out
 
 
-def count_kernels(fn):
-    """Kernels launched by one step (CUPTI via torch.profiler); -1 when the profiler is unavailable."""
+def count_kernels(fn, align=None):
+    """Kernels launched by one step (CUPTI via torch.profiler); -1 when the profiler is unavailable.
+    `align` (data parallel: a barrier) runs after the profiler has started, so that ranks whose profiler start-up
+    differs by seconds enter the step's exchange kernels together."""
     try:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            if align is not None:
+                align()
+                torch.cuda.synchronize()
             fn()
             torch.cuda.synchronize()
-        names = [e.name for e in prof.events() if getattr(e, "device_type", None) is not None and "cuda" in str(e.device_type).lower()]
-        ours = [n for n in names if "pero" in n or "cub" in n.lower()]
+        names = [e.name for e in prof.events() if getattr(e, "device_type", None) is not None and "cuda" in str(e.device_type).lower()
+                 and "nccl" not in e.name.lower()]
+        ours = [n for n in names if "pero" in n or "cub" in n.lower() or "allreduce" in n]
         return len(names), len(ours)
     except Exception:
         return -1, -1
@@ -510,7 +516,7 @@ def our_arm(args):
         ds()
     torch.cuda.synchronize()
     _log("eager warm-up done")
-    n_kernels, n_ours = count_kernels(ds)
+    n_kernels, n_ours = count_kernels(ds, torch.distributed.barrier if dp else None)
     _log(f"kernel count {n_kernels}")
     graph = None
     if not args.no_graph:

@@ -232,7 +232,7 @@ int pero_mask_compact(const void* mask, int mask_dtype, int want_value, const in
  * multimem.st) or NULL (peer loads summed in rank order + peer stores).  One kernel per call, n_blocks CTAs
  * (1..PERO_PEER_MAX_BLOCKS; 16-32 saturate NVLink and leave the other SMs to the GEMMs running beside it);
  * all ranks must issue the same sequence of calls with the same n_blocks.  n_elems % 4 == 0 (f32) / % 2 == 0 (i64).
- * A rank that does not arrive within ~4 s makes the waiting kernels trap (sticky CUDA error) instead of hanging.
+ * A rank that does not arrive within 30 s makes the waiting kernels trap (sticky CUDA error) instead of hanging.
  * pero_peer_allreduce_emulate: the same protocol with all `world` buffers on ONE device and the ranks played
  * by blockIdx.y of one cooperative launch (op 0 = f32 sum, 1 = i64 min) — single-GPU test of the protocol only.
  */

@@ -15,7 +15,7 @@
 // Barriers are one-way release stores of a growing epoch into arrival words in the first
 // PERO_PEER_HEADER_BYTES of each peer's buffer ([block][source rank] u32) polled locally with acquire loads;
 // nothing is ever reset, so the kernels are CUDA-graph replayable.
-// A rank that never arrives makes the waiters trap after ~4 s instead of hanging the GPU.
+// A rank that never arrives makes the waiters trap after 30 s instead of hanging the GPU.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -27,7 +27,8 @@ namespace {
 constexpr int kMaxThreads = 512;
 constexpr int kMaxWorld = PERO_PEER_MAX_WORLD;
 constexpr int kMaxBlocks = PERO_PEER_MAX_BLOCKS;
-constexpr unsigned long long kTimeoutNs = 4000000000ull;
+constexpr unsigned long long kTimeoutNs = 30000000000ull;   // 30 s: ranks may reach their first exchange seconds apart
+                                                            // (lazy module loading, profiler start-up), never minutes
 static_assert(kMaxWorld * kMaxBlocks * 4 <= 8192 && 8192 + kMaxBlocks * 4 <= PERO_PEER_HEADER_BYTES, "flag words must fit the buffer header");
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {

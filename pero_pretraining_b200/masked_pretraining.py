@@ -13,22 +13,31 @@ import torch
 from . import ops
 
 
-_PINNED_RING = {"bufs": [], "next": 0}
+_PINNED_RING = {"bufs": [], "events": [], "next": 0}
 
 
-def _pinned_rows(rows, ring=8):
-    """Copy `rows` (numpy int32) into one of `ring` reusable pinned host buffers and return the view.
-    A buffer is reused only `ring` calls later, long after the asynchronous copy that read it."""
+def _pinned_rows(rows, device, ring=8):
+    """Stage `rows` (numpy int32) through one of `ring` reusable pinned host buffers and return the device copy.
+    A pageable-memory H2D copy would block the host until everything already queued on the stream has run; a pinned
+    source keeps it asynchronous.  Each slot remembers the event recorded behind its last copy and is reused only
+    once that copy has executed, however far the host has run ahead of the device."""
     st = _PINNED_RING
     if len(st["bufs"]) < ring:
         st["bufs"] = [torch.empty(max(4096, rows.size), dtype=torch.int32).pin_memory() for _ in range(ring)]
+        st["events"] = [None] * ring
     i = st["next"]
     st["next"] = (i + 1) % ring
+    if st["events"][i] is not None:
+        st["events"][i].synchronize()
     if st["bufs"][i].numel() < rows.size:
         st["bufs"][i] = torch.empty(int(rows.size * 1.5) + 16, dtype=torch.int32).pin_memory()
     buf = st["bufs"][i][:rows.size]
     buf.numpy()[:] = rows
-    return buf
+    out = buf.to(device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    st["events"][i] = ev
+    return out
 
 
 def _rows_from_mask(mask, labels, want, require_label, device):
@@ -43,10 +52,7 @@ def _rows_from_mask(mask, labels, want, require_label, device):
         rows = np.flatnonzero(sel).astype(np.int32)
         if device.type != "cuda":
             return torch.from_numpy(rows), int(rows.size)
-        # A pageable-memory H2D copy blocks the host until everything already queued on the stream has
-        # run; staging through a small ring of pinned buffers keeps the copy asynchronous.
-        staged = _pinned_rows(rows)
-        return staged.to(device, non_blocking=True), int(rows.size)
+        return _pinned_rows(rows, device), int(rows.size)
     mask = mask.to(device)
     rows, count = ops.mask_compact(mask, labels if require_label else None, want)
     m = int(count.item())
