@@ -40,6 +40,22 @@ def _pinned_rows(rows, device, ring=8):
     return out
 
 
+def create_mask(labels, masking_prob, rng=None):
+    """BatchOperator._create_mask (masked_pretraining/batch_operator.py:27-32): mask = (rand < p) * (labels >= 0) as a
+    host numpy int array, so that the masked-frame list and its length M are known without a device sync.
+    rng=None draws from numpy's global generator exactly like the reference (same seed -> same mask); a
+    numpy Generator / RandomState may be passed instead."""
+    labels = np.asarray(labels)
+    active = (labels >= 0).astype(int)
+    if rng is None:
+        draw = np.random.rand(*labels.shape)
+    elif hasattr(rng, "random"):
+        draw = rng.random(labels.shape)
+    else:
+        draw = rng.rand(*labels.shape)
+    return (draw < masking_prob).astype(int) * active
+
+
 def _rows_from_mask(mask, labels, want, require_label, device):
     """Ordered int32 frame indices with mask == want.  A numpy mask (what BatchOperator._create_mask
     returns, batch_operator.py:27-32) is compacted on the host: M is known without a device sync.  A tensor

@@ -161,3 +161,18 @@ def test_label_wire_format_roundtrip(tmp_path):
     q = os.path.join(tmp_path, "m.txt")
     save_labels({"x": [5, 6], "y": [9, 11, 12]}, q)
     assert open(q).read() == open(p).read()
+
+
+def test_create_mask_matches_reference_batch_operator():
+    """masked_pretraining/batch_operator.py:27-32 restated: same global-numpy seed -> same mask; padding (-1) never masked."""
+    import numpy as np
+    from pero_pretraining_b200 import create_mask
+    labels = np.random.default_rng(0).integers(-1, 50, size=(6, 40))
+    np.random.seed(123)
+    want = (np.random.rand(*labels.shape) < 0.15).astype(int) * (labels >= 0).astype(int)      # the reference's two lines
+    np.random.seed(123)
+    got = create_mask(labels, 0.15)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    assert not got[labels < 0].any()
+    g = create_mask(labels, 0.5, np.random.default_rng(1))
+    assert g.shape == labels.shape and set(np.unique(g)) <= {0, 1}
