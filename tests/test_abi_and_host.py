@@ -176,3 +176,17 @@ def test_create_mask_matches_reference_batch_operator():
     assert not got[labels < 0].any()
     g = create_mask(labels, 0.5, np.random.default_rng(1))
     assert g.shape == labels.shape and set(np.unique(g)) <= {0, 1}
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/pero_b200.h is the drop-in boundary: it must compile as C99 (no C++-isms, no CUDA or torch types), so
+    that cgo / JNI / ctypes-style bindings of any host language can consume it."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "pero_b200.h"\n'
+                   'int probe(void) { return pero_version() + (int)pero_vq_codebook_bytes(8, 8) + PERO_PEER_HEADER_BYTES; }\n')
+    res = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"),
+                          str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
