@@ -249,9 +249,10 @@ int pero_peer_allreduce_emulate(void* const* bufs_on_one_device, int world, int 
 /* ------------------------------------------------------------------ test hook
  * C[rows_a, rows_b] = A @ B^T through the same tcgen05 core (bf16 operands with row pitch `kd`,
  * fp32 out).  variant: bit0 = CTA pairs (cta_group::2), bit1 = resident A.  Used by tests only. */
-/* Debug only: while non-NULL, every GEMM launch writes clock64 stamps of its worker 0 to device_buffer
+/* Debug only: the next `slots` GEMM launches each write clock64 stamps of their worker 0 into the next 64 KiB
+ * (8192 u64) slot of device_buffer, later launches none; NULL switches it off.  Slot layout
  * ([unit][8] u64: mma_top, mma_tempty_ok, mma_first_full, mma_issued, epi_tfull_ok, epi_done, prod_first, prod_last). */
-int pero_debug_set_timeline(void* device_buffer);
+int pero_debug_set_timeline(void* device_buffer, int slots);
 int pero_debug_gemm_tn(const void* a_bf16, int64_t rows_a, const void* b_bf16, int64_t rows_b, int64_t kd,
                        int variant, int num_splits, float* out, pero_stream_t stream);
 

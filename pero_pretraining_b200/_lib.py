@@ -63,7 +63,7 @@ SIGNATURES = {
     "pero_peer_allreduce_sum_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "pero_peer_allreduce_min_i64": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "pero_peer_allreduce_emulate": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
-    "pero_debug_set_timeline": (c_int, [c_vp]),
+    "pero_debug_set_timeline": (c_int, [c_vp, c_int]),
     "pero_debug_gemm_tn": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
 }
 

@@ -81,8 +81,10 @@ inline int device_sm_count() {
     return sms;
 }
 
-// Debug only (pero_debug_set_timeline): when set, every GEMM launch records worker 0's clock64 stamps there.
+// Debug only (pero_debug_set_timeline): while slots remain, every GEMM launch records worker 0's clock64 stamps
+// in the next 64 KiB slot of the caller's buffer; once the slots are used up, launches run without stamps.
 inline unsigned long long* g_debug_timeline = nullptr;
+inline int g_debug_timeline_slots = 0;
 
 constexpr size_t kSmemBudget = 227 * 1024;
 // Budget for GEMMs that run beside other chains of the step (masked CE): leaves ~27 KB of shared memory and, with
@@ -108,8 +110,12 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
                    int k_rows = 0, int pdl = 0) {
     if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
     GemmShape sh;
-    sh.timeline = timeline ? timeline : g_debug_timeline;
-    if (!timeline && g_debug_timeline) g_debug_timeline += 8192;    // debug: one 64 KiB slot per GEMM launch
+    sh.timeline = timeline;
+    if (!timeline && g_debug_timeline && g_debug_timeline_slots > 0) {     // debug: one 64 KiB slot per GEMM launch
+        sh.timeline = g_debug_timeline;
+        g_debug_timeline += 8192;
+        --g_debug_timeline_slots;
+    }
     sh.rows_a = rows_a; sh.rows_b = rows_b;
     sh.num_kb = kd / kBlockK;
     sh.num_rb = (rows_a + kBlockM * kCtaGroup - 1) / (kBlockM * kCtaGroup);

@@ -239,8 +239,9 @@ int pero_vq_assign_bf16(const void* x_bf16, int64_t N, int64_t K, int64_t D, con
                            reinterpret_cast<long long*>(packed_io), (cudaStream_t)stream);
 }
 
-int pero_debug_set_timeline(void* device_buffer) {
+int pero_debug_set_timeline(void* device_buffer, int slots) {
     g_debug_timeline = static_cast<unsigned long long*>(device_buffer);
+    g_debug_timeline_slots = device_buffer ? (slots > 0 ? slots : 0) : 0;
     return PERO_OK;
 }
 

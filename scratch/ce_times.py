@@ -13,11 +13,11 @@ names = ["lse", "dlogits", "dW", "dh"]
 for rep in range(2):
     tl = torch.zeros(4 * 8192, dtype=torch.int64, device=dev)
     flush.zero_(); torch.cuda.synchronize()
-    L.pero_debug_set_timeline(tl.data_ptr())
+    L.pero_debug_set_timeline(tl.data_ptr(), tl.numel() // 8192)
     loss_sum, lse, ws = ops.masked_ce_fwd(h, rows, labels, head)
     ops.masked_ce_bwd(h, rows, labels, head, lse, None, 1.0 / rows.numel(), ws=ws)
     torch.cuda.synchronize()
-    L.pero_debug_set_timeline(None)
+    L.pero_debug_set_timeline(None, 0)
 t = tl.view(4, 8192).cpu()
 for gi, nm in enumerate(names):
     c = t[gi][4096:4096 + 148 * 4].view(148, 4).double()

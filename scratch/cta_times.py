@@ -10,7 +10,7 @@ for N, K, D in [(8192, 8192, 256), (16384, 16384, 256)]:
     cb = ops.PreparedCodebook(K, D, dev).prepare(w)
     packed = torch.empty(N, dtype=torch.int64, device=dev)
     tl = torch.zeros(4096 + 148 * 4 + 64, dtype=torch.int64, device=dev)
-    L.pero_debug_set_timeline(tl.data_ptr())
+    L.pero_debug_set_timeline(tl.data_ptr(), tl.numel() // 8192)
     for cold in (0, 1, 1):
         tl.zero_(); L.pero_vq_packed_init(packed.data_ptr(), N, stream)
         if cold: flush.zero_()
@@ -23,4 +23,4 @@ for N, K, D in [(8192, 8192, 256), (16384, 16384, 256)]:
         ent, setup, epi, ex = [(t[:, i] - t0) / 1e3 for i in range(4)]
         print(f"N={N} K={K} cold={cold}: event {e0.elapsed_time(e1)*1e3:.1f} us | entry spread {ent.max():.1f} us | setup done {setup.min():.1f}..{setup.max():.1f} | "
               f"epilogue done {epi[epi>0].min():.1f}..{epi.max():.1f} | exit {ex.min():.1f}..{ex.max():.1f} | per-cta busy {(ex-ent).min():.1f}..{(ex-ent).max():.1f}")
-    L.pero_debug_set_timeline(None)
+    L.pero_debug_set_timeline(None, 0)

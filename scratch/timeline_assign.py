@@ -10,12 +10,12 @@ for N, K, D in [(16384, 16384, 256)]:
     cb = ops.PreparedCodebook(K, D, dev).prepare(w)
     packed = torch.empty(N, dtype=torch.int64, device=dev)
     tl = torch.zeros(256 * 8, dtype=torch.int64, device=dev)
-    L.pero_debug_set_timeline(tl.data_ptr())
+    L.pero_debug_set_timeline(tl.data_ptr(), tl.numel() // 8192)
     for _ in range(2):
         tl.zero_(); L.pero_vq_packed_init(packed.data_ptr(), N, stream)
         _lib.check(L.pero_vq_assign_bf16(xb.data_ptr(), N, K, D, cb.blob.data_ptr(), 0, packed.data_ptr(), stream), "assign")
         torch.cuda.synchronize()
-    L.pero_debug_set_timeline(None)
+    L.pero_debug_set_timeline(None, 0)
     t = tl.view(256, 8).cpu(); t0 = int(t[0][6])
     print("unit " + " ".join(f"{n:>14s}" for n in names))
     for u in list(range(6)) + list(range(40, 46)):

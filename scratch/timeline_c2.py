@@ -12,10 +12,10 @@ packed = torch.empty(N, dtype=torch.int64, device=dev)
 tl = torch.zeros(8192 + 148 * 4 + 64, dtype=torch.int64, device=dev)
 for _ in range(3):
     tl.zero_(); L.pero_vq_packed_init(packed.data_ptr(), N, stream); flush.zero_()
-    L.pero_debug_set_timeline(tl.data_ptr())       # every launch advances the debug pointer by one 64 KiB slot
+    L.pero_debug_set_timeline(tl.data_ptr(), tl.numel() // 8192)       # every launch advances the debug pointer by one 64 KiB slot
     _lib.check(L.pero_vq_assign_bf16(xb.data_ptr(), N, K, D, cb.blob.data_ptr(), 0, packed.data_ptr(), stream), "assign")
     torch.cuda.synchronize()
-    L.pero_debug_set_timeline(None)
+    L.pero_debug_set_timeline(None, 0)
 t = tl[:4096].view(512, 8).cpu(); t0 = int(t[0][6])
 c = tl[4096:4096 + 4].cpu()
 print("cta0 ns: setup", int(c[1]-c[0]), "epi_done", int(c[2]-c[0]), "exit", int(c[3]-c[0]))
