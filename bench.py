@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the BASELINE configs[2..4] legs (c3, c4, c5)")
+    ap.add_argument("--skip-gpu-baseline", action="store_true", help="skip the torch-on-B200 reference leg")
+    ap.add_argument("--cpu-time-cap", type=float, default=150.0, help="reference arm: stop after this many seconds of CPU steps")
     ap.add_argument("--timeline", default=None, help="write the kernel timeline (CUPTI) of 2 step replays to this file")
     return ap.parse_args()
 
@@ -158,17 +161,26 @@ def cpu_step_factory(batch):
     return step
 
 
-def run_cpu(batch, reps, warm):
+def run_cpu(batch, reps, warm, time_cap=None):
+    """Returns (mean s/step, min s/step, timed steps done, warm-up steps done).  `time_cap` (seconds) bounds the
+    whole call: the warm-up is cut to one step and the timed loop stops early when the cap is reached."""
     torch.set_num_threads(os.cpu_count() or 1)
     step = cpu_step_factory(batch)
+    t_start = time.perf_counter()
+    warm_done = 0
     for _ in range(warm):
         step()
+        warm_done += 1
+        if time_cap is not None and time.perf_counter() - t_start > 0.25 * time_cap:
+            break
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
         step()
         ts.append(time.perf_counter() - t0)
-    return float(np.mean(ts)), float(np.min(ts))
+        if time_cap is not None and time.perf_counter() - t_start > time_cap:
+            break
+    return float(np.mean(ts)), float(np.min(ts)), len(ts), warm_done
 
 
 def reference_arm(args):
@@ -177,16 +189,19 @@ def reference_arm(args):
         return
     batch = make_batch(0)
     M = int(batch["mask"].sum())
-    steps = max(1, min(args.steps, 5))           # bounded sample: each CPU step takes seconds
-    warm = 1 if args.warmup > 0 else 0
-    mean_s, _ = run_cpu(batch, steps, warm)
+    # --steps / --warmup are honoured up to a wall-clock cap (a CPU step takes 0.1-1 s depending on the host)
+    mean_s, _, steps, warm = run_cpu(batch, max(1, args.steps), max(0, args.warmup), time_cap=args.cpu_time_cap)
     val = M / mean_s
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": "masked_frames_per_sec", "value": val, "unit": "masked frames/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": mean_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, **{k: CFG[k] for k in ("lines", "frames", "K", "D", "Dh", "V", "p")},
-                       "note": "reference path restated on torch CPU ops (oracle port); rank 0 only, N ranks do not add CPU work"},
+                       "masked_frames_per_step": float(M), "frames_per_step": CFG["lines"] * CFG["frames"],
+                       "parallelism": "host cores of rank 0 (N ranks do not add CPU work)", "exchange": None, "l2": "n/a",
+                       "launch": "cpu", "host_affinity": "all host cores",
+                       "note": "reference path restated on torch CPU ops (oracle port)",
+                       "steps_requested": args.steps, "warmup_requested": args.warmup, "time_cap_s": args.cpu_time_cap},
             "cpu_baseline": {"value": val, "unit": "masked frames/s", "cores": cores, "kind": "port",
                              "sample": f"{steps} full-size steps of one 64-line batch after {warm} warm-up"},
             "e2e": {"value": val, "unit": "masked frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -463,6 +478,260 @@ def gemm_roofline_leg(ds, dev, iters, flush):
     return float(np.mean(ts)), float(np.min(ts)), R
 
 
+# ------------------------------------------------------------------------------------------------ GPU bar + other configs
+def timed_loop(fn, steps, warm, flush, dp, use_graph=True):
+    """ms per call of fn(): `warm` untimed calls, then `steps` calls each bracketed by CUDA events on the current stream
+    with the L2 flushed in between; max over ranks.  fn is captured into a CUDA graph when possible."""
+    run, graph = fn, None
+    for _ in range(max(1, warm)):
+        fn()
+    torch.cuda.synchronize()
+    if use_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                fn()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=s):
+                fn()
+            graph.replay()
+            torch.cuda.synchronize()
+            run = graph.replay
+        except Exception as e:      # noqa: BLE001
+            sys.stderr.write(f"[bench] graph capture unavailable for {getattr(fn, '__name__', fn)}: {e}\n")
+            torch.cuda.synchronize()
+            run, graph = fn, None
+    for _ in range(max(3, warm)):
+        run()
+    torch.cuda.synchronize()
+    if dp:
+        torch.distributed.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record()
+        run()
+        e1.record()
+    torch.cuda.synchronize()
+    if dp:
+        torch.distributed.barrier()
+    ts = [e0.elapsed_time(e1) for e0, e1 in ev]
+    total = float(sum(ts))
+    if dp:
+        t = torch.tensor([total], device=flush.device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total = float(t.item())
+    return total / steps, float(min(ts)), ("cuda_graph" if graph is not None else "eager"), graph
+
+
+def gpu_baseline_leg(batch, dev, flush, steps=10, warm=3):
+    """The bar SURVEY 2b / 8d names: the reference's own torch op sequence for this step run on the SAME B200 (cuBLAS /
+    ATen pick their sm_100 kernels), restated here op for op:
+      VectorQuantizer.forward + calculate_loss   models/autoencoders.py:193-241  (3 dense fp32 GEMMs, one-hot matrix)
+      LinearHead over EVERY frame                masked_pretraining/model.py:104-105
+      MaskedCrossEntropyLoss                     masked_pretraining/model.py:78-82  (boolean-mask gather, F.cross_entropy)
+      loss.backward()                            autograd
+    fp32 with TF32 off (torch's default, what the reference runs), and with the head + loss under bf16 autocast as
+    masked_pretraining/trainer.py:57-59 does with --bfloat16.  Device time per step by CUDA events, L2 flushed."""
+    import torch.nn.functional as F
+    c = CFG
+    K = c["K"]
+    x = batch["x"].to(dev).requires_grad_(True)                       # [Nl, D, 1, T]
+    gq = batch["gq"].to(dev)
+    h = batch["h"].to(dev).requires_grad_(True)                       # [Nl, T, Dh]
+    W = batch["W"].to(dev).requires_grad_(True)
+    b = batch["b"].to(dev).requires_grad_(True)
+    mask_t = torch.from_numpy(batch["mask"]).to(dev)
+    state = dict(weight=batch["weight"].to(dev).clone(), ema_w=batch["weight"].to(dev).clone(), cs=torch.ones(K, device=dev))
+    out = {}
+
+    def step(autocast):
+        weight = state["weight"]
+        inputs = x.permute(0, 2, 3, 1).contiguous()                                                    # :205
+        flat = inputs.view(-1, c["D"])                                                                 # :209
+        distances = (torch.sum(flat ** 2, dim=1, keepdim=True) + torch.sum(weight ** 2, dim=1)
+                     - 2 * torch.matmul(flat, weight.t()))                                             # :212-214
+        idx = torch.argmin(distances, dim=1).unsqueeze(1)                                              # :217
+        enc = torch.zeros(idx.shape[0], K, device=dev)
+        enc.scatter_(1, idx, 1)                                                                        # :218-219
+        quantized = torch.matmul(enc, weight).view(inputs.shape)                                       # :222
+        with torch.no_grad():                                                                          # :225-237
+            cs = state["cs"] * c["decay"] + (1 - c["decay"]) * torch.sum(enc, 0)
+            n = torch.sum(cs)
+            cs = (cs + c["epsilon"]) / (n + K * c["epsilon"]) * n
+            dw = torch.matmul(enc.t(), flat)
+            ema_w = state["ema_w"] * c["decay"] + (1 - c["decay"]) * dw
+            state.update(weight=ema_w / cs.unsqueeze(1), ema_w=ema_w, cs=cs)
+        quantized = inputs + (quantized - inputs).detach()                                             # :239
+        q = quantized.permute(0, 3, 1, 2).contiguous()                                                 # :241
+        loss_c = c["commitment_cost"] * F.mse_loss(q.detach(), x)                                      # :198-200
+        labels = idx.detach().view(c["lines"], c["frames"])
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):                           # trainer.py:57-59
+            logits = F.linear(h, W, b)                                                                 # model.py:104-105
+            sel = mask_t == 1                                                                          # model.py:79-80
+            loss = F.cross_entropy(logits[sel], labels[sel])                                           # model.py:82
+        x.grad = h.grad = W.grad = b.grad = None
+        torch.autograd.backward([loss_c + loss, q], [None, gq])
+        out["loss"] = loss
+
+    res = {}
+    M = int(batch["mask"].sum())
+    for name, autocast in (("fp32", False), ("bf16_autocast_head", True)):
+        state.update(weight=batch["weight"].to(dev).clone(), ema_w=batch["weight"].to(dev).clone(), cs=torch.ones(K, device=dev))
+        ms, ms_min, _, _ = timed_loop(lambda: step(autocast), steps, warm, flush, False, use_graph=False)
+        res[name] = {"ms_per_step": ms, "ms_min": ms_min, "value": M / (ms * 1e-3), "unit": "masked frames/s"}
+    res["kind"] = "port"
+    res["what"] = ("the reference's torch op sequence (models/autoencoders.py:193-241, masked_pretraining/model.py:78-105, "
+                   "autograd backward) restated in bench.py and run on this B200 through cuBLAS/ATen; TF32 off; eager launches")
+    res["steps"] = steps
+    del x, h, W, b, state
+    torch.cuda.empty_cache()
+    return res
+
+
+class CeChain:
+    """Head operand preparation + fused masked CE forward + backward (+ the data-parallel gradient exchange) on
+    device-resident inputs: BASELINE configs[2] (V = 4096 labels, Dh = 512, 128 frames per line, 15 % masking)."""
+
+    def __init__(self, dev, dp, Nl, T_, Dh, V, p, rank, seed, h_dtype):
+        from pero_pretraining_b200 import ops
+        self.ops, self.dp, self.V, self.Dh = ops, dp, V, Dh
+        g = torch.Generator().manual_seed(seed)
+        bound = 1.0 / np.sqrt(Dh)
+        self.W = ((torch.rand(V, Dh, generator=g) * 2 - 1) * bound).to(dev)
+        self.b = ((torch.rand(V, generator=g) * 2 - 1) * bound).to(dev)
+        gr = torch.Generator().manual_seed(seed + 1000 + rank)
+        self.h = torch.randn(Nl * T_, Dh, generator=gr).to(dev).to(h_dtype)
+        self.labels = torch.randint(0, V, (Nl * T_,), generator=gr).to(dev)
+        mask = (np.random.default_rng(seed + rank).random((Nl, T_)) < p)
+        rows = np.flatnonzero(mask.reshape(-1)).astype(np.int32)
+        self.M = int(rows.size)
+        self.rows = torch.from_numpy(rows).to(dev)
+        self.head = ops.PreparedHead(V, Dh, dev)
+        self.m_global = float(self.M)
+        self.n_grad = V * Dh + V
+        if dp:
+            from pero_pretraining_b200.peer import PeerBuffer, PeerRange
+            t = torch.tensor([float(self.M)], device=dev)
+            torch.distributed.all_reduce(t)
+            self.m_global = float(t.item())
+            self.peer = PeerBuffer(4 * self.n_grad + 1024, dev)
+            self.grad_x = PeerRange(self.peer, self.n_grad + 1, torch.float32)
+
+    def __call__(self):
+        ops = self.ops
+        self.head.prepare(self.W, self.b)
+        if not self.dp:
+            loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, self.labels, self.head)
+            self.out = ops.masked_ce_bwd(self.h, self.rows, self.labels, self.head, lse, None, 1.0 / self.m_global, ws=ws,
+                                         ws_from_fwd=True)
+        else:
+            g = self.grad_x.tensor
+            loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, self.labels, self.head, loss_out=g[self.n_grad:])
+            self.out = ops.masked_ce_bwd(self.h, self.rows, self.labels, self.head, lse, None, 1.0 / self.m_global, ws=ws,
+                                         ws_from_fwd=True, flat_out=g[:self.n_grad], return_flat=True)
+            self.grad_x.all_reduce_sum_()
+        return self.out
+
+
+def configs_legs(dev, dp, rank, world, flush, steps):
+    """BASELINE configs[2..4] measured with the same timing method as the headline workload:
+      c3  masked CE over 4096 labels, Dh 512, 32 lines x 128 frames PER GPU, bf16 hidden states, data parallel (weak)
+      c4  assign + quantize + EMA update, 16384 x 512 codebook, 512 lines x 128 frames in total, batch-sharded (strong)
+      c5  codebook-sharded assign, 65536 x 512 codebook split over the ranks, 2**20 frames on every rank, MIN exchange
+    Every entry: ms per step (device events, L2 flushed, max over ranks), throughput, algorithmic TFLOP/s and the
+    fraction of the measured bf16 peak (burst for the single-kernel c5, sustained for the multi-kernel steps)."""
+    from pero_pretraining_b200 import ShardedCodebook, VectorQuantizer
+    burst, sustained, hbm, src = peaks()
+    out = {}
+    # ---- c3
+    ce = CeChain(dev, dp, 32, 128, 512, 4096, 0.15, rank, 1237, torch.bfloat16)
+    ms, ms_min, launch, graph = timed_loop(ce, steps, 3, flush, dp)
+    fl = 6.0 * ce.m_global * 512 * 4096
+    out["c3"] = {"workload": "configs[2]: masked CE fwd+bwd, V=4096, Dh=512, 32 lines x 128 frames per GPU, 15% masking, bf16 hidden states",
+                 "n_gpus": world, "scaling": "weak", "ms_per_step": ms, "ms_min": ms_min, "masked_frames_per_step": ce.m_global,
+                 "value": ce.m_global / (ms * 1e-3), "unit": "masked frames/s", "tflops": fl / (ms * 1e-3) / 1e12,
+                 "frac_of_sustained": fl / (ms * 1e-3) / 1e12 / sustained / world, "launch": launch,
+                 "note": "4-6 GFLOP per GPU: launch/latency-bound (SURVEY 7), reported as measured"}
+    graph = None
+    del ce
+    # ---- c4
+    K, D, lines, T_ = 16384, 512, 512, 128
+    my_lines = lines // world
+    g = torch.Generator().manual_seed(1238)
+    w0 = torch.randn(K, D, generator=g)
+    gd = torch.Generator(device=dev).manual_seed(1238 + rank)
+    j = torch.randint(0, K, (my_lines * T_,), device=dev, generator=gd)
+    w0d = w0.to(dev)
+    rows = w0d[j] + 0.5 * torch.randn(my_lines * T_, D, device=dev, generator=gd)
+    x = rows.view(my_lines, 1, T_, D).permute(0, 3, 1, 2).contiguous()
+    del rows
+    vq = VectorQuantizer(K, D, 0.25, 0.99).to(dev).train()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(w0d); vq.ema_w.copy_(w0d); vq.ema_cluster_size.fill_(1.0)
+    if dp:
+        vq.enable_data_parallel()
+
+    def c4_step():
+        with torch.no_grad():
+            return vq(x)
+
+    ms, ms_min, launch, graph = timed_loop(c4_step, steps, 3, flush, dp)
+    fl = 2.0 * lines * T_ * K * D
+    out["c4"] = {"workload": "configs[3]: PQ-AE feature quantization: assign + quantize + EMA codebook update, 16384x512 codebook, 512 lines x 128 frames in total",
+                 "n_gpus": world, "scaling": "strong", "ms_per_step": ms, "ms_min": ms_min, "frames_per_step": lines * T_,
+                 "value": lines * T_ / (ms * 1e-3), "unit": "frames/s", "tflops": fl / (ms * 1e-3) / 1e12,
+                 "frac_of_sustained": fl / (ms * 1e-3) / 1e12 / sustained / world, "launch": launch,
+                 "api": "VectorQuantizer.forward (training mode)" + (" + enable_data_parallel()" if dp else "")}
+    graph = None
+    del vq, x, w0d
+    torch.cuda.empty_cache()
+    # ---- c5
+    K, D, N = 65536, 512, 1 << 20
+    gd = torch.Generator(device=dev).manual_seed(1239)            # every rank holds ALL frames: same seed everywhere
+    C = torch.randn(K, D, device=dev, generator=gd)
+    X = torch.randn(N, D, device=dev, generator=gd)
+    sc = ShardedCodebook(C, K, rank, world, peer_frames=N if dp else 0)
+    del C
+
+    def c5_step():
+        return sc.assign(X, N, 1, False)
+
+    ms, ms_min, launch, graph = timed_loop(c5_step, max(3, steps // 4), 2, flush, dp)
+    fl = 2.0 * N * K * D
+    out["c5"] = {"workload": "configs[4]: codebook-sharded stress, 65536x512 codebook, 2**20 frames, (distance,index) MIN exchange",
+                 "n_gpus": world, "scaling": "strong (codebook split over the ranks)", "ms_per_step": ms, "ms_min": ms_min,
+                 "frames_per_step": N, "value": N / (ms * 1e-3), "unit": "frames/s", "tflops": fl / (ms * 1e-3) / 1e12,
+                 "frac_of_burst": fl / (ms * 1e-3) / 1e12 / burst / world, "launch": launch,
+                 "exchange": (f"pero_peer_allreduce_min_i64 ({sc._peer.transport})" if dp else None),
+                 "api": "ShardedCodebook.assign (frame preparation fp32 -> bf16 inside the timed region)"}
+    graph = None
+    del sc, X
+    torch.cuda.empty_cache()
+    return out
+
+
+def roofline_traffic():
+    """DRAM bytes per launch of the distance GEMM from the committed ncu capture (profiles/roofline_traffic.json, written by
+    tools/summarize_profiles.py together with a hash of the kernel's sources).  A capture taken from other sources is
+    not reported: `traffic` is then null instead of a stale number."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed (profiles/roofline_traffic.json)"
+    d = json.load(open(path))
+    hsh = hashlib.sha256()
+    for f in d.get("sources", []):
+        with open(os.path.join(ROOT, f), "rb") as fh:
+            hsh.update(fh.read())
+    if hsh.hexdigest() != d.get("sources_sha256"):
+        return None, f"capture {d.get('capture')} predates the current kernel sources"
+    return d["traffic_bytes"], f"{d.get('capture')}: dram read {d['dram_read_bytes'] / 1e6:.2f} MB + write {d['dram_write_bytes'] / 1e6:.2f} MB per launch"
+
+
 def _log(msg):
     if os.environ.get("PERO_BENCH_VERBOSE"):
         sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} t={time.time() % 1000:.2f}] {msg}\n")
@@ -584,9 +853,11 @@ def our_arm(args):
     burst, sustained, hbm, src = peaks()
     flops = 2.0 * N * c["K"] * c["D"]
     achieved = flops / (gemm_ms * 1e-3) / 1e12
+    traffic, traffic_src = roofline_traffic()
     roofline = {"bound": "tensor", "kernel": "gemm_tn_kernel<2,true,ArgminEpi> (distance GEMM + arg-min)",
                 "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
-                "traffic": 8.52e6, "traffic_source": "profiles/r1_assign_gemm_ncu.md: dram read 8.52 MB + write 0.00 MB per launch (algorithmic 8.49 MB)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": 2.0 * (N * c["D"] + c["K"] * c["D"]) + 4.0 * c["K"] + 8.0 * N,
                 "peak_source": f"{src} bf16 burst (kernel timed alone)", "kernel_us": gemm_ms * 1e3, "kernel_us_min": gemm_min * 1e3,
                 "timing": f"{gemm_sets} launches back to back on {gemm_sets} distinct operand sets (> L2 in total) between two CUDA events, x20",
                 "algorithmic_flops_per_launch": flops,
@@ -599,11 +870,29 @@ def our_arm(args):
         e2e = {"value": m_total / s_per_step, "unit": "masked frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": s_per_step * 1e3, "api": "VectorQuantizer.forward/calculate_loss + LinearHead.masked_loss + backward"}
     _log("e2e leg done")
+    # the step's graph, exchange buffers and streams are no longer needed: free them before the large configs
+    launch_mode = "cuda_graph" if graph is not None else "eager"
+    graph = run = None
+    ds_M, ds_info = ds.M, ((ds.peer.transport, ds.peer.n_blocks, len(ds.v_ranges)) if dp else None)
+    ds = None
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.skip_gpu_baseline:
+        gpu_base = gpu_baseline_leg(batch, dev, flush)
+        gpu_base["ours_over_fp32"] = value / gpu_base["fp32"]["value"]
+        gpu_base["ours_over_bf16_autocast_head"] = value / gpu_base["bf16_autocast_head"]["value"]
+    _log("gpu baseline leg done")
+    configs = None
+    if not args.skip_configs:
+        configs = configs_legs(dev, dp, rank, world, flush, max(5, min(args.steps, 20)))
+    _log("configs legs done")
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         os.sched_setaffinity(0, all_cpus)              # the CPU arm gets every host core again
-        mean_s, min_s = run_cpu(make_batch(0), 3, 1)
-        cpu = {"value": ds.M / mean_s, "unit": "masked frames/s", "cores": torch.get_num_threads(), "kind": "port",
+        mean_s, min_s, _, _ = run_cpu(make_batch(0), 3, 1)
+        cpu = {"value": ds_M / mean_s, "unit": "masked frames/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "3 full-size steps of one 64-line batch after 1 warm-up", "ms_per_step": mean_s * 1e3}
 
     if rank == 0:
@@ -612,20 +901,16 @@ def our_arm(args):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, **{k: c[k] for k in ("lines", "frames", "K", "D", "Dh", "V", "p")},
                            "masked_frames_per_step": m_total, "frames_per_step": N * world, "parallelism": f"dp{world}" if dp else "single",
-                           "exchange": (f"libpero peer all-reduce ({ds.peer.transport}, {ds.peer.n_blocks} CTAs), head backward in "
-                                        f"{len(ds.v_ranges)} label ranges" if dp else None),
-                           "l2": "flushed (256 MiB write) between timed steps", "launch": "cuda_graph" if graph is not None else "eager",
+                           "exchange": (f"libpero peer all-reduce ({ds_info[0]}, {ds_info[1]} CTAs), head backward in "
+                                        f"{ds_info[2]} label ranges" if dp else None),
+                           "l2": "flushed (256 MiB write) between timed steps", "launch": launch_mode,
                            "host_affinity": (f"{len(bound_cpus)} CPUs local to the GPU (NVML)" if bound_cpus else "unchanged")},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_baseline": gpu_base, "configs": configs,
                 "gpu_launches": (n_ours if n_ours > 0 else n_kernels) * args.steps, "kernels_per_step": n_kernels, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if dp:
         # A captured graph that contains NCCL collectives must be gone before the communicator is torn down,
         # and a stuck teardown must not keep the job alive after the result line is out.
-        graph = None
-        ds = None
-        import gc
-        gc.collect()
         torch.cuda.synchronize()
         torch.distributed.barrier()
         sys.stdout.flush()

@@ -9,7 +9,8 @@
  * Conventions
  *   - All pointers are DEVICE pointers unless stated; sizes are int64_t; no torch types.
  *   - The caller owns every buffer including workspaces; the library allocates nothing persistent,
- *     keeps no state between calls and is re-entrant.  All work is enqueued on `stream`; no call
+ *     keeps no mutable state between calls (only per-device memos of immutable facts: SM count, "shared-memory
+ *     attribute already set", and a per-thread memo of encoded TMA descriptors) and is re-entrant.  All work is enqueued on `stream`; no call
  *     synchronises, so sequences of calls are CUDA-graph capturable.
  *   - Return 0 on success; negative = PERO_ERR_* below; positive = a cudaError_t.  Never throws, never
  *     prints.  pero_strerror() names any code.
@@ -232,11 +233,17 @@ int pero_mask_compact(const void* mask, int mask_dtype, int want_value, const in
  * multimem.st) or NULL (peer loads summed in rank order + peer stores).  One kernel per call, n_blocks CTAs
  * (1..PERO_PEER_MAX_BLOCKS; 16-32 saturate NVLink and leave the other SMs to the GEMMs running beside it);
  * all ranks must issue the same sequence of calls with the same n_blocks.  n_elems % 4 == 0 (f32) / % 2 == 0 (i64).
- * A rank that does not arrive within 30 s makes the waiting kernels trap (sticky CUDA error) instead of hanging.
+ * Header words the CALLER may touch (all others belong to the library): the u32 at PERO_PEER_TIMEOUT_OFFSET is the
+ * barrier timeout in milliseconds (0 = the default, 600 000 ms = NCCL's watchdog); the u32 at PERO_PEER_ERROR_OFFSET is
+ * set non-zero by a kernel whose peer did not arrive in time — that kernel returns WITHOUT trapping (the CUDA context
+ * stays usable) and leaves the payload unreduced, so a caller that cannot rule out stragglers reads the word back
+ * (peer.PeerBuffer.check()).  Ranks that do rank-local long work between steps should barrier on the host first.
  * pero_peer_allreduce_emulate: the same protocol with all `world` buffers on ONE device and the ranks played
  * by blockIdx.y of one cooperative launch (op 0 = f32 sum, 1 = i64 min) — single-GPU test of the protocol only.
  */
 #define PERO_PEER_HEADER_BYTES 16384
+#define PERO_PEER_TIMEOUT_OFFSET 12288
+#define PERO_PEER_ERROR_OFFSET 12292
 #define PERO_PEER_MAX_WORLD 16
 #define PERO_PEER_MAX_BLOCKS 64
 int pero_peer_allreduce_sum_f32(void* const* peer_bufs, void* multicast_base, int rank, int world, int64_t offset_bytes,
@@ -246,15 +253,21 @@ int pero_peer_allreduce_min_i64(void* const* peer_bufs, void* multicast_base, in
 int pero_peer_allreduce_emulate(void* const* bufs_on_one_device, int world, int op, int64_t offset_bytes, int64_t n_elems,
                                 int n_blocks, pero_stream_t stream);
 
-/* ------------------------------------------------------------------ test hook
- * C[rows_a, rows_b] = A @ B^T through the same tcgen05 core (bf16 operands with row pitch `kd`,
- * fp32 out).  variant: bit0 = CTA pairs (cta_group::2), bit1 = resident A.  Used by tests only. */
-/* Debug only: the next `slots` GEMM launches each write clock64 stamps of their worker 0 into the next 64 KiB
- * (8192 u64) slot of device_buffer, later launches none; NULL switches it off.  Slot layout
- * ([unit][8] u64: mma_top, mma_tempty_ok, mma_first_full, mma_issued, epi_tfull_ok, epi_done, prod_first, prod_last). */
+/* ------------------------------------------------------------------ the GEMM core on its own (parity-test entry)
+ * C[rows_a, rows_b] = A @ B^T through the same tcgen05 core every contraction of the path uses (bf16 operands with row
+ * pitch `kd`, fp32 out [num_splits, rows_a, rows_b], one plane per contraction split).  variant: bit0 = CTA pairs
+ * (cta_group::2), bit1 = resident A, bit5 = MN-major operands (A stored [kd, rows_a], B [kd, rows_b], C = A^T B).
+ * tests/test_gpu_assign.py checks it against an fp64 matmul; nothing on the product path calls it. */
+int pero_gemm_tn_bf16(const void* a_bf16, int64_t rows_a, const void* b_bf16, int64_t rows_b, int64_t kd,
+                      int variant, int num_splits, float* out, pero_stream_t stream);
+
+#ifdef PERO_DEV_BUILD
+/* Dev build only (make DEV=1; not part of the production export table).  The next `slots` GEMM launches each write
+ * clock64 stamps of their worker 0 into the next 64 KiB (8192 u64) slot of device_buffer, later launches none; NULL
+ * switches it off.  Slot layout ([unit][8] u64: mma_top, mma_tempty_ok, mma_first_full, mma_issued, epi_tfull_ok,
+ * epi_done, prod_first, prod_last).  The dev build also honours the PERO_* tuning knobs listed in csrc/knobs.h. */
 int pero_debug_set_timeline(void* device_buffer, int slots);
-int pero_debug_gemm_tn(const void* a_bf16, int64_t rows_a, const void* b_bf16, int64_t rows_b, int64_t kd,
-                       int variant, int num_splits, float* out, pero_stream_t stream);
+#endif
 
 #ifdef __cplusplus
 }

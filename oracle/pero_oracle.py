@@ -132,6 +132,34 @@ def assign_fp64(flat, weight, chunk=4096):
     return idx, dmin, gap
 
 
+def assign_fp64_torch(flat, weight, chunk=2048):
+    """The same fp64 brute force as assign_fp64, stated in torch ops so that the TEST may run it on whatever
+    device the tensors live on (a B200 does the 8192 x 8192 x 256 case in milliseconds, which is what lets the
+    near-tie rule be applied at the BASELINE sizes; models/autoencoders.py:212-217 in fp64).  Returns torch tensors
+    (idx int64, d_min fp64, relative top-2 gap fp64) on flat's device.  Ties: lowest index, like torch.argmin."""
+    x = flat.double()
+    c = weight.double()
+    cn = (c * c).sum(1)
+    N, K = x.shape[0], c.shape[0]
+    idx = torch.empty(N, dtype=torch.int64, device=x.device)
+    dmin = torch.empty(N, dtype=torch.float64, device=x.device)
+    gap = torch.empty(N, dtype=torch.float64, device=x.device)
+    for s in range(0, N, chunk):
+        xs = x[s:s + chunk]
+        d = (xs * xs).sum(1, keepdim=True) + cn[None, :] - 2.0 * (xs @ c.t())
+        i0 = torch.argmin(d, dim=1)                             # first minimal index
+        d0 = d.gather(1, i0[:, None]).squeeze(1)
+        if K > 1:
+            d.scatter_(1, i0[:, None], float("inf"))
+            d1 = d.min(dim=1).values
+        else:
+            d1 = torch.full_like(d0, float("inf"))
+        idx[s:s + chunk] = i0
+        dmin[s:s + chunk] = d0
+        gap[s:s + chunk] = (d1 - d0) / d0.abs().clamp_min(1e-30)
+    return idx, dmin, gap
+
+
 # ------------------------------------------------------------------------------------------ masked CE
 def linear_head(x, W, b):
     """LinearHead.forward.  masked_pretraining/model.py:104-105."""

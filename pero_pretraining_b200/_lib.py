@@ -63,8 +63,11 @@ SIGNATURES = {
     "pero_peer_allreduce_sum_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "pero_peer_allreduce_min_i64": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "pero_peer_allreduce_emulate": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
+    "pero_gemm_tn_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
+}
+# present only in a dev build of the library (make DEV=1): bound when the symbol exists
+DEV_SIGNATURES = {
     "pero_debug_set_timeline": (c_int, [c_vp, c_int]),
-    "pero_debug_gemm_tn": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
 }
 
 
@@ -75,9 +78,10 @@ class PeroError(RuntimeError):
 _lib = None
 
 
-def build(verbose=False):
-    """Compile libpero_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    res = subprocess.run(["make", "-C", CSRC_DIR, "-j", "8"], capture_output=True, text=True)
+def build(verbose=False, dev=False):
+    """Compile libpero_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+    dev=True: the measurement build (make DEV=1: PERO_* environment knobs and timeline hooks compiled in)."""
+    res = subprocess.run(["make", "-C", CSRC_DIR, "-j", "8"] + (["DEV=1"] if dev else []), capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout[-4000:])
         print(res.stderr[-4000:])
@@ -99,6 +103,11 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
+        for name, (res, args) in DEV_SIGNATURES.items():
+            fn = getattr(handle, name, None)
+            if fn is not None:
+                fn.restype = res
+                fn.argtypes = args
         _lib = handle
     return _lib
 

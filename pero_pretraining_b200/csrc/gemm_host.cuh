@@ -4,6 +4,8 @@
 #pragma once
 #include "gemm_core.cuh"
 #include "errors.h"
+#include "knobs.h"
+#include <atomic>
 #include <stdlib.h>
 
 namespace pero {
@@ -70,21 +72,43 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
     return PERO_OK;
 }
 
-inline int device_sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
 
-// Debug only (pero_debug_set_timeline): while slots remain, every GEMM launch records worker 0's clock64 stamps
+// Memo of an immutable device property (per device; racing first calls store the same value).
+inline int device_sm_count() {
+    static std::atomic<int> sms[kMaxDevices];
+    const int dev = current_device();
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+        sms[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device, idempotent setting: it is applied once per
+// (kernel, device) and remembered in a per-kernel table of atomics (thread-safe; no other global state).
+template <class Kernel>
+inline cudaError_t ensure_max_dynamic_smem(Kernel kern, std::atomic<bool>* done_per_device, size_t bytes) {
+    const int dev = current_device();
+    if (done_per_device[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done_per_device[dev].store(true, std::memory_order_release);
+    return e;
+}
+
+#ifdef PERO_DEV_BUILD
+// Dev build only (pero_debug_set_timeline): while slots remain, every GEMM launch records worker 0's clock64 stamps
 // in the next 64 KiB slot of the caller's buffer; once the slots are used up, launches run without stamps.
 inline unsigned long long* g_debug_timeline = nullptr;
 inline int g_debug_timeline_slots = 0;
+#endif
 
 constexpr size_t kSmemBudget = 227 * 1024;
 // Budget for GEMMs that run beside other chains of the step (masked CE): leaves ~27 KB of shared memory and, with
@@ -111,11 +135,13 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
     GemmShape sh;
     sh.timeline = timeline;
+#ifdef PERO_DEV_BUILD
     if (!timeline && g_debug_timeline && g_debug_timeline_slots > 0) {     // debug: one 64 KiB slot per GEMM launch
         sh.timeline = g_debug_timeline;
         g_debug_timeline += 8192;
         --g_debug_timeline_slots;
     }
+#endif
     sh.rows_a = rows_a; sh.rows_b = rows_b;
     sh.num_kb = kd / kBlockK;
     sh.num_rb = (rows_a + kBlockM * kCtaGroup - 1) / (kBlockM * kCtaGroup);
@@ -124,11 +150,7 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     sh.kb_per_split = (sh.num_kb + sh.num_ks - 1) / sh.num_ks;
     sh.num_ks = (sh.num_kb + sh.kb_per_split - 1) / sh.kb_per_split;   // no empty splits
     sh.split_mode = split_mode; sh.fixed_s = fixed_s < 1 ? 1 : fixed_s;
-    {
-        static int pdl_off = -1;       // PERO_PDL=0: no programmatic dependent launches at all (diagnostic knob)
-        if (pdl_off < 0) { const char* e = getenv("PERO_PDL"); pdl_off = (e && atoi(e) == 0) ? 1 : 0; }
-        if (pdl_off) pdl = 0;
-    }
+    if (PERO_KNOB("PERO_PDL", 1) == 0) pdl = 0;       // dev build: no programmatic dependent launches at all
     sh.pdl = pdl;
     if (kAResident && (sh.num_ks != 1 || sh.num_kb > kMaxAKb)) return PERO_ERR_BAD_SHAPE;
     sh.num_stages = pick_stages(kCtaGroup, kAResident, sh.num_kb, Epi::kScratchPerWarp, smem_budget);
@@ -151,9 +173,8 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     const long long units = (long long)sh.num_rb * sh.num_ct * sh.num_ks;
     int max_workers = device_sm_count() / kCtaGroup;
     {
-        static int env_cap = -2;       // PERO_GEMM_MAX_CTAS: tuning knob for the co-residency experiments
-        if (env_cap == -2) { const char* e = getenv("PERO_GEMM_MAX_CTAS"); env_cap = e ? atoi(e) : -1; }
-        if (env_cap > 0 && env_cap / kCtaGroup < max_workers) max_workers = env_cap / kCtaGroup;
+        const int cap = PERO_KNOB("PERO_GEMM_MAX_CTAS", -1);      // dev build: co-residency experiments
+        if (cap > 0 && cap / kCtaGroup < max_workers) max_workers = cap / kCtaGroup;
     }
     if (split_mode == 1) workers = sh.num_rb * sh.fixed_s;
     else if (workers <= 0 || workers > max_workers) workers = max_workers;
@@ -162,11 +183,10 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     size_t smem = gemm_smem_bytes(kCtaGroup, kAResident, sh.num_kb, sh.num_stages, Epi::kScratchPerWarp);
     if (smem < kSmemFloor) smem = kSmemFloor;
     auto kern = gemm_tn_kernel<kCtaGroup, kAResident, Epi, kMnMajor>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    {
+        static std::atomic<bool> attr_done[kMaxDevices];
+        cudaError_t e = ensure_max_dynamic_smem(kern, attr_done, kSmemBudget);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(workers * kCtaGroup));

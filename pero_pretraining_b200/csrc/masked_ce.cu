@@ -770,15 +770,13 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + l.p_off);
     float* dbpart = reinterpret_cast<float*>(ws + l.dbpart_off);
     const int db_nparts = (int)((M + kDbRows - 1) / kDbRows);
-    static int store_pairs = -1;     // PERO_CE_STORE_PAIRS=0: gradient GEMMs on single CTAs (tuning knob)
-    if (store_pairs < 0) { const char* e = getenv("PERO_CE_STORE_PAIRS"); store_pairs = e ? atoi(e) : 1; }
+    const int store_pairs = PERO_KNOB("PERO_CE_STORE_PAIRS", 1);     // dev build, 0: gradient GEMMs on single CTAs
     // When one call produces both gradients, the d_W and d_h GEMMs each get half of the SM pairs and run side by
     // side, with the d_b column sums filling in beside them: none of the three reads another's output, so each
     // kernel releases its successor at once (programmatic dependent launch) and every successor, before it exits,
     // waits for its predecessor, so that stream order still implies "all three are done".  Each GEMM CTA then walks
     // two tiles, and the store of one overlaps the loads of the next.
-    static int pdl_on = -1;          // PERO_CE_PDL=0: the two gradient GEMMs run one after the other
-    if (pdl_on < 0) { const char* e = getenv("PERO_CE_PDL"); pdl_on = e ? atoi(e) : 1; }
+    const int pdl_on = PERO_KNOB("PERO_CE_PDL", 1);                  // dev build, 0: the gradient GEMMs run one after the other
     const bool side_by_side = pdl_on && store_pairs && !dh_only && d_h != nullptr && full_range;
     const int half_workers = device_sm_count() / 4;
     if (!dh_only) {

@@ -21,15 +21,23 @@
 #include <stdlib.h>
 
 #include "../../include/pero_b200.h"
+#include "knobs.h"
 
 namespace {
 
 constexpr int kMaxThreads = 512;
 constexpr int kMaxWorld = PERO_PEER_MAX_WORLD;
 constexpr int kMaxBlocks = PERO_PEER_MAX_BLOCKS;
-constexpr unsigned long long kTimeoutNs = 30000000000ull;   // 30 s: ranks may reach their first exchange seconds apart
-                                                            // (lazy module loading, profiler start-up), never minutes
-static_assert(kMaxWorld * kMaxBlocks * 4 <= 8192 && 8192 + kMaxBlocks * 4 <= PERO_PEER_HEADER_BYTES, "flag words must fit the buffer header");
+// Barrier timeout.  Ranks may reach an exchange minutes apart (a checkpoint or an evaluation on one rank, a data-loader
+// stall, lazy module loading), so the default matches NCCL's watchdog: 10 minutes.  The caller may store another value
+// (milliseconds, u32) in the TIMEOUT word of its own buffer header.  On a timeout the kernel does NOT trap (a trap
+// is a sticky error that kills the CUDA context of every waiting rank): it stores a non-zero code in the local ERROR
+// word and returns without touching the payload again; the host reads that word (peer.PeerBuffer.check()).
+constexpr unsigned long long kDefaultTimeoutMs = 600000ull;
+constexpr int kTimeoutOffsetWords = PERO_PEER_TIMEOUT_OFFSET / 4;
+constexpr int kErrorOffsetWords = PERO_PEER_ERROR_OFFSET / 4;
+static_assert(kMaxWorld * kMaxBlocks * 4 <= 8192 && 8192 + kMaxBlocks * 4 <= PERO_PEER_TIMEOUT_OFFSET &&
+              PERO_PEER_ERROR_OFFSET + 4 <= PERO_PEER_HEADER_BYTES, "flag words must fit the buffer header");
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -74,20 +82,32 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
 //             read was written by earlier kernels of this stream and is already in this GPU's L2 — so a relaxed
 //             store suffices there.
 //   kConsume: the block goes on to read peers' data (opening barrier): one acquire load after the poll.
+// Returns false (for every thread of the block) when a peer did not arrive in time.
 template <bool kPublish, bool kConsume>
-__device__ __forceinline__ void rank_barrier(void* const* bufs, int rank, int world, int blk, uint32_t target) {
+__device__ __forceinline__ bool rank_barrier(void* const* bufs, int rank, int world, int blk, uint32_t target) {
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
     __syncthreads();
     const int t = threadIdx.x;
     if (t < world) {
         uint32_t* theirs = arrival_word(bufs[t], blk, rank);
         if (kPublish) st_release_sys(theirs, target); else st_relaxed_sys(theirs, target);
         const uint32_t* mine = arrival_word(bufs[rank], blk, t);
+        const uint32_t* hdr = reinterpret_cast<const uint32_t*>(bufs[rank]);
+        const unsigned long long ms = hdr[kTimeoutOffsetWords] ? hdr[kTimeoutOffsetWords] : kDefaultTimeoutMs;
         const unsigned long long t0 = now_ns();
-        while ((int32_t)(ld_relaxed_sys(mine) - target) < 0)
-            if (now_ns() - t0 > kTimeoutNs) __trap();
+        unsigned spins = 0;
+        while ((int32_t)(ld_relaxed_sys(mine) - target) < 0) {
+            if ((++spins & 1023u) == 0 && now_ns() - t0 > ms * 1000000ull) {
+                reinterpret_cast<uint32_t*>(bufs[rank])[kErrorOffsetWords] = 0x80000000u | ((uint32_t)blk << 8) | (uint32_t)t;
+                atomicExch(&timed_out, 1);
+                break;
+            }
+        }
         if (kConsume) (void)ld_acquire_sys(mine);
     }
     __syncthreads();
+    return timed_out == 0;
 }
 
 // Epoch of this launch for the block (read before the first barrier, advanced after the second).
@@ -168,7 +188,7 @@ __global__ void __launch_bounds__(kMaxThreads) peer_allreduce_kernel(void* const
     const int world = kWorld > 0 ? kWorld : world_arg;
     const int rank = kEmulate ? (int)blockIdx.y : rank_arg;
     const uint32_t epoch = begin_collective(bufs, rank, blockIdx.x);
-    rank_barrier<false, true>(bufs, rank, world, blockIdx.x, epoch + 1);
+    if (!rank_barrier<false, true>(bufs, rank, world, blockIdx.x, epoch + 1)) return;
     const Range r = slice_of(nvec, world, rank);
     constexpr int U = kWorld == 2 ? 4 : (kWorld == 8 ? 1 : 2);
     const int kThreads = blockDim.x;
@@ -212,7 +232,7 @@ __global__ void __launch_bounds__(kMaxThreads) peer_allreduce_kernel(void* const
             }
         }
     }
-    rank_barrier<true, false>(bufs, rank, world, blockIdx.x, epoch + 2);
+    if (!rank_barrier<true, false>(bufs, rank, world, blockIdx.x, epoch + 2)) return;
     end_collective(bufs, rank, blockIdx.x, epoch);
 }
 
@@ -220,7 +240,7 @@ __global__ void __launch_bounds__(kMaxThreads) peer_allreduce_kernel(void* const
 __global__ void __launch_bounds__(kMaxThreads) mc_allreduce_sum_f32_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
                                                                         int world, int64_t off_bytes, int64_t nvec) {
     const uint32_t epoch = begin_collective(bufs, rank, blockIdx.x);
-    rank_barrier<false, true>(bufs, rank, world, blockIdx.x, epoch + 1);
+    if (!rank_barrier<false, true>(bufs, rank, world, blockIdx.x, epoch + 1)) return;
     const Range r = slice_of(nvec, world, rank);
     constexpr int U = 8;
     const int kThreads = blockDim.x;
@@ -239,14 +259,14 @@ __global__ void __launch_bounds__(kMaxThreads) mc_allreduce_sum_f32_kernel(void*
             if (i < r.hi) mc_st(base_ptr + i * 16, v[u]);
         }
     }
-    rank_barrier<true, false>(bufs, rank, world, blockIdx.x, epoch + 2);
+    if (!rank_barrier<true, false>(bufs, rank, world, blockIdx.x, epoch + 2)) return;
     end_collective(bufs, rank, blockIdx.x, epoch);
 }
 
 __global__ void __launch_bounds__(kMaxThreads) mc_allreduce_min_i64_kernel(void* const* __restrict__ bufs, char* __restrict__ mc, int rank,
                                                                         int world, int64_t off_bytes, int64_t n) {
     const uint32_t epoch = begin_collective(bufs, rank, blockIdx.x);
-    rank_barrier<false, true>(bufs, rank, world, blockIdx.x, epoch + 1);
+    if (!rank_barrier<false, true>(bufs, rank, world, blockIdx.x, epoch + 1)) return;
     const Range r = slice_of(n, world, rank);
     constexpr int U = 8;
     const int kThreads = blockDim.x;
@@ -265,7 +285,7 @@ __global__ void __launch_bounds__(kMaxThreads) mc_allreduce_min_i64_kernel(void*
             if (i < r.hi) mc_st(base_ptr + i * 8, v[u]);
         }
     }
-    rank_barrier<true, false>(bufs, rank, world, blockIdx.x, epoch + 2);
+    if (!rank_barrier<true, false>(bufs, rank, world, blockIdx.x, epoch + 2)) return;
     end_collective(bufs, rank, blockIdx.x, epoch);
 }
 
@@ -280,15 +300,10 @@ int check_args(void* const* peer_bufs, int rank, int world, int64_t off_bytes, i
 // CTA size of the exchange kernels.  Small CTAs (few registers, no shared memory) slot in beside the resident
 // GEMM CTAs instead of waiting for a whole SM; PERO_PEER_THREADS is a tuning knob.
 int peer_threads() {
-    static int t = 0;
-    if (!t) {
-        const char* e = getenv("PERO_PEER_THREADS");
-        t = e ? atoi(e) : 256;
-        if (t < 32) t = 32;
-        if (t > kMaxThreads) t = kMaxThreads;
-        t = t / 32 * 32;
-    }
-    return t;
+    int t = PERO_KNOB("PERO_PEER_THREADS", 256);      // dev build only
+    if (t < 32) t = 32;
+    if (t > kMaxThreads) t = kMaxThreads;
+    return t / 32 * 32;
 }
 
 template <class Op, bool kEmulate>

@@ -106,8 +106,7 @@ __global__ void unpack_kernel(const long long* __restrict__ packed, long long N,
 
 // bit0: CTA pairs (cta_group::2); bit1: resident A row block.  PERO_ASSIGN_VARIANT overrides.
 int assign_variant_default(int num_kb) {
-    static int env = -2;
-    if (env == -2) { const char* e = getenv("PERO_ASSIGN_VARIANT"); env = e ? atoi(e) : -1; }
+    const int env = PERO_KNOB("PERO_ASSIGN_VARIANT", -1);       // dev build only
     int v = env >= 0 ? env : 3;
     if (num_kb > 8) v &= ~2;   // resident A beyond D = 512 leaves no room for the B ring
     return v;
@@ -239,18 +238,21 @@ int pero_vq_assign_bf16(const void* x_bf16, int64_t N, int64_t K, int64_t D, con
                            reinterpret_cast<long long*>(packed_io), (cudaStream_t)stream);
 }
 
+#ifdef PERO_DEV_BUILD
 int pero_debug_set_timeline(void* device_buffer, int slots) {
     g_debug_timeline = static_cast<unsigned long long*>(device_buffer);
     g_debug_timeline_slots = device_buffer ? (slots > 0 ? slots : 0) : 0;
     return PERO_OK;
 }
+#endif
 
-int pero_debug_gemm_tn(const void* a_bf16, int64_t rows_a, const void* b_bf16, int64_t rows_b, int64_t kd,
+int pero_gemm_tn_bf16(const void* a_bf16, int64_t rows_a, const void* b_bf16, int64_t rows_b, int64_t kd,
                        int variant, int num_splits, float* out, pero_stream_t stream) {
     if (!a_bf16 || !b_bf16 || !out) return PERO_ERR_NULL;
     StoreEpi::Params ep;
     ep.out = out; ep.ld = rows_b; ep.split_stride = rows_a * rows_b; ep.rows = (int)rows_a; ep.cols = (int)rows_b;
     const int ra = (int)rows_a, rb = (int)rows_b, k = (int)kd;
+#ifdef PERO_DEV_BUILD
     if (variant & 16) {          // timeline: `out` receives clock64 stamps [unit][8] of worker 0 (u64)
         NullEpi::Params np; np.out = nullptr;
         unsigned long long* tl = reinterpret_cast<unsigned long long*>(out);
@@ -275,6 +277,9 @@ int pero_debug_gemm_tn(const void* a_bf16, int64_t rows_a, const void* b_bf16, i
         if (res) return launch_gemm_tn<1, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
         return launch_gemm_tn<1, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
     }
+#else
+    if (variant & (4 | 8 | 16)) return PERO_ERR_UNSUPPORTED;      // measurement variants exist in the dev build only
+#endif
     if (variant & 32) {          // MN-major operands: a is [kd, rows_a], b is [kd, rows_b]; out = a^T b
         const int kp = (k + 63) / 64 * 64;
         if (variant & 1)

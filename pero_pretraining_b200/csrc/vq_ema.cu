@@ -17,6 +17,8 @@
 #include <math_constants.h>
 #include "../../include/pero_b200.h"
 #include "layout.h"
+#include "knobs.h"
+#include <atomic>
 
 namespace pero {
 
@@ -462,16 +464,20 @@ int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, i
     float* sums = sums_counts;
     float* counts = sums_counts + (size_t)K * D;
 
-    static int bin_sort = -1;      // PERO_EMA_BIN_SORT=0: radix sort also for the small case (tuning / cross-check knob)
-    if (bin_sort < 0) { const char* e = getenv("PERO_EMA_BIN_SORT"); bin_sort = e ? atoi(e) : 1; }
+    const int bin_sort = PERO_KNOB("PERO_EMA_BIN_SORT", 1);     // dev build, 0: radix sort also for the small case
     if (bin_sort && N <= kBinSortThreads * kBinSortItems && K <= kBinSortMaxK) {
         const size_t smem = ((size_t)2 * K + kBinSortThreads * kBinSortItems) * 4;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(ema_bin_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(((size_t)2 * kBinSortMaxK + kBinSortThreads * kBinSortItems) * 4));
-            if (e != cudaSuccess) return (int)e;
-            attr_set = true;
+        {
+            static std::atomic<bool> attr_done[64];
+            int dev = 0;
+            cudaGetDevice(&dev);
+            dev = (dev >= 0 && dev < 64) ? dev : 0;
+            if (!attr_done[dev].load(std::memory_order_acquire)) {
+                cudaError_t e = cudaFuncSetAttribute(ema_bin_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)(((size_t)2 * kBinSortMaxK + kBinSortThreads * kBinSortItems) * 4));
+                if (e != cudaSuccess) return (int)e;
+                attr_done[dev].store(true, std::memory_order_release);
+            }
         }
         ema_bin_small_kernel<<<1, kBinSortThreads, smem, stream>>>(reinterpret_cast<const long long*>(idx), (int)N, (int)K, keys_out,
                                                                   vals_out, seg);

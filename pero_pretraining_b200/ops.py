@@ -334,6 +334,6 @@ def debug_gemm_tn(a_bf16, b_bf16, variant=0, splits=1):
     ra, kd = a_bf16.shape
     rb = b_bf16.shape[0]
     out = torch.zeros(max(splits, 1), ra, rb, dtype=torch.float32, device=a_bf16.device)
-    check(_lib.lib().pero_debug_gemm_tn(a_bf16.data_ptr(), ra, b_bf16.data_ptr(), rb, kd, int(variant), int(splits),
-                                        out.data_ptr(), _stream()), "pero_debug_gemm_tn")
+    check(_lib.lib().pero_gemm_tn_bf16(a_bf16.data_ptr(), ra, b_bf16.data_ptr(), rb, kd, int(variant), int(splits),
+                                        out.data_ptr(), _stream()), "pero_gemm_tn_bf16")
     return out

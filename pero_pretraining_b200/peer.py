@@ -15,6 +15,8 @@ from . import _lib
 from ._lib import check
 
 HEADER_BYTES = 16384          # PERO_PEER_HEADER_BYTES
+TIMEOUT_OFFSET = 12288        # PERO_PEER_TIMEOUT_OFFSET: u32 milliseconds, 0 = default (600 s, NCCL's watchdog)
+ERROR_OFFSET = 12292          # PERO_PEER_ERROR_OFFSET: non-zero after a barrier timed out
 DEFAULT_BLOCKS = 24
 
 
@@ -26,8 +28,10 @@ class PeerBuffer:
     """[header flags | payload] symmetric buffer.  ``carve(nbytes)`` hands out 256-byte aligned payload ranges
     (same sequence of carves on every rank -> same offsets everywhere)."""
 
-    def __init__(self, payload_bytes, device, group=None, n_blocks=DEFAULT_BLOCKS, use_multicast=None):
-        """use_multicast: None = switch-side reduction whenever the group has a multicast object, True / False to
+    def __init__(self, payload_bytes, device, group=None, n_blocks=DEFAULT_BLOCKS, use_multicast=None, timeout_s=None):
+        """timeout_s: how long an exchange kernel waits for a late rank (default 600 s, like NCCL's watchdog).  A kernel
+        that gives up does not trap: it flags the buffer (see check()) and leaves the range unreduced.
+        use_multicast: None = switch-side reduction whenever the group has a multicast object, True / False to
         force.  Per-direction link traffic for a payload S: multimem 1.5 S at 2 ranks, 1.125 S at 8; peer pointers
         1.0 S at 2 ranks, 1.75 S at 8 — but the multimem kernel needs far fewer threads to keep the links busy
         (it is the switch that fans out), which matters beside the GEMMs it overlaps with."""
@@ -40,6 +44,8 @@ class PeerBuffer:
         self.storage = symm_mem.empty(self.total, dtype=torch.uint8, device=self.device)
         self.handle = symm_mem.rendezvous(self.storage, self.group)
         self.storage.zero_()
+        if timeout_s is not None:
+            self.storage[TIMEOUT_OFFSET:TIMEOUT_OFFSET + 4].view(torch.int32).fill_(max(1, int(timeout_s * 1000)))
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)       # every rank's flag words are zero before any kernel touches them
         self.rank, self.world = int(self.handle.rank), int(self.handle.world_size)
@@ -50,6 +56,13 @@ class PeerBuffer:
         self.multicast = mc if mc != 0 else None
         self.n_blocks = int(n_blocks)
         self._next = HEADER_BYTES
+
+    def check(self):
+        """Raise if an exchange kernel of this rank ever gave up waiting for a peer (synchronises the device)."""
+        code = int(self.storage[ERROR_OFFSET:ERROR_OFFSET + 4].view(torch.int32).item())
+        if code != 0:
+            raise _lib.PeroError(f"peer exchange timed out waiting for rank {code & 0xff} (block {(code >> 8) & 0xff}); "
+                                 "the last exchanged ranges are not reduced")
 
     @property
     def transport(self):

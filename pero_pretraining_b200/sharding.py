@@ -81,5 +81,6 @@ class ShardedCodebook:
             return ops.vq_unpack(packed[:N], want_dmin)
         packed = ops.vq_packed_init(N, x.device)
         ops.vq_assign(x, self.codebook, n_lines, frames_per_line, channels_first, index_offset=self.k_lo, packed=packed)
-        merge_packed(packed, self.group)
+        if self.world_size > 1:
+            merge_packed(packed, self.group)
         return ops.vq_unpack(packed, want_dmin)

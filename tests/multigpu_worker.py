@@ -49,7 +49,9 @@ def check_peer_allreduce(dev, rank, world):
         for r in range(1, world):
             want = want + vals[r]
         want_min = torch.stack(ints).min(0).values
-        for rep in range(3):
+        first_bits = None
+        stable = True
+        for rep in range(6):
             rng_f.tensor.copy_(vals[rank])
             rng_i.tensor.copy_(ints[rank])
             rng_f.all_reduce_sum_()
@@ -63,6 +65,17 @@ def check_peer_allreduce(dev, rank, world):
             assert torch.equal(rng_i.tensor.cpu(), want_min), f"min rep {rep}"
             copies = gather_bytes(rng_f.tensor)
             assert all(torch.equal(copies[0], c) for c in copies[1:]), "replicas differ"
+            # run-to-run determinism of the SUM (north_star: "deterministic"): the peer-pointer transport adds in rank
+            # order and must repeat bit for bit; for the switch-side reduction PTX leaves the order to the switch, so
+            # the observation is reported (DESIGN.md section 5 states the outcome and the deterministic mode)
+            if first_bits is None:
+                first_bits = got.clone()
+            elif not torch.equal(first_bits, got):
+                stable = False
+        if buf.multicast:
+            log(f"  multimem SUM bit-identical over 6 repeats: {stable}")
+        else:
+            assert stable, "peer-pointer SUM must be bit-identical run to run"
         # CUDA-graph replay of produce -> exchange
         src = vals[rank].to(dev)
         side = torch.cuda.Stream()

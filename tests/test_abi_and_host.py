@@ -12,9 +12,16 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
+def _declared_symbols(dev_only=False):
+    """Functions declared in the header; the `#ifdef PERO_DEV_BUILD` block (measurement hooks that the production
+    library does not export) is returned separately."""
     text = open(os.path.join(ROOT, "include", "pero_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    dev_blocks = re.findall(r"#ifdef PERO_DEV_BUILD(.*?)#endif", text, flags=re.S)
+    if dev_only:
+        text = "\n".join(dev_blocks)
+    else:
+        text = re.sub(r"#ifdef PERO_DEV_BUILD.*?#endif", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(pero_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -34,6 +41,14 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [s for s in declared if not hasattr(raw, s)]
     assert not missing, f"declared in include/pero_b200.h but not exported: {missing}"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes signatures must mirror the header one to one"
+    dev = _declared_symbols(dev_only=True)
+    assert sorted(_lib.DEV_SIGNATURES) == dev and dev
+    exported_dev = [s for s in dev if hasattr(raw, s)]
+    # production build (what __graft_entry__.build() makes): no measurement hooks, no environment knobs
+    assert exported_dev in ([], dev), "either a production build (no dev symbols) or a full dev build"
+    if not exported_dev:
+        blob = open(_lib.LIB_PATH, "rb").read()
+        assert b"PERO_GEMM_MAX_CTAS" not in blob and b"PERO_PDL" not in blob, "production build must not read tuning knobs"
 
 
 def test_version_strerror_and_size_queries(lib):

@@ -49,8 +49,8 @@ def test_gemm_core_mn_major_operands(cuda_dev, pairs, shape):
     b = torch.randn(kd, rb, generator=g).to(cuda_dev).bfloat16()
     out = torch.zeros(1, ra, rb, dtype=torch.float32, device=cuda_dev)
     from pero_pretraining_b200 import _lib
-    _lib.check(_lib.lib().pero_debug_gemm_tn(a.data_ptr(), ra, b.data_ptr(), rb, kd, 32 + pairs, 1, out.data_ptr(),
-                                             torch.cuda.current_stream().cuda_stream), "pero_debug_gemm_tn")
+    _lib.check(_lib.lib().pero_gemm_tn_bf16(a.data_ptr(), ra, b.data_ptr(), rb, kd, 32 + pairs, 1, out.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "pero_gemm_tn_bf16")
     ref = a.double().t() @ b.double()
     assert (out[0].double() - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
 
@@ -80,7 +80,7 @@ def _assign_vs_oracle(ops, x_rows, w, channels_first_x=None, n_lines=None, frame
     got = idx.cpu().numpy()
     differs = got != ref_idx
     assert (gap[differs] < EPS_TIE).all(), f"{differs.sum()} flips, worst gap {gap[differs].max():.3e}"
-    assert differs.mean() < 0.02
+    assert differs.mean() < 0.01
     # dmin is the squared distance minus |x|^2, evaluated on bf16-rounded operands
     xn = (x_rows.double() ** 2).sum(1).cpu().numpy()
     np.testing.assert_allclose(dmin.cpu().numpy()[~differs] + xn[~differs], ref_dmin[~differs],
@@ -162,6 +162,95 @@ def test_assign_fixed_point_and_full_size_properties(cuda_dev):
     assert (idx4 == j).float().mean().item() > 0.999
     d = ((X.double() - C4[idx4].double()) ** 2).sum(1) - (X.double() ** 2).sum(1)
     assert (dmin4.double() - d).abs().max().item() < 2e-2 * d.abs().max().item()
+
+
+def _near_tie_check(idx, x_rows, w, sample=None, seed=0):
+    """Near-tie rule against the fp64 brute force run ON THE DEVICE (oracle.assign_fp64_torch) for a random subset
+    of the frames (the assignment is row-independent, so a subset of rows is an exact check of those rows).
+    Returns (flip rate, worst gap among the flips)."""
+    N = x_rows.shape[0]
+    if sample is not None and sample < N:
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        sel = torch.randperm(N, generator=g)[:sample].to(x_rows.device)
+    else:
+        sel = torch.arange(N, device=x_rows.device)
+    ref_idx, _, gap = O.assign_fp64_torch(x_rows[sel], w)
+    differs = idx[sel] != ref_idx
+    worst = float(gap[differs].max()) if bool(differs.any()) else 0.0
+    assert worst < EPS_TIE, f"{int(differs.sum())} flips, worst gap {worst:.3e}"
+    rate = float(differs.float().mean())
+    assert rate <= 0.01, f"flip rate {rate:.4f}"
+    return rate, worst
+
+
+def test_device_fp64_oracle_matches_numpy_oracle(cuda_dev):
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x, w = torch.randn(700, 96, generator=g), torch.randn(333, 96, generator=g)
+    i_np, d_np, gap_np = O.assign_fp64(x.numpy(), w.numpy())
+    i_t, d_t, gap_t = O.assign_fp64_torch(x.to(cuda_dev), w.to(cuda_dev), chunk=128)
+    assert np.array_equal(i_t.cpu().numpy(), i_np)
+    np.testing.assert_allclose(d_t.cpu().numpy(), d_np, rtol=1e-10)
+    np.testing.assert_allclose(gap_t.cpu().numpy(), gap_np, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", ["normal", "mixture"])
+def test_assign_near_tie_rule_config2_full_size(cuda_dev, kind):
+    """BASELINE configs[1] (8192 frames, 8192 x 256 codebook) against the fp64 oracle on every frame: pure N(0,1)
+    frames are the worst case SURVEY 8d names (median relative top-2 gap ~1e-2), the mixture is the bench's input."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(1236)
+    C = torch.randn(8192, 256, generator=g).to(cuda_dev)
+    if kind == "normal":
+        X = torch.randn(8192, 256, generator=g).to(cuda_dev)
+    else:
+        j = torch.randint(0, 8192, (8192,), generator=g).to(cuda_dev)
+        X = C[j] + 0.5 * torch.randn(8192, 256, generator=g).to(cuda_dev)
+    cb = ops.PreparedCodebook(8192, 256, cuda_dev).prepare(C)
+    idx, _, _ = ops.vq_assign(X, cb, 8192, 1, False)
+    xcf = X.view(64, 128, 256).permute(0, 2, 1).contiguous()
+    idx_cf, _, _ = ops.vq_assign(xcf, cb, 64, 128, True)
+    assert torch.equal(idx, idx_cf)
+    rate, worst = _near_tie_check(idx, X, C)
+    print(f"config 2 ({kind}): flip rate {rate:.5f}, worst flipped gap {worst:.2e}")
+
+
+def test_assign_near_tie_rule_config4_full_size(cuda_dev):
+    """BASELINE configs[3] (65536 frames, 16384 x 512): all frames assigned, 8192 random frames checked in fp64;
+    both the mixture and pure N(0,1) frames."""
+    ops = _ops()
+    g = torch.Generator(device=cuda_dev).manual_seed(1238)
+    K, D, N = 16384, 512, 65536
+    C = torch.randn(K, D, device=cuda_dev, generator=g)
+    cb = ops.PreparedCodebook(K, D, cuda_dev).prepare(C)
+    j = torch.randint(0, K, (N,), device=cuda_dev, generator=g)
+    for kind in ("mixture", "normal"):
+        X = torch.randn(N, D, device=cuda_dev, generator=g)
+        if kind == "mixture":
+            X = C[j] + 0.5 * X
+        idx, _, _ = ops.vq_assign(X, cb, N, 1, False)
+        rate, worst = _near_tie_check(idx, X, C, sample=8192, seed=4)
+        print(f"config 4 ({kind}): flip rate {rate:.5f}, worst flipped gap {worst:.2e}")
+
+
+def test_assign_near_tie_rule_config5_subsample(cuda_dev):
+    """BASELINE configs[4] codebook (65536 x 512): 65536 frames assigned against the whole codebook and against 8
+    shards merged by MIN (bit-identical), 4096 random frames checked in fp64."""
+    ops = _ops()
+    g = torch.Generator(device=cuda_dev).manual_seed(1239)
+    K, D, N, world = 65536, 512, 65536, 8
+    C = torch.randn(K, D, device=cuda_dev, generator=g)
+    X = torch.randn(N, D, device=cuda_dev, generator=g)
+    full = ops.PreparedCodebook(K, D, cuda_dev).prepare(C)
+    idx, _, _ = ops.vq_assign(X, full, N, 1, False)
+    packed = ops.vq_packed_init(N, cuda_dev)
+    for r in range(world):
+        lo = r * (K // world)
+        shard = ops.PreparedCodebook(K // world, D, cuda_dev).prepare(C[lo:lo + K // world].contiguous())
+        ops.vq_assign(X, shard, N, 1, False, index_offset=lo, packed=packed)
+    idx_sh, _ = ops.vq_unpack(packed)
+    assert torch.equal(idx, idx_sh)
+    rate, worst = _near_tie_check(idx, X, C, sample=4096, seed=5)
+    print(f"config 5 (N(0,1) frames): flip rate {rate:.5f}, worst flipped gap {worst:.2e}")
 
 
 def test_config5_codebook_sharded_stress_full_size(cuda_dev):

@@ -60,6 +60,8 @@ def test_fused_head_ce_golden(cuda_dev):
     (8, 128, 512, 4096, 0.15, torch.float32),      # config c1
     (8, 128, 512, 4096, 0.15, torch.bfloat16),     # --bfloat16 autocast hands the head bf16 hidden states
     (32, 128, 512, 4096, 0.15, torch.bfloat16),    # config c3: one rank's share (32 lines) of the 256-line batch
+    (64, 128, 512, 8192, 0.15, torch.float32),     # the shape every bench.py number is quoted on (configs[1] labels)
+    (64, 128, 512, 8192, 0.15, torch.bfloat16),
     (5, 37, 96, 1000, 0.5, torch.float32),         # ragged: V, Dh, M not multiples of any tile
     (2, 9, 64, 300, 1.0, torch.float32),           # every frame masked
     (3, 50, 512, 257, 0.02, torch.float32),        # a handful of masked frames

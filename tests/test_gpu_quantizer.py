@@ -205,6 +205,75 @@ def test_ema_accumulate_deterministic_and_exact_counts(cuda_dev):
         assert torch.equal(ops.vq_counts(idx, K), torch.bincount(idx, minlength=K))
 
 
+@pytest.mark.parametrize("N,K,D,branch", [
+    (32768, 1024, 64, "cub device radix sort (N > 8192)"),
+    (4096, 20000, 32, "single-CTA block radix sort (N <= 8192, K > 16384)"),
+    (8192, 8192, 256, "single-CTA counting sort (bench shape)"),
+])
+def test_vq_ema_three_steps_vs_oracle_all_sort_branches(cuda_dev, N, K, D, branch):
+    """3 consecutive training steps of the drop-in VectorQuantizer from a warmed state against the oracle evaluated on
+    the CUDA indices (models/autoencoders.py:225-237), for every sort branch of pero_vq_ema_accumulate
+    (csrc/vq_ema.cu): the EMA state after each step, counts exact, and bit-identical when repeated."""
+    from pero_pretraining_b200 import VectorQuantizer, ops
+    g = torch.Generator(device="cpu").manual_seed(N + K)
+    w0 = torch.randn(K, D, generator=g)
+    T_ = 128
+    nl = N // T_
+
+    def run():
+        vq = VectorQuantizer(K, D, 0.25, 0.99).to(cuda_dev).train()
+        with torch.no_grad():
+            vq.embedding.weight.copy_(w0); vq.ema_w.copy_(w0); vq.ema_cluster_size.fill_(1.0)
+        gg = torch.Generator(device="cpu").manual_seed(5)
+        w, ema_w, cs = w0.clone(), w0.clone(), torch.ones(K)
+        states = []
+        for s in range(3):
+            j = torch.randint(0, K, (N,), generator=gg)
+            rows = w[j] + 0.3 * torch.randn(N, D, generator=gg)
+            x = rows.view(nl, 1, T_, D).permute(0, 3, 1, 2).contiguous()
+            q, idx = vq(x.to(cuda_dev))
+            torch.cuda.synchronize()
+            ref = O.vq_forward(x, w, ema_w, cs, 0.99, 1e-5, True, indices_override=idx.cpu())
+            ref_idx, _, gap = O.assign_fp64_torch(rows.to(cuda_dev), w.to(cuda_dev))
+            differs = idx != ref_idx
+            assert not bool(differs.any()) or float(gap[differs].max()) < EPS_TIE
+            assert torch.equal(ops.vq_counts(idx, K).cpu(), torch.bincount(idx.cpu(), minlength=K))
+            np.testing.assert_allclose(vq.ema_cluster_size.cpu().numpy(), ref["ema_cluster_size"].numpy(), rtol=2e-6)
+            np.testing.assert_allclose(vq.ema_w.detach().cpu().numpy(), ref["ema_w"].numpy(), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(vq.embedding.weight.detach().cpu().numpy(), ref["weight"].numpy(), rtol=2e-5, atol=1e-6)
+            w, ema_w, cs = ref["weight"], ref["ema_w"], ref["ema_cluster_size"]
+            states.append((idx.cpu().clone(), vq.embedding.weight.detach().cpu().clone(), vq.ema_w.detach().cpu().clone()))
+        return states
+
+    a, b = run(), run()
+    for (i1, w1, e1), (i2, w2, e2) in zip(a, b):
+        assert torch.equal(i1, i2) and torch.equal(w1, w2) and torch.equal(e1, e2), f"{branch}: not bit-identical run to run"
+
+
+def test_ema_accumulate_large_and_wide_codebooks(cuda_dev):
+    """pero_vq_ema_accumulate beyond the single-CTA sorts: N = 65536 (config 4's frames per step), K up to 65536."""
+    from pero_pretraining_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(29)
+    for N, K, D, mode in [(65536, 16384, 128, "uniform"), (20000, 65536, 64, "uniform"), (8000, 30000, 32, "skewed"),
+                          (40000, 50, 96, "collapsed")]:
+        x = torch.randn(N, D, generator=g).to(cuda_dev)
+        if mode == "uniform":
+            idx = torch.randint(0, K, (N,), generator=g)
+        elif mode == "skewed":
+            idx = (torch.rand(N, generator=g) ** 4 * K).long().clamp_(0, K - 1)
+        else:
+            idx = torch.full((N,), 7, dtype=torch.int64)
+        idx = idx.to(cuda_dev)
+        a = ops.vq_ema_accumulate(x, idx, K)
+        b = ops.vq_ema_accumulate(x, idx, K)
+        assert torch.equal(a, b)
+        sums, counts = a[:K * D].view(K, D), a[K * D:]
+        assert torch.equal(counts.long(), torch.bincount(idx, minlength=K))
+        ref = torch.zeros(K, D, dtype=torch.float64, device=cuda_dev).index_add_(0, idx, x.double())
+        tol = 1e-6 * max(1.0, float(counts.max())) ** 0.5 * 8
+        assert (sums.double() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
 def test_gather_st_and_mse_kernels(cuda_dev):
     from pero_pretraining_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(23)
