@@ -226,6 +226,7 @@ class DeviceStep:
         self.M = int(rows.size)
         self.rows = torch.from_numpy(rows).to(dev)
         self.cb = ops.PreparedCodebook(c["K"], c["D"], dev).prepare(self.weight)
+        self.packed = torch.empty(c["lines"] * c["frames"], dtype=torch.int64, device=dev)
         self.head = ops.PreparedHead(c["V"], c["Dh"], dev)
         self.m_global = float(self.M)
         if dp:
@@ -264,25 +265,33 @@ class DeviceStep:
             self.v_ranges = [(v, min(v + step, c["V"])) for v in range(0, c["V"], step)]
 
     def __call__(self):
-        """Three independent chains after the assignment, forked onto side streams (captured as parallel
-        branches of the CUDA graph): A gather/straight-through + commitment loss fwd/bwd, B the EMA codebook
-        update (needs A's gather to have read the old codebook before it overwrites it), C the masked CE
-        (its head operand preparation does not even depend on the assignment)."""
+        """Three chains, forked onto side streams (captured as parallel branches of the CUDA graph):
+          A (capture stream)  frame preparation + distance GEMM, unpack, gather/straight-through, commitment loss fwd/bwd
+          B (EMA stream)      EMA codebook update (needs A's gather to have read the old codebook before it is overwritten)
+          C (CE stream)       head operand preparation and the gather of the masked hidden states at the START of the step
+                              (neither needs this step's labels), then -- directly behind the distance GEMM, reading the
+                              labels from its packed (distance, index) winners -- logits GEMM + LSE, dlogits, d_W | d_h,
+                              scatter; the loss sum is read out of the partials at the end, off the GEMM chain."""
         ops, c = self.ops, CFG
+        N = c["lines"] * c["frames"]
         main = torch.cuda.current_stream()
         s_ema, s_ce = self.s_ema, self.s_ce
         s_ema.wait_stream(main)
-        idx, _, x_rows = ops.vq_assign(self.x, self.cb, c["lines"], c["frames"], True, want_rows=True)
-        with torch.cuda.stream(s_ema):
-            # Launched AFTER the distance GEMM and on the low-priority stream: the GEMM's CTAs are placed first and
-            # this bandwidth-bound kernel fills in beside them (it does not depend on the assignment).
-            self.head.prepare(self.W, self.b)        # head weights change every optimizer step in training
-            prepared = torch.cuda.Event()
-            prepared.record(s_ema)
-        s_ema.wait_stream(main)
         s_ce.wait_stream(main)
-        s_ce.wait_event(prepared)
+        with torch.cuda.stream(s_ce):
+            packed = ops.vq_packed_init(N, self.x.device, out=self.packed)
+            inited = torch.cuda.Event()
+            inited.record(s_ce)
+            self.head.prepare(self.W, self.b)        # head weights change every optimizer step in training
+            ce_ws = ops.masked_ce_gather(self.h, self.rows, c["V"])
+        main.wait_event(inited)
+        _, _, x_rows = ops.vq_assign(self.x, self.cb, c["lines"], c["frames"], True, want_rows=True, packed=packed)
+        assigned = torch.cuda.Event()
+        assigned.record(main)
+        s_ce.wait_event(assigned)
         # --- chain A (main stream)
+        idx, _ = ops.vq_unpack(packed)
+        s_ema.wait_stream(main)
         q = ops.vq_gather_st(x_rows, idx, self.weight, c["lines"], c["frames"], True)
         gathered = torch.cuda.Event()
         gathered.record(main)
@@ -301,29 +310,31 @@ class DeviceStep:
             s_ema.wait_event(gathered)
             ops.vq_ema_apply(sums, self.ema_w, self.cs, self.weight, c["decay"], c["epsilon"], self.cb)
         # --- chain C
+        Dh = c["Dh"]
         with torch.cuda.stream(s_ce):
+            _, _, ws = ops.masked_ce_fwd(self.h, self.rows, packed, self.head, ws=ce_ws, finalize=False, labels_packed=True)
             if not self.dp:
-                loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head)
-                d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
-                                                        return_flat=True, ws_from_fwd=True)
+                d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global, ws=ws,
+                                                        return_flat=True, ws_from_fwd=True, labels_packed=True)
+                loss_sum, lse = ops.masked_ce_loss(ws, N, Dh, self.M, c["V"])
             else:
                 # loss_sum rides in the same exchange range as d_W | d_b.  The backward walks the label axis range by
                 # range: each range's rows of d_W are reduced over the ranks on the communication stream while the
                 # next range (and finally d_h) is computed.
                 g = self.grad_x.tensor
-                Dh = c["Dh"]
-                loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, idx, self.head, loss_out=g[self.n_grad:])
                 for v0, v1 in self.v_ranges:
-                    _, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global,
+                    _, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global,
                                                           ws=ws, return_flat=True, want_dh=False, flat_out=g[:self.n_grad],
-                                                          ws_from_fwd=True, v_range=(v0, v1))
+                                                          ws_from_fwd=True, v_range=(v0, v1), labels_packed=True)
+                    last = v1 == c["V"]             # the last exchange also carries d_b | loss_sum, which follow d_W
+                    if last:
+                        loss_sum, lse = ops.masked_ce_loss(ws, N, Dh, self.M, c["V"], loss_out=g[self.n_grad:])
                     self.s_comm.wait_stream(s_ce)
                     with torch.cuda.stream(self.s_comm):
-                        last = v1 == c["V"]         # the last exchange also carries d_b | loss_sum, which follow d_W
                         numel = (self.grad_x.padded - v0 * Dh) if last else (v1 - v0) * Dh
                         self.peer.all_reduce_sum_(self.grad_x.offset + 4 * v0 * Dh, numel)
-                d_h, _, _ = ops.masked_ce_bwd(self.h, self.rows, idx, self.head, lse, None, 1.0 / self.m_global, ws=ws,
-                                              want_dw=False)
+                d_h, _, _ = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global, ws=ws,
+                                              want_dw=False, ws_from_fwd=True, labels_packed=True)
         main.wait_stream(s_ema)
         main.wait_stream(s_ce)
         if self.dp:

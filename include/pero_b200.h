@@ -155,28 +155,48 @@ int pero_vq_st_commit_bwd(const float* g_quantized, const float* quantized, cons
  * gather the masked frames, logits = h @ W^T + b over them only, mean cross-entropy with an online
  * log-sum-exp; the [M, V] logits never reach HBM in the forward.
  *
- * pero_head_prepare: fp32 head [V, Dh] (+ bias [V]) -> opaque blob with bf16 W, bf16 W^T and the bias.
+ * pero_head_prepare: fp32 head [V, Dh] (+ bias [V]) -> opaque blob with ONE bf16 copy of W and the bias (the logits
+ *   GEMMs read it K-major, d_h = dlogits W reads the same copy MN-major).
  * pero_masked_ce_fwd:
- *   h        hidden states [N, Dh], fp32 (h_is_bf16 = 0) or bf16 (1)
+ *   flags    PERO_CE_H_BF16 (1): h is bf16 (else fp32); PERO_CE_LABELS_PACKED (2): `labels` holds the packed
+ *            (distance, index) winners of pero_vq_assign instead of plain int64 labels (label = low 32 bits), so that
+ *            the head of a step whose labels are that step's codeword indices can start right behind the distance
+ *            GEMM, without waiting for pero_vq_unpack
+ *   h        hidden states [N, Dh]
  *   rows     [M] int32 frame indices of the masked frames, ascending (mask == 1 order)
- *   labels   [N] int64 (only labels[rows[m]] are read; must lie in [0, V))
- *   loss_sum [1] fp32: sum over masked frames of (lse - logit[label]);  lse [M] fp32 saved for backward
+ *   labels   [N] int64 (only labels[rows[m]] are read, by the GEMM epilogues, not by the gather; a label outside
+ *            [0, V) -- where the reference's F.cross_entropy raises a device assert -- makes the loss NaN)
+ *   loss_sum [1] fp32: sum over masked frames of (lse - logit[label]);  lse [M] fp32 saved for backward.  Both NULL:
+ *            the log-sum-exp partials stay in the workspace and pero_masked_ce_loss() produces loss_sum / lse later
+ *            (a backward on the same workspace does not need them), which takes the finalize launch off the
+ *            forward -> backward critical path.
+ *   h = NULL: pero_masked_ce_gather already ran on this workspace for the same (h, rows).  The gather reads neither the
+ *            labels nor the head, so a caller whose labels are produced late in the step (the quantizer's indices)
+ *            can issue it ahead of them, off the critical path.
+ *   Any hidden size works; up to Dh = 512 the masked rows stay resident in shared memory during the label sweep.
  * pero_masked_ce_bwd: gradients of  loss = grad_scale[0] * inv_count * loss_sum:
  *   d_h [N, Dh] (same dtype as h, zero on unmasked frames), d_W [V, Dh] fp32, d_b [V] fp32.
  *   Two-phase use: a first call with d_h = NULL produces d_W, d_b (ready to be all-reduced); a second call with
  *   d_W = d_b = NULL and the SAME workspace produces d_h from the dlogits the first call left there.
  *   h = NULL: the workspace is the one pero_masked_ce_fwd ran on for the same (h, rows, labels) and has not been
- *   written since; the operands gathered there are reused (h_is_bf16 must still describe d_h's dtype).
+ *   written since; the operands gathered there are reused (PERO_CE_H_BF16 must still describe d_h's dtype) and the
+ *   log-sum-exp is rebuilt from the forward's partials (`lse` may then be NULL).
  *   `rows` must be ascending (the order of mask == 1): the frame -> masked-row map is a binary search over it.
  */
 size_t pero_head_bytes(int64_t V, int64_t Dh);
 int pero_head_prepare(const float* W, const float* bias, int64_t V, int64_t Dh, void* head, size_t head_bytes,
                       pero_stream_t stream);
 size_t pero_masked_ce_workspace_bytes(int64_t N, int64_t M, int64_t V, int64_t Dh);
-int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+int pero_masked_ce_gather(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M, int64_t V,
+                          void* workspace, size_t workspace_bytes, pero_stream_t stream);
+#define PERO_CE_H_BF16 1
+#define PERO_CE_LABELS_PACKED 2
+int pero_masked_ce_fwd(const void* h, int flags, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
                        const int64_t* labels, const void* head, int64_t V, float* loss_sum, float* lse,
                        void* workspace, size_t workspace_bytes, pero_stream_t stream);
-int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+int pero_masked_ce_loss(int64_t N, int64_t Dh, int64_t M, int64_t V, float* loss_sum, float* lse, void* workspace,
+                        size_t workspace_bytes, pero_stream_t stream);
+int pero_masked_ce_bwd(const void* h, int flags, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
                        const int64_t* labels, const void* head, int64_t V, const float* lse,
                        const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
                        void* workspace, size_t workspace_bytes, pero_stream_t stream);
@@ -187,7 +207,7 @@ int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, cons
  * top-k predictions"; exact logit ties are broken in favour of the label).
  *   topk_host  HOST array of num_topk (1..8) values k >= 1, e.g. {1, 3, 10}
  *   rank  [M] int32 or NULL;  errors [num_topk] int64 (device).  Workspace: pero_masked_ce_workspace_bytes(). */
-int pero_masked_ce_eval(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+int pero_masked_ce_eval(const void* h, int flags, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
                         const int64_t* labels, const void* head, int64_t V, const int32_t* topk_host, int num_topk,
                         float* loss_sum, float* lse, int32_t* rank, int64_t* errors, void* workspace,
                         size_t workspace_bytes, pero_stream_t stream);
@@ -196,7 +216,7 @@ int pero_masked_ce_eval(const void* h, int h_is_bf16, int64_t N, int64_t Dh, con
  * dlogits kept in the workspace.  A data-parallel caller walks the label axis range by range and exchanges each
  * range of d_W while the next one is being computed; once all ranges are done, a call with d_W = d_b = NULL and
  * d_h given produces d_h.  d_h together with d_W/d_b is accepted only for the full range. */
-int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
                              const int64_t* labels, const void* head, int64_t V, const float* lse,
                              const float* grad_scale, float inv_count, int64_t v_begin, int64_t v_end, void* d_h,
                              float* d_W, float* d_b, void* workspace, size_t workspace_bytes, pero_stream_t stream);

@@ -48,8 +48,10 @@ SIGNATURES = {
     "pero_head_bytes": (c_sz, [c_i64, c_i64]),
     "pero_head_prepare": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
     "pero_masked_ce_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_i64]),
+    "pero_masked_ce_gather": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
     "pero_masked_ce_fwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp,
                                    c_sz, c_vp]),
+    "pero_masked_ce_loss": (c_int, [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pero_masked_ce_bwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32,
                                    c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pero_masked_ce_eval": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp,

@@ -44,12 +44,20 @@ class _QuantizeST(torch.autograd.Function):
         # data parallel: the EMA sums|counts are exchanged between accumulate and apply
         idx, _, x_rows = ops.vq_assign(x, cb, n_lines, frames, channels_first=True, want_rows=True)
         out = ops.vq_gather_st(x_rows, idx, weight, n_lines, frames, channels_first=True)
-        if update and idx.numel() > 0:
+        if update:
+            # Every rank enters the exchange, also one whose shard of the batch is empty (it contributes zeros): the
+            # peers are waiting for it inside their exchange kernel.
             if vq._peer_range is not None:      # [K, D+1] SUM over ranks, in place in the peer-mapped range
-                sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings, out=vq._peer_range.tensor)
+                if idx.numel() > 0:
+                    sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings, out=vq._peer_range.tensor)
+                else:
+                    sums_counts = vq._peer_range.tensor.zero_()
                 vq._peer_range.all_reduce_sum_()
             else:
-                sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings)
+                if idx.numel() > 0:
+                    sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings)
+                else:
+                    sums_counts = torch.zeros(vq.num_embeddings * (D + 1), dtype=torch.float32, device=x.device)
                 torch.distributed.all_reduce(sums_counts, group=vq._dp_group)
             ops.vq_ema_apply(sums_counts, vq.ema_w.data, vq.ema_cluster_size, weight, vq.decay, vq.epsilon, cb)
             vq._codebook_tag = vq._weight_tag()
@@ -139,6 +147,17 @@ class VectorQuantizer(torch.nn.Module):
             buf = PeerBuffer(4 * n + 256, self.embedding.weight.device, self._dp_group)
             self._peer_range = PeerRange(buf, n, torch.float32)
         return self
+
+    def invalidate_codebook(self):
+        """Forget the prepared codebook (bf16 operand + |c|^2).  The cache is keyed on (data_ptr, _version) of
+        embedding.weight; a write through `.data` (e.g. `vq.embedding.weight.data.copy_(kmeans_centers)`, the idiom
+        the reference's own __init__ uses) does not bump `_version`, so call this after one.  load_state_dict() does it
+        by itself."""
+        self._codebook_tag = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._codebook_tag = None
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def _weight_tag(self):
         w = self.embedding.weight

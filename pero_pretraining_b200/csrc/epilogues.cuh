@@ -134,6 +134,49 @@ struct StoreEpi {
 };
 
 // ------------------------------------------------------------------------------------------------
+// fp32 store C[split][row, col] through TMA: every warp stages its 32 x 32 chunk (32 rows of 128 B) in one of two
+// 4 KiB shared-memory tiles laid out as a SWIZZLE_128B box (16-byte piece j of row r at position j ^ (r & 7):
+// conflict-free 16-byte stores) and one lane hands it to cp.async.bulk.tensor, which clips against the output's rows
+// and columns.  The thread-level work per chunk is 8 shared-memory stores; the global stores run asynchronously
+// while the next chunk is read from TMEM (two tiles in flight).  Needs a 16-byte aligned output with ld % 4 == 0.
+struct StoreTmaEpi {
+    static constexpr bool kColVec = false;
+    static constexpr int kScratchPerWarp = 2 * 4096;
+    struct Params {
+        CUtensorMap tmap_out;     // make_tmap_f32_store: {cols, rows, splits}
+    };
+    struct State { int n; };
+    static __device__ __forceinline__ void begin_rb(State& st, const Params&, const TileCtx&) { st.n = 0; }
+    static __device__ __forceinline__ void tile(State& st, const Params& ep, const TileCtx& cx, uint32_t taddr) {
+        const int lane = threadIdx.x & 31;
+        const int row_base = cx.row - lane;
+        const uint32_t stage0 = smem_u32(cx.scratch);
+        const uint32_t sw = (uint32_t)(lane & 7);
+        for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
+            const uint32_t stage = stage0 + (uint32_t)(st.n & 1) * 4096u;
+            if (lane == 0) tma_store_wait_read1();          // the store issued two chunks ago has read this tile
+            __syncwarp();
+            const uint32_t rowaddr = stage + (uint32_t)lane * 128u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                             ::"r"(rowaddr + (((uint32_t)i ^ sw) * 16u)), "r"(r[4 * i]), "r"(r[4 * i + 1]), "r"(r[4 * i + 2]),
+                               "r"(r[4 * i + 3]) : "memory");
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_3d(&ep.tmap_out, stage, cx.col0 + c * 32, row_base, cx.ks);
+                tma_store_commit();
+            }
+            ++st.n;
+        });
+    }
+    static __device__ __forceinline__ void end_rb(State&, const Params&, const TileCtx&) {
+        if ((threadIdx.x & 31) == 0) tma_store_wait_read();      // the tiles must outlive the stores' reads
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Measurement-only epilogues (pero_debug_gemm_tn): NullEpi never touches TMEM (MMA + TMA ceiling),
 // LoadEpi only streams the accumulator out of TMEM (adds the tcgen05.ld cost).
 struct NullEpi {

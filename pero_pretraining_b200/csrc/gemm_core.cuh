@@ -19,8 +19,10 @@
 //   eligible warp id, and a producer / MMA issuer that loses issue slots to ALU-heavy epilogue warps
 //   stalls the tensor pipe (measured: 2400 instead of 2048 cycles per 256-deep tile).
 //
-// With kAResident the A row block is loaded ONCE per row block into its own k-block slots and only B
-// streams through the stage ring; otherwise A and B k-blocks share the ring (long contractions: dW, dh).
+// With kARes >= 1 the A row block is loaded ONCE per row block into its own k-block slots and only B streams
+// through the stage ring; kARes == 2 keeps TWO such sets (short contractions, Kd <= 384), so the next row block's A is
+// loaded while the current one is still being multiplied and a row-block change does not drain the MMA queue.
+// kARes == 0: A and B k-blocks share the ring (long contractions: dW, dh).
 //
 // The epilogue is a policy class (see epilogues.cuh / masked_ce.cu):
 //   struct Epi { static constexpr bool kColVec; struct Params; struct State;
@@ -39,7 +41,7 @@ constexpr int kBlockN = 256;        // accumulator columns per tile (UMMA N)
 constexpr int kBlockK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxStages = 8;
-constexpr int kMaxAKb = 12;         // resident A: up to 12 k-blocks (Kd <= 768)
+constexpr int kMaxAKb = 12;         // resident A: up to 12 k-block slots (Kd <= 768, or two sets of Kd <= 384)
 constexpr int kGemmThreads = 384;
 constexpr int kHalfN = kBlockN / 2; // columns per epilogue warp group
 constexpr int kEpiThreads = 256;
@@ -60,7 +62,13 @@ struct GemmShape {
                        // not read this kernel's output), bit 1 = before exiting, wait for the previous kernel (this
                        // kernel was released early by it, does not read its output, and must not be seen to finish
                        // first), bit 2 = wait for the previous kernel after the set-up (barriers, TMEM, descriptor
-                       // prefetch), before the first global access: the set-up overlaps the producer kernel's tail
+                       // prefetch), before the first global access: the set-up overlaps the producer kernel's tail,
+                       // bit 3 (with bit 2 and a resident A) = the B operand and the column vector are NOT written by
+                       // the previous kernel: the first ring of B loads is issued before the wait, only the A loads
+                       // and the epilogue's global accesses come after it,
+                       // bit 4 = release the next kernel of the stream LATE: when this CTA has requested its last
+                       // operand load (about one unit before it exits), so that a dependent GEMM -- which cannot be
+                       // co-resident anyway -- is dispatched while the last tiles drain instead of after a launch gap
     unsigned long long* timeline;   // debug: per-unit clock64 stamps of worker 0 ([unit][8]); NULL in production
 };
 
@@ -76,11 +84,11 @@ struct TileCtx {
     int num_workers;
 };
 
-__host__ __device__ inline size_t gemm_smem_bytes(int cta_group, bool a_resident, int num_kb, int stages,
+__host__ __device__ inline size_t gemm_smem_bytes(int cta_group, int a_sets, int num_kb, int stages,
                                                   int scratch_per_warp) {
     const size_t b_bytes = (size_t)(kBlockN / cta_group) * kBlockK * 2;
-    const size_t stage = b_bytes + (a_resident ? 0 : kABlockBytes);
-    const size_t a_res = a_resident ? (size_t)num_kb * kABlockBytes : 0;
+    const size_t stage = b_bytes + (a_sets ? 0 : kABlockBytes);
+    const size_t a_res = (size_t)a_sets * num_kb * kABlockBytes;
     return 1024 /*align slack*/ + a_res + stage * stages + 1024 /*barriers*/ + 2 * kBlockN * 4 /*column vector x2*/ +
            (size_t)scratch_per_warp * (kEpiThreads / 32);
 }
@@ -135,14 +143,18 @@ __device__ __forceinline__ void stamp_cta(const GemmShape& sh, bool on, int slot
 // 128 registers per thread (384 threads -> 48 K of the SM's 64 K registers): the remaining 16 K let one CTA of a
 // bandwidth-bound kernel or of the peer-exchange kernel run on the same SM, so those kernels overlap a resident
 // GEMM instead of waiting for it (or, worse, keeping the next GEMM's CTA off the SM).
-// kMnMajor: both operands are read "transposed" — A is stored [k][rows_a] and B [k][rows_b] (the contraction index
+// kMajor (bit 0: A, bit 1: B) marks operands that are read "transposed" (MN-major): with both bits set A is stored
+// [k][rows_a] and B [k][rows_b] (the contraction index
 // runs over the rows of the stored matrices), i.e. C = A^T B without a transposed copy of either in HBM.  TMA
 // fetches boxes of {64 contiguous MN-elements, 64 k-rows}; the UMMA descriptors are MN-major.
-template <int kCtaGroup, bool kAResident, class Epi, bool kMnMajor = false>
+template <int kCtaGroup, int kARes, class Epi, int kMajor = 0>
 __global__ void __maxnreg__(128)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmShape sh, const typename Epi::Params ep) {
-    static_assert(!(kMnMajor && kAResident), "MN-major operands are streamed through the ring");
+               const GemmShape sh, const __grid_constant__ typename Epi::Params ep) {
+    constexpr bool kAResident = kARes != 0;
+    constexpr int kASets = kARes == 2 ? 2 : 1;
+    constexpr bool kAMn = (kMajor & 1) != 0, kBMn = (kMajor & 2) != 0;
+    static_assert(!(kMajor && kAResident), "MN-major operands are streamed through the ring");
     if (sh.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -161,7 +173,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int stages = sh.num_stages;
 
     const uint32_t a_res = smem_base;                                        // resident A k-blocks
-    const uint32_t ring = smem_base + (kAResident ? sh.num_kb * kABlockBytes : 0);
+    const uint32_t ring = smem_base + (kAResident ? kASets * sh.num_kb * kABlockBytes : 0);
     const uint32_t bars = ring + stages * kStageBytes;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
@@ -190,7 +202,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    if (sh.pdl & 4) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // bit 3: only the threads that touch memory written by the previous kernel wait, and as late as they can (below)
+    const bool late_wait = kAResident && (sh.pdl & 12) == 12;
+    if ((sh.pdl & 4) && !late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     stamp_cta(sh, threadIdx.x == 0, 1);
     int u0, u1;
@@ -202,6 +216,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             int prev_rb = -1, rbi = -1;
+            // late_wait: B never comes from the kernel this launch programmatically depends on, so the first ring of B
+            // k-blocks is requested at once; the A loads (and everything else) follow the wait.
+            int pre_issued = 0;
+            bool waited = !late_wait;
+            if constexpr (kAResident) {
+                if (late_wait) {
+                    for (UnitIter ui(sh, u0, u1); ui.valid() && pre_issued < stages; ui.next()) {
+                        const int brow0 = ui.ct * kBlockN + (int)cta_rank * (int)kBRows;
+                        for (int kb = 0; kb < sh.num_kb && pre_issued < stages; ++kb, ++pre_issued) {
+                            const uint32_t sbase = ring + pre_issued * kStageBytes;        // first pass over the ring: all free
+                            if constexpr (kCtaGroup == 1) {
+                                mbar_arrive_expect_tx(full_bar(pre_issued), kStageBytes);
+                                tma_load_2d(sbase, &tmap_b, full_bar(pre_issued), kb * kBlockK, brow0);
+                            } else {
+                                if (leader) mbar_arrive_expect_tx(full_bar(pre_issued), 2 * kStageBytes);
+                                else mbar_arrive_remote(full_bar(pre_issued), 0);
+                                tma_load_2d_pair(sbase, &tmap_b, full_bar(pre_issued), kb * kBlockK, brow0);
+                            }
+                        }
+                    }
+                }
+            }
             for (UnitIter ui(sh, u0, u1); ui.valid(); ui.next()) {
                 const bool new_rb = (ui.rb != prev_rb);
                 if (new_rb) { ++rbi; prev_rb = ui.rb; }
@@ -209,72 +245,89 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int brow0 = ui.ct * kBlockN + (int)cta_rank * (int)kBRows;
                 const int kb0 = ui.ks * sh.kb_per_split;
                 const int kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
+                const int aset = (kASets == 2) ? (rbi & 1) : 0;
+                const int ause = (kASets == 2) ? (rbi >> 1) : rbi;        // how often this A set has been filled before
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (kb == kb0) stamp(sh, tl, ui.u - u0, 6);
                     if (kAResident && new_rb) {
-                        mbar_wait(aempty_bar(kb), (rbi & 1) ^ 1);
+                        if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
+                        const int slot = aset * sh.num_kb + kb;
+                        mbar_wait(aempty_bar(slot), (ause & 1) ^ 1);
                         if constexpr (kCtaGroup == 1) {
-                            mbar_arrive_expect_tx(afull_bar(kb), kABlockBytes);
-                            tma_load_2d(a_res + kb * kABlockBytes, &tmap_a, afull_bar(kb), kb * kBlockK, row0);
+                            mbar_arrive_expect_tx(afull_bar(slot), kABlockBytes);
+                            tma_load_2d(a_res + slot * kABlockBytes, &tmap_a, afull_bar(slot), kb * kBlockK, row0);
                         } else {
-                            if (leader) mbar_arrive_expect_tx(afull_bar(kb), 2 * kABlockBytes);
-                            else mbar_arrive_remote(afull_bar(kb), 0);
-                            tma_load_2d_pair(a_res + kb * kABlockBytes, &tmap_a, afull_bar(kb), kb * kBlockK, row0);
+                            if (leader) mbar_arrive_expect_tx(afull_bar(slot), 2 * kABlockBytes);
+                            else mbar_arrive_remote(afull_bar(slot), 0);
+                            tma_load_2d_pair(a_res + slot * kABlockBytes, &tmap_a, afull_bar(slot), kb * kBlockK, row0);
                         }
+                    }
+                    if (pre_issued > 0) {               // this k-block's B was requested ahead of the wait
+                        --pre_issued;
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                        if (kb + 1 == kb1) stamp(sh, tl, ui.u - u0, 7);
+                        continue;
                     }
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sbase = ring + stage * kStageBytes;
-                    if constexpr (kMnMajor) {
-                        // boxes of {64 MN-elements, 64 k-rows} = 8 KiB each: 2 for A, kBRows / 64 for B
+                    {
+                        // K-major operand: one box {64 k-elements, rows}.  MN-major operand: boxes of {64 MN-elements,
+                        // 64 k-rows} = 8 KiB each (2 for A, kBRows / 64 for B), the contraction index running over rows.
                         constexpr uint32_t kBox = 64u * kBlockK * 2u;
                         if constexpr (kCtaGroup == 1) {
                             mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-#pragma unroll
-                            for (int j = 0; j < kBlockM / 64; ++j)
-                                tma_load_2d(sbase + kBBlockBytes + j * kBox, &tmap_a, full_bar(stage), row0 + 64 * j, kb * kBlockK);
-#pragma unroll
-                            for (int j = 0; j < (int)kBRows / 64; ++j)
-                                tma_load_2d(sbase + j * kBox, &tmap_b, full_bar(stage), brow0 + 64 * j, kb * kBlockK);
                         } else {
                             if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);
                             else mbar_arrive_remote(full_bar(stage), 0);
-#pragma unroll
-                            for (int j = 0; j < kBlockM / 64; ++j)
-                                tma_load_2d_pair(sbase + kBBlockBytes + j * kBox, &tmap_a, full_bar(stage), row0 + 64 * j, kb * kBlockK);
-#pragma unroll
-                            for (int j = 0; j < (int)kBRows / 64; ++j)
-                                tma_load_2d_pair(sbase + j * kBox, &tmap_b, full_bar(stage), brow0 + 64 * j, kb * kBlockK);
                         }
-                    } else if constexpr (kCtaGroup == 1) {
-                        mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-                        if constexpr (!kAResident) tma_load_2d(sbase + kBBlockBytes, &tmap_a, full_bar(stage), kb * kBlockK, row0);
-                        tma_load_2d(sbase, &tmap_b, full_bar(stage), kb * kBlockK, brow0);
-                    } else {
-                        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);
-                        else mbar_arrive_remote(full_bar(stage), 0);
-                        if constexpr (!kAResident) tma_load_2d_pair(sbase + kBBlockBytes, &tmap_a, full_bar(stage), kb * kBlockK, row0);
-                        tma_load_2d_pair(sbase, &tmap_b, full_bar(stage), kb * kBlockK, brow0);
+                        auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+                            if constexpr (kCtaGroup == 1) tma_load_2d(dst, m, full_bar(stage), c0, c1);
+                            else tma_load_2d_pair(dst, m, full_bar(stage), c0, c1);
+                        };
+                        if constexpr (!kAResident) {
+                            if constexpr (kAMn) {
+#pragma unroll
+                                for (int j = 0; j < kBlockM / 64; ++j) load(sbase + kBBlockBytes + j * kBox, &tmap_a, row0 + 64 * j, kb * kBlockK);
+                            } else {
+                                load(sbase + kBBlockBytes, &tmap_a, kb * kBlockK, row0);
+                            }
+                        }
+                        if constexpr (kBMn) {
+#pragma unroll
+                            for (int j = 0; j < (int)kBRows / 64; ++j) load(sbase + j * kBox, &tmap_b, brow0 + 64 * j, kb * kBlockK);
+                        } else {
+                            load(sbase, &tmap_b, kb * kBlockK, brow0);
+                        }
                     }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                     if (kb + 1 == kb1) stamp(sh, tl, ui.u - u0, 7);
                 }
             }
+            if (sh.pdl & 16) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
             // Drain: every tcgen05.commit aimed at this CTA's barriers must have landed before the
             // CTA may exit (in pair mode they are multicast from the leader).
             for (int s = 0; s < stages; ++s) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
-            if (kAResident && rbi >= 0)
-                for (int kb = 0; kb < sh.num_kb; ++kb) mbar_wait(aempty_bar(kb), rbi & 1);
+            if (kAResident && rbi >= 0) {
+                for (int set = 0; set < kASets; ++set) {
+                    const int uses = (kASets == 2) ? ((rbi - set) >= 0 ? (rbi - set) / 2 + 1 : 0) : rbi + 1;
+                    if (uses == 0) continue;
+                    for (int kb = 0; kb < sh.num_kb; ++kb) mbar_wait(aempty_bar(set * sh.num_kb + kb), (uses - 1) & 1);
+                }
+            }
         }
     } else if (warp == 9) {
         // ------------------------------------------------------------ MMA issuer (leader CTA)
         // The whole warp walks the loop (uniform control flow) and one elected lane issues.  The full-
         // barrier probe of the NEXT stage is issued before the MMAs of the current one, so its latency
         // hides behind the issue instead of adding ~100 cycles per k-block.
+        // (Measured, round 2: handing alternate units to a second issuing warp that has already passed the waits of
+        // the next unit does not shorten a unit -- the 16 MMAs of a 256 x 256 x 256 unit take ~2700 cycles back to
+        // back either way -- so the single issuer stays.)
         if (leader && u0 < u1) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, kBlockN, kMnMajor);
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, kBlockN, kAMn, kBMn);
             int stage = 0; uint32_t phase = 0;
             int prev_rb = -1, rbi = -1, it = 0;
             uint32_t ready = 0;
@@ -285,12 +338,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int kb0 = ui.ks * sh.kb_per_split;
                 const int kb1 = min(sh.num_kb, kb0 + sh.kb_per_split);
                 const int buf = it & 1;
+                const int aset = (kASets == 2) ? (rbi & 1) : 0;
+                const int ause = (kASets == 2) ? (rbi >> 1) : rbi;
                 stamp(sh, tl && lane == 0, it, 0);
                 mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
                 stamp(sh, tl && lane == 0, it, 1);
                 const uint32_t tmem_d = tmem_base + buf * kBlockN;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    if (kAResident && new_rb) mbar_wait(afull_bar(kb), rbi & 1);
+                    if (kAResident && new_rb) mbar_wait(afull_bar(aset * sh.num_kb + kb), ause & 1);
                     if (!ready) mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     if (kb == kb0) stamp(sh, tl && lane == 0, it, 2);
@@ -299,21 +354,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     // probe only if another k-block follows: a probe of a phase that never completes would stall
                     ready = (kb + 1 < kb1 || ui.u + 1 < u1) ? mbar_test_wait(full_bar(nstage), nphase) : 0u;
                     const uint32_t sbase = ring + stage * kStageBytes;
-                    const uint32_t a_addr = kAResident ? (a_res + kb * kABlockBytes) : (sbase + kBBlockBytes);
+                    const uint32_t a_addr = kAResident ? (a_res + (aset * sh.num_kb + kb) * kABlockBytes) : (sbase + kBBlockBytes);
                     constexpr uint32_t kMnBox = 64u * kBlockK * 2u;
-                    const uint64_t adesc = kMnMajor ? make_mnmajor_sw128_desc(a_addr, kMnBox) : make_kmajor_sw128_desc(a_addr);
-                    const uint64_t bdesc = kMnMajor ? make_mnmajor_sw128_desc(sbase, kMnBox) : make_kmajor_sw128_desc(sbase);
+                    const uint64_t adesc = kAMn ? make_mnmajor_sw128_desc(a_addr, kMnBox) : make_kmajor_sw128_desc(a_addr);
+                    const uint64_t bdesc = kBMn ? make_mnmajor_sw128_desc(sbase, kMnBox) : make_kmajor_sw128_desc(sbase);
                     // address-field step per UMMA_K (16 contraction elements): K-major +32 B inside the 128-byte
                     // swizzle row (+2 in the >>4 field); MN-major +16 k-rows = two 1024-byte atoms (+128)
-                    constexpr uint64_t kDescStep = kMnMajor ? (2048u >> 4) : 2u;
+                    constexpr uint64_t kAStep = kAMn ? (2048u >> 4) : 2u, kBStep = kBMn ? (2048u >> 4) : 2u;
                     if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                            umma_bf16<kCtaGroup>(tmem_d, adesc + kDescStep * k, bdesc + kDescStep * k, idesc,
+                            umma_bf16<kCtaGroup>(tmem_d, adesc + kAStep * k, bdesc + kBStep * k, idesc,
                                                  (kb > kb0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit<kCtaGroup>(empty_bar(stage));
-                        if (kAResident && last_of_rb) umma_commit<kCtaGroup>(aempty_bar(kb));
+                        if (kAResident && last_of_rb) umma_commit<kCtaGroup>(aempty_bar(aset * sh.num_kb + kb));
                         if (kb + 1 == kb1) { umma_commit<kCtaGroup>(tfull_bar(buf)); stamp(sh, tl, it, 3); }
                     }
                     __syncwarp();
@@ -323,6 +378,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp < 8) {
         // ------------------------------------------------------------ epilogue (both CTAs of a pair)
+        if (late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");     // before the first access to the previous kernel's output
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
         const int half = warp >> 2;                   // which 128 columns of every tile
         const int ht = q * 32 + lane;                 // thread index inside its half group

@@ -7,6 +7,7 @@
 #include "knobs.h"
 #include <atomic>
 #include <stdlib.h>
+#include <string.h>
 
 namespace pero {
 
@@ -27,27 +28,30 @@ inline EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
-// Row-major bf16 matrix [rows, cols] with row pitch `pitch_elems` (multiple of 8 elements), tiled in
-// boxes of {64 columns, box_rows rows}, SWIZZLE_128B, out-of-bounds elements read as zero.
-inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
-                          uint32_t box_rows) {
+// Tiled tensor map (rank 2 or 3), SWIZZLE_128B, out-of-bounds elements read as zero / not written.
+// The encode is a pure function of its arguments and costs ~3 us of host time per call; a training loop asks for the
+// same few descriptors every step (the caching allocator hands back the same addresses), so the last results are
+// memoised per thread.  Nothing here refers to device state: a stale entry cannot exist.
+inline int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int elem_bytes, const void* base, int rank,
+                     const uint64_t* dims, const uint64_t* stride_elems /* rank - 1 entries */, const uint32_t* box) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return PERO_ERR_DRIVER;
-    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch_elems & 7u) || box_rows == 0 || box_rows > 256)
-        return PERO_ERR_BAD_ALIGN;
-    // The encode is a pure function of its arguments and costs ~3 us of host time per call; a training loop asks
-    // for the same few descriptors every step (the caching allocator hands back the same addresses), so the last
-    // results are memoised per thread.  Nothing here refers to device state: a stale entry cannot exist.
-    struct Key { const void* base; uint64_t rows, cols, pitch; uint32_t box_rows; };
+    if (reinterpret_cast<uintptr_t>(base) & 15u) return PERO_ERR_BAD_ALIGN;
+    for (int i = 0; i + 1 < rank; ++i)
+        if ((stride_elems[i] * elem_bytes) & 15u) return PERO_ERR_BAD_ALIGN;
+    struct Key { const void* base; uint64_t d[3], s[2]; uint32_t b[3]; int rank, dtype; };
     struct Entry { Key k; CUtensorMap map; bool valid; };
     constexpr int kSlots = 32;
     static thread_local Entry cache[kSlots] = {};
-    const Key key{base, rows, cols, pitch_elems, box_rows};
+    Key key = {};
+    key.base = base; key.rank = rank; key.dtype = (int)dtype;
+    for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) key.s[i] = stride_elems[i];
     uint64_t hsh = reinterpret_cast<uintptr_t>(base) >> 8;
-    hsh = (hsh ^ (rows * 0x9E3779B97F4A7C15ull) ^ (cols << 17) ^ (pitch_elems << 29) ^ box_rows) * 0xD6E8FEB86659FD93ull;
+    hsh = (hsh ^ (key.d[1] * 0x9E3779B97F4A7C15ull) ^ (key.d[0] << 17) ^ (key.s[0] << 29) ^ key.b[1] ^ ((uint64_t)dtype << 50) ^
+           (key.d[2] << 7)) * 0xD6E8FEB86659FD93ull;
     Entry& e = cache[(hsh >> 40) % kSlots];
-    if (e.valid && e.k.base == key.base && e.k.rows == key.rows && e.k.cols == key.cols && e.k.pitch == key.pitch &&
-        e.k.box_rows == key.box_rows) {
+    if (e.valid && memcmp(&e.k, &key, sizeof(Key)) == 0) {
         *out = e.map;
         return PERO_OK;
     }
@@ -60,16 +64,35 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
         if (cudaGetDevice(&dev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) return PERO_ERR_DRIVER;
         context_bound = true;
     }
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {pitch_elems * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t gd[3] = {1, 1, 1};
+    cuuint64_t gs[2] = {0, 0};
+    cuuint32_t bx[3] = {1, 1, 1}, estr[3] = {1, 1, 1};
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = stride_elems[i] * elem_bytes;
+    CUresult r = enc(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return PERO_ERR_DRIVER;
     e.k = key; e.map = *out; e.valid = true;
     return PERO_OK;
+}
+
+// Row-major bf16 matrix [rows, cols] with row pitch `pitch_elems` (multiple of 8 elements), tiled in
+// boxes of {64 columns, box_rows rows}.
+inline int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                          uint32_t box_rows) {
+    if ((pitch_elems & 7u) || box_rows == 0 || box_rows > 256) return PERO_ERR_BAD_ALIGN;
+    const uint64_t dims[2] = {cols, rows}, strides[1] = {pitch_elems};
+    const uint32_t box[2] = {(uint32_t)kBlockK, box_rows};
+    return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, 2, dims, strides, box);
+}
+
+// fp32 output [planes][rows][cols] (row pitch ld, plane pitch plane_stride, both multiples of 4 elements), stored in
+// boxes of {32 columns = 128 B, 32 rows, 1 plane}: the staging tile of StoreTmaEpi.
+inline int make_tmap_f32_store(CUtensorMap* out, const void* base, uint64_t planes, uint64_t rows, uint64_t cols, uint64_t ld,
+                               uint64_t plane_stride) {
+    const uint64_t dims[3] = {cols, rows, planes}, strides[2] = {ld, plane_stride};
+    const uint32_t box[3] = {32, 32, 1};
+    return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, 3, dims, strides, box);
 }
 
 constexpr int kMaxDevices = 64;
@@ -117,17 +140,19 @@ constexpr size_t kSmemBudgetShared = 200 * 1024;
 constexpr size_t kSmemFloor = 120 * 1024;   // > half an SM: never two TMEM-hungry CTAs on one SM
 
 // Picks the deepest ring that fits; returns 0 when even 2 stages do not fit.
-inline int pick_stages(int cta_group, bool a_resident, int num_kb, int scratch_per_warp, size_t budget = kSmemBudget) {
+inline int pick_stages(int cta_group, int a_sets, int num_kb, int scratch_per_warp, size_t budget = kSmemBudget) {
     for (int s = kMaxStages; s >= 2; --s)
-        if (gemm_smem_bytes(cta_group, a_resident, num_kb, s, scratch_per_warp) <= budget) return s;
+        if (gemm_smem_bytes(cta_group, a_sets, num_kb, s, scratch_per_warp) <= budget) return s;
     return 0;
 }
 
 // A: [rows_a, kd] bf16, pitch_a elements; B: [rows_b, kd] bf16, pitch_b elements; kd % 64 == 0.
 // `workers` = number of CTAs (kCtaGroup == 1) or CTA pairs (== 2); 0 = fill the machine.
-// kMnMajor: A is stored [k_rows, rows_a] and B [k_rows, rows_b] (row pitches pitch_a / pitch_b), C = A^T B; kd is the
+// kMajor bit 0 / bit 1: A / B is MN-major, i.e. stored [k_rows, rows_a] / [k_rows, rows_b] (row pitch pitch_a / pitch_b);
+// both bits: C = A^T B.  kd is the
 // contraction length rounded up to 64 and k_rows (<= kd, 0 = kd) the rows that exist (TMA zero-fills the rest).
-template <int kCtaGroup, bool kAResident, class Epi, bool kMnMajor = false>
+// kARes: 0 = A streams through the ring with B, 1 = resident A row block, 2 = two resident A sets (num_kb <= 6).
+template <int kCtaGroup, int kARes, class Epi, int kMajor = 0>
 int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int rows_b, int pitch_b, int kd,
                    int num_ks, int split_mode, int fixed_s, int workers, const typename Epi::Params& ep,
                    cudaStream_t stream, unsigned long long* timeline = nullptr, size_t smem_budget = kSmemBudget,
@@ -152,22 +177,23 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     sh.split_mode = split_mode; sh.fixed_s = fixed_s < 1 ? 1 : fixed_s;
     if (PERO_KNOB("PERO_PDL", 1) == 0) pdl = 0;       // dev build: no programmatic dependent launches at all
     sh.pdl = pdl;
-    if (kAResident && (sh.num_ks != 1 || sh.num_kb > kMaxAKb)) return PERO_ERR_BAD_SHAPE;
-    sh.num_stages = pick_stages(kCtaGroup, kAResident, sh.num_kb, Epi::kScratchPerWarp, smem_budget);
+    constexpr int kASets = kARes == 2 ? 2 : (kARes ? 1 : 0);
+    if (kARes && (sh.num_ks != 1 || sh.num_kb * kASets > kMaxAKb)) return PERO_ERR_BAD_SHAPE;
+    sh.num_stages = pick_stages(kCtaGroup, kASets, sh.num_kb, Epi::kScratchPerWarp, smem_budget);
+    {
+        const int cap = PERO_KNOB("PERO_GEMM_STAGES", 0);        // dev build: ring-depth experiments
+        if (cap >= 2 && cap < sh.num_stages) sh.num_stages = cap;
+    }
     if (sh.num_stages < 2) return PERO_ERR_BAD_SHAPE;
 
     CUtensorMap ta, tb;
     int rc;
-    if constexpr (kMnMajor) {
-        const uint64_t kr = (uint64_t)(k_rows > 0 ? k_rows : kd);
-        rc = make_tmap_bf16(&ta, a, kr, (uint64_t)rows_a, (uint64_t)pitch_a, 64);
-        if (rc) return rc;
-        rc = make_tmap_bf16(&tb, b, kr, (uint64_t)rows_b, (uint64_t)pitch_b, 64);
-    } else {
-        rc = make_tmap_bf16(&ta, a, (uint64_t)rows_a, (uint64_t)kd, (uint64_t)pitch_a, kBlockM);
-        if (rc) return rc;
-        rc = make_tmap_bf16(&tb, b, (uint64_t)rows_b, (uint64_t)kd, (uint64_t)pitch_b, kBlockN / kCtaGroup);
-    }
+    const uint64_t kr = (uint64_t)(k_rows > 0 ? k_rows : kd);
+    if constexpr (kMajor & 1) rc = make_tmap_bf16(&ta, a, kr, (uint64_t)rows_a, (uint64_t)pitch_a, 64);
+    else rc = make_tmap_bf16(&ta, a, (uint64_t)rows_a, kr, (uint64_t)pitch_a, kBlockM);
+    if (rc) return rc;
+    if constexpr (kMajor & 2) rc = make_tmap_bf16(&tb, b, kr, (uint64_t)rows_b, (uint64_t)pitch_b, 64);
+    else rc = make_tmap_bf16(&tb, b, (uint64_t)rows_b, kr, (uint64_t)pitch_b, kBlockN / kCtaGroup);
     if (rc) return rc;
 
     const long long units = (long long)sh.num_rb * sh.num_ct * sh.num_ks;
@@ -180,9 +206,9 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     else if (workers <= 0 || workers > max_workers) workers = max_workers;
     if (split_mode == 0 && workers > units) workers = (int)units;
 
-    size_t smem = gemm_smem_bytes(kCtaGroup, kAResident, sh.num_kb, sh.num_stages, Epi::kScratchPerWarp);
+    size_t smem = gemm_smem_bytes(kCtaGroup, kASets, sh.num_kb, sh.num_stages, Epi::kScratchPerWarp);
     if (smem < kSmemFloor) smem = kSmemFloor;
-    auto kern = gemm_tn_kernel<kCtaGroup, kAResident, Epi, kMnMajor>;
+    auto kern = gemm_tn_kernel<kCtaGroup, kARes, Epi, kMajor>;
     {
         static std::atomic<bool> attr_done[kMaxDevices];
         cudaError_t e = ensure_max_dynamic_smem(kern, attr_done, kSmemBudget);

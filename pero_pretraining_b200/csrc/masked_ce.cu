@@ -28,15 +28,15 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return y;
 }
 
-// Prepared head: bf16 W [V, Dhp] | bf16 W^T [Dh, Vp] | bias fp32 [Vt] (-inf beyond V so padded label
-// columns vanish from the log-sum-exp).  Dhp, Vp: rounded up to 64; Vt: rounded up to 256.
-struct HeadLayout { int64_t Dhp, Vp, Vt; size_t w_off, wt_off, bias_off, total; };
+// Prepared head: bf16 W [V, Dhp] | bias fp32 [Vt] (-inf beyond V so padded label columns vanish from the
+// log-sum-exp).  Dhp, Vp: rounded up to 64; Vt: rounded up to 256.  ONE bf16 copy serves all three GEMMs that touch the
+// head: the logits GEMMs read it K-major (contraction over Dh), d_h = dlogits W reads it MN-major (contraction over V).
+struct HeadLayout { int64_t Dhp, Vp, Vt; size_t w_off, bias_off, total; };
 inline HeadLayout head_layout(int64_t V, int64_t Dh) {
     HeadLayout l;
     l.Dhp = round_up(Dh, 64); l.Vp = round_up(V, 64); l.Vt = round_up(V, 256);
     l.w_off = 0;
-    l.wt_off = align256((size_t)V * l.Dhp * 2);
-    l.bias_off = l.wt_off + align256((size_t)Dh * l.Vp * 2);
+    l.bias_off = align256((size_t)V * l.Dhp * 2);
     l.total = l.bias_off + align256((size_t)l.Vt * 4);
     return l;
 }
@@ -89,58 +89,80 @@ inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
 
 // ------------------------------------------------------------------------------------------------ prep
 __global__ void __launch_bounds__(256)
-head_prepare_kernel(const float* __restrict__ W, const float* __restrict__ bias, int V, int Dh, int Dhp, int Vp, int Vt,
-                    __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wbt, float* __restrict__ bias_out) {
-    // 32 x 32 tiles of W: coalesced read along Dh, bf16 copy, transposed bf16 copy through shared memory.
-    __shared__ float tile[32][33];
-    const int v0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+head_prepare_kernel(const float* __restrict__ W, const float* __restrict__ bias, int V, int Dh, int Dhp, int Vt,
+                    __nv_bfloat16* __restrict__ wb, float* __restrict__ bias_out) {
+    // bf16 copy of W, rows zero-padded to Dhp columns: 4 elements per thread (16-byte loads when Dh % 4 == 0)
+    const long long quads = (long long)V * (Dhp / 4);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool vec = (Dh & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+        const long long v = q / (Dhp / 4);
+        const int d = (int)(q - v * (Dhp / 4)) * 4;
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec) {
+            if (d < Dh) { const float4 t = __ldg(reinterpret_cast<const float4*>(W + v * Dh + d)); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w; }
+        } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int v = v0 + ty + i * 8, d = d0 + tx;
-        const float x = (v < V && d < Dh) ? __ldg(W + (size_t)v * Dh + d) : 0.f;
-        tile[ty + i * 8][tx] = x;
-        if (v < V && d < Dhp) wb[(size_t)v * Dhp + d] = __float2bfloat16_rn(x);
+            for (int j = 0; j < 4; ++j) if (d + j < Dh) x[j] = __ldg(W + v * Dh + d + j);
+        }
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(wb + v * Dhp + d) = o;
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int d = d0 + ty + i * 8, v = v0 + tx;
-        if (d < Dh && v < Vp) wbt[(size_t)d * Vp + v] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
-    }
-    if (blockIdx.y == 0) {
-        const int v = v0 + (int)threadIdx.x;
-        if (threadIdx.x < 32 && v < Vt) bias_out[v] = v < V ? (bias ? __ldg(bias + v) : 0.f) : -CUDART_INF_F;
-    }
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < Vt; v += stride)
+        bias_out[v] = v < V ? (bias ? __ldg(bias + v) : 0.f) : -CUDART_INF_F;
 }
 
 // Gather the masked frames into the GEMM operand A [M, Dhp] bf16 (rows = masked frames: the K-major operand of the
-// logits GEMMs and, read through MN-major descriptors, the operand of d_W = dlogits^T A), their labels, and the
-// inverse frame -> masked-row map inv [N] at the selected frames (see masked_row_of).  One warp per masked row.
-// Also clears the ticket word that ce_finalize_kernel's last block uses.
+// logits GEMMs and, read through MN-major descriptors, the operand of d_W = dlogits^T A) and the inverse
+// frame -> masked-row map inv [N] at the selected frames (see masked_row_of).  One warp per masked row.
+// Also clears the ticket word that ce_finalize_kernel's last block uses.  Nothing here reads the labels, so a
+// caller whose labels are produced late (by the quantizer of the same step) can gather ahead of them.
 template <typename T>
 __global__ void __launch_bounds__(256)
-ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, const long long* __restrict__ labels, int M,
-                 int Dh, int Dhp, int Mpad, __nv_bfloat16* __restrict__ a, int* __restrict__ lab, int* __restrict__ inv,
-                 unsigned int* __restrict__ ticket) {
+ce_gather_kernel(const T* __restrict__ h, const int* __restrict__ rows, int M, int Dh, int Dhp,
+                 __nv_bfloat16* __restrict__ a, int* __restrict__ inv, unsigned int* __restrict__ ticket) {
     // the logits GEMM behind this kernel sets itself up meanwhile and waits for this grid before its first load
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;
-    if (m >= Mpad) return;
-    if (m >= M) { if (lane == 0) lab[m] = -1; return; }
+    if (m >= M) return;
     const int r = __ldg(rows + m);
     const T* src = h + (size_t)r * Dh;
     __nv_bfloat16* dst = a + (size_t)m * Dhp;
+    if constexpr (sizeof(T) == 4) {
+        if ((Dh & 3) == 0) {                            // 16-byte loads, 8-byte stores
+            for (int d = 4 * lane; d < Dhp; d += 128) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (d < Dh) x = __ldg(reinterpret_cast<const float4*>(src + d));
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                uint2 o;
+                o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(dst + d) = o;
+            }
+            if (lane == 0) inv[r] = m;
+            return;
+        }
+    }
     for (int d = 2 * lane; d < Dhp; d += 64) {          // Dhp is a multiple of 64: every lane writes whole pairs
         const float x0 = d < Dh ? (float)src[d] : 0.f, x1 = d + 1 < Dh ? (float)src[d + 1] : 0.f;
         *reinterpret_cast<__nv_bfloat162*>(dst + d) = __floats2bfloat162_rn(x0, x1);
     }
-    if (lane == 0) {
-        lab[m] = (int)__ldg(labels + r);
-        inv[r] = m;
-    }
+    if (lane == 0) inv[r] = m;
+}
+
+// Label of masked row `row` (-1 beyond M; -2 when the label is outside [0, V): the reference's F.cross_entropy raises a
+// device assert there, here the row's loss becomes NaN and no one-hot is subtracted).
+// packed: `labels` holds the packed (distance, index) winners of pero_vq_assign (the label is the low 32 bits), which
+// lets the head of the same step start right behind the distance GEMM, without waiting for pero_vq_unpack.
+__device__ __forceinline__ int masked_label(const long long* __restrict__ labels, const int* __restrict__ rows, int row, int M, int V,
+                                            int packed) {
+    if (row >= M) return -1;
+    long long l = __ldg(labels + __ldg(rows + row));
+    if (packed) l = (long long)(unsigned long long)(l & 0xffffffffll);
+    return (l < 0 || l >= V) ? -2 : (int)l;
 }
 
 // The frame -> masked-row map `inv` is written only at the selected frames; every other entry keeps whatever the
@@ -162,17 +184,18 @@ struct LseEpiT {
     static constexpr int kScratchPerWarp = 0;
     struct Params {
         const float* colvec;  // bias [Vt], -inf beyond V
-        const int* lab;       // [Mpad]
+        const int* rows;      // [M] frame of every masked row
+        const long long* labels;   // [N] label of every frame
         float* pm; float* ps; // [2 * S, Mpad] partial max / sum(exp(z - max))
         float* zlab;          // [Mpad] logit at the label
         const float* zl_in;   // kRank: [Mpad] label logit computed ahead of the sweep
         int* pcnt;            // kRank: [2 * S, Mpad] partial counts of logits above zl_in
-        int M, Mpad, S;
+        int M, Mpad, S, V, packed;
     };
     struct State { float m, s, zl, zin; int label, cnt; bool has; };
     static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
         st.m = -CUDART_INF_F; st.s = 0.f; st.zl = 0.f; st.has = false;
-        st.label = cx.row < ep.M ? __ldg(ep.lab + cx.row) : -1;
+        st.label = masked_label(ep.labels, ep.rows, cx.row, ep.M, ep.V, ep.packed);
         st.cnt = 0;
         st.zin = (kRank && cx.row < ep.M) ? __ldg(ep.zl_in + cx.row) : CUDART_INF_F;
     }
@@ -230,41 +253,67 @@ struct LseEpiT {
         ep.pm[(size_t)slot * ep.Mpad + cx.row] = st.m;
         ep.ps[(size_t)slot * ep.Mpad + cx.row] = st.s;
         if (st.has) ep.zlab[cx.row] = st.zl;
+        else if (st.label == -2 && slot == 0) ep.zlab[cx.row] = CUDART_NAN_F;      // label outside [0, V)
         if constexpr (kRank) ep.pcnt[(size_t)slot * ep.Mpad + cx.row] = st.cnt;
     }
 };
 using LseEpi = LseEpiT<false>;
 using EvalEpi = LseEpiT<true>;
 
-// dlogits tile = (exp(z - lse) - [col == label]) * scale, written bf16 as P [M, Vp] only: 32 x 32 chunks are staged
-// row-major in a warp-private shared-memory tile so that one store instruction writes 8 rows x 64 B.  Both gradient
-// GEMMs read this one copy: d_h = P W consumes it K-major, d_W = P^T A through MN-major descriptors.
+// dlogits tile = (exp(z - lse) - [col == label]) * scale, written bf16 as P [M, Vp] only.  Both gradient GEMMs read
+// this one copy: d_h = P W consumes it K-major, d_W = P^T A through MN-major descriptors.
+// Every warp stages 32 rows x 64 columns (two 32-column chunks) in its own 4 KiB shared-memory tile, laid out as a
+// SWIZZLE_128B TMA box (row r at r * 128 B, its 16-byte piece j at position j ^ (r & 7): conflict-free 16-byte
+// stores), and one lane hands the tile to a TMA store (cp.async.bulk.tensor, clipped against M and Vp by the
+// descriptor): no per-row predicates, no address arithmetic, full 128-byte row segments on the way to L2
+// (16 us instead of 24 us for the kernel at the bench shape, round 2).
 struct DlogitsEpi {
     static constexpr bool kColVec = true;
-    static constexpr int kScratchPerWarp = 32 * 80;      // 32 rows x 32 bf16, 80-byte pitch
+    static constexpr int kScratchPerWarp = 4096;
     struct Params {
+        CUtensorMap tmap_p;   // P (first column = the range's first label column), box {64 columns, 32 rows}
         const float* colvec;  // bias [Vt], -inf beyond V (already offset to the range's first column)
-        const int* lab; const float* lse; const float* grad_scale;
+        const int* rows; const long long* labels;
+        const float* lse; const float* grad_scale;
         float inv_count;
         const float* pm; const float* ps;   // when not NULL: the forward's LSE partials [slots, Mpad]; the log-sum-exp
         int slots, Mpad;                    // is rebuilt from them instead of being read from `lse`
         __nv_bfloat16* p;      // already offset to the first label column of the range
-        int M, Vp;             // Vp: label columns of the range to write (multiple of 32)
+        int M, Vp;             // Vp: label columns of the range to write (multiple of 64)
         int p_pitch;           // row pitch of P (the full padded label count)
         int col_base;          // global index of the range's first label column
+        int V, packed;
     };
     struct State { float lse2, scale; int label; };
     static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
         const bool ok = cx.row < ep.M;
-        st.label = ok ? __ldg(ep.lab + cx.row) : -1;
+        st.label = masked_label(ep.labels, ep.rows, cx.row, ep.M, ep.V, ep.packed);
         if (ok && ep.pm) {
-            // same combination as ce_finalize_kernel, in slot order (coalesced: neighbouring lanes own neighbouring rows)
+            // The forward's per-slot partials (max, sum) of this row are combined here, in slot order and with the same
+            // arithmetic for every worker that owns the row, instead of waiting for ce_finalize_kernel: 16 loads in
+            // flight per batch, and the whole rebuild hides behind the first accumulator tile of the row block.
             float mx = -CUDART_INF_F;
-            for (int s = 0; s < ep.slots; ++s) mx = fmaxf(mx, __ldg(ep.pm + (size_t)s * ep.Mpad + cx.row));
+            for (int s0 = 0; s0 < ep.slots; s0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = (s0 + j < ep.slots) ? __ldg(ep.pm + (size_t)(s0 + j) * ep.Mpad + cx.row) : -CUDART_INF_F;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j]);
+            }
             float sum = 0.f;
-            for (int s = 0; s < ep.slots; ++s)
-                sum += __ldg(ep.ps + (size_t)s * ep.Mpad + cx.row) * exp2f((__ldg(ep.pm + (size_t)s * ep.Mpad + cx.row) - mx) * kLog2e);
-            st.lse2 = fmaf(mx, kLog2e, log2f(sum));
+            const float mx2 = mx * kLog2e;
+            for (int s0 = 0; s0 < ep.slots; s0 += 16) {
+                float pmv[16], psv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const bool in = s0 + j < ep.slots;
+                    pmv[j] = in ? __ldg(ep.pm + (size_t)(s0 + j) * ep.Mpad + cx.row) : -CUDART_INF_F;
+                    psv[j] = in ? __ldg(ep.ps + (size_t)(s0 + j) * ep.Mpad + cx.row) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum = fmaf(psv[j], ex2_fast(fmaf(pmv[j], kLog2e, -mx2)), sum);      // 2^-inf = 0 on empty slots
+            }
+            st.lse2 = mx2 + log2f(sum);
         } else {
             st.lse2 = ok ? __ldg(ep.lse + cx.row) * kLog2e : CUDART_INF_F;
         }
@@ -274,9 +323,10 @@ struct DlogitsEpi {
         const float4* cv = reinterpret_cast<const float4*>(cx.cv);
         const int lane = threadIdx.x & 31;
         const int row_base = cx.row - lane;
+        const uint32_t stage = smem_u32(cx.scratch);
         for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
             const int col = cx.col0 + c * 32;
-            if (col >= ep.Vp) return;                           // warp-uniform: Vp is a multiple of 32
+            if (col >= ep.Vp) return;                           // warp-uniform: Vp is a multiple of 64
             float g[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -294,21 +344,33 @@ struct DlogitsEpi {
             __nv_bfloat162 o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = __floats2bfloat162_rn(g[2 * j], g[2 * j + 1]);
-            uint4* srow = reinterpret_cast<uint4*>(cx.scratch + lane * 80);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) srow[i] = *reinterpret_cast<uint4*>(&o[4 * i]);
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int rr = 8 * k + (lane >> 2), piece = lane & 3;
-                const uint4 v = *reinterpret_cast<const uint4*>(cx.scratch + rr * 80 + piece * 16);
-                if (row_base + rr < ep.M)
-                    *reinterpret_cast<uint4*>(ep.p + (size_t)(row_base + rr) * ep.p_pitch + col + piece * 8) = v;
+            if ((c & 1) == 0) {                             // the previous store must have read the tile
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
             }
-            __syncwarp();
+            const uint32_t rowaddr = stage + (uint32_t)lane * 128u;
+            const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t piece = (uint32_t)((c & 1) * 4 + i) ^ sw;
+                const uint4 v = *reinterpret_cast<uint4*>(&o[4 * i]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                             ::"r"(rowaddr + piece * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+            if (c & 1) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&ep.tmap_p, stage, col - 32, row_base);
+                    tma_store_commit();
+                }
+            }
         });
     }
-    static __device__ __forceinline__ void end_rb(State&, const Params&, const TileCtx&) {}
+    static __device__ __forceinline__ void end_rb(State&, const Params&, const TileCtx&) {
+        // the staging tile must stay valid until the last store has read it (the CTA may exit right after this)
+        if ((threadIdx.x & 31) == 0) tma_store_wait_read();
+    }
 };
 
 // ------------------------------------------------------------------------------------------------ small kernels
@@ -377,11 +439,13 @@ ce_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps, c
 // (fp32 accumulation); one warp per masked row.
 __global__ void __launch_bounds__(256)
 ce_label_logit_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ wb, const float* __restrict__ bias,
-                      const int* __restrict__ lab, int M, int Dhp, float* __restrict__ zl) {
+                      const int* __restrict__ rows, const long long* __restrict__ labels, int M, int V, int Dhp, int packed,
+                      float* __restrict__ zl) {
     const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (m >= M) return;
-    const int label = __ldg(lab + m);
+    const int label = masked_label(labels, rows, m, M, V, packed);
+    if (label < 0) { if (lane == 0) zl[m] = CUDART_NAN_F; return; }      // outside [0, V): never index W with it
     const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(a + (size_t)m * Dhp);
     const __nv_bfloat162* w = reinterpret_cast<const __nv_bfloat162*>(wb + (size_t)label * Dhp);
     float acc = 0.f;
@@ -509,9 +573,17 @@ ce_dh_scatter_kernel(const float* __restrict__ planes, const int* __restrict__ i
         const long long i = n * g4 + g;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m >= 0) {
-            for (int k = 0; k < KS; ++k) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(planes + ((size_t)k * M + m) * Dh) + g);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            // all plane loads of a group of 8 are in flight before the (fixed-order) adds
+            for (int k0 = 0; k0 < KS; k0 += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    v[k] = (k0 + k < KS) ? __ldg(reinterpret_cast<const float4*>(planes + ((size_t)(k0 + k) * M + m) * Dh) + g)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k0 + k < KS) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+                }
             }
         }
         if constexpr (sizeof(T) == 4) {
@@ -608,15 +680,28 @@ struct MaskPred {
 };
 
 template <typename T>
-int launch_ce_gather(const void* h, const int32_t* rows, const int64_t* labels, long long N, int M, int Dh, const CeWsLayout& l,
-                     char* ws, cudaStream_t stream) {
-    (void)N;
-    ce_gather_kernel<T><<<(unsigned)((l.Mpad + 7) / 8), 256, 0, stream>>>(
-        static_cast<const T*>(h), rows, reinterpret_cast<const long long*>(labels), M, Dh, (int)l.Dhp, (int)l.Mpad,
-        reinterpret_cast<__nv_bfloat16*>(ws + l.a_off), reinterpret_cast<int*>(ws + l.lab_off),
+int launch_ce_gather(const void* h, const int32_t* rows, int M, int Dh, const CeWsLayout& l, char* ws, cudaStream_t stream) {
+    ce_gather_kernel<T><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
+        static_cast<const T*>(h), rows, M, Dh, (int)l.Dhp, reinterpret_cast<__nv_bfloat16*>(ws + l.a_off),
         reinterpret_cast<int*>(ws + l.inv_off), reinterpret_cast<unsigned int*>(ws + l.ticket_off));
     return (int)cudaGetLastError();
 }
+inline int ce_gather(const void* h, int h_is_bf16, const int32_t* rows, int M, int Dh, const CeWsLayout& l, char* ws,
+                     cudaStream_t stream) {
+    return h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, M, Dh, l, ws, stream)
+                     : launch_ce_gather<float>(h, rows, M, Dh, l, ws, stream);
+}
+
+// The logits GEMMs keep the masked rows resident in shared memory while the label tiles stream by when the hidden
+// dimension allows it (Dh <= 512: 8 k-blocks = 128 KB); wider heads stream both operands through the ring.
+template <class Epi>
+int launch_logits_gemm(const void* a, int M, int Dhp, const void* w, int vlen, int split_mode, int fixed_s,
+                       const typename Epi::Params& ep, cudaStream_t st, size_t budget, int pdl) {
+    if (Dhp / kBlockK <= 8)
+        return launch_gemm_tn<2, 1, Epi>(a, M, Dhp, w, vlen, Dhp, Dhp, 1, split_mode, fixed_s, 0, ep, st, nullptr, budget, 0, pdl);
+    return launch_gemm_tn<2, 0, Epi>(a, M, Dhp, w, vlen, Dhp, Dhp, 1, split_mode, fixed_s, 0, ep, st, nullptr, budget, 0, pdl);
+}
+
 
 }  // namespace pero
 
@@ -637,11 +722,11 @@ int pero_head_prepare(const float* W, const float* bias, int64_t V, int64_t Dh, 
     if (head_bytes < l.total) return PERO_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(head) & 255) return PERO_ERR_BAD_ALIGN;
     char* base = static_cast<char*>(head);
-    dim3 grid((unsigned)(l.Vt / 32), (unsigned)(l.Dhp / 32));
-    head_prepare_kernel<<<grid, 256, 0, stream>>>(W, bias, (int)V, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.Vt,
-                                                  reinterpret_cast<__nv_bfloat16*>(base + l.w_off),
-                                                  reinterpret_cast<__nv_bfloat16*>(base + l.wt_off),
-                                                  reinterpret_cast<float*>(base + l.bias_off));
+    long long blocks = ((long long)V * (l.Dhp / 4) + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    head_prepare_kernel<<<(unsigned)blocks, 256, 0, stream>>>(W, bias, (int)V, (int)Dh, (int)l.Dhp, (int)l.Vt,
+                                                            reinterpret_cast<__nv_bfloat16*>(base + l.w_off),
+                                                            reinterpret_cast<float*>(base + l.bias_off));
     return (int)cudaGetLastError();
 }
 
@@ -653,52 +738,87 @@ size_t pero_masked_ce_workspace_bytes(int64_t N, int64_t M, int64_t V, int64_t D
 static int ce_check(const void* h, int64_t N, int64_t Dh, const int32_t* rows, int64_t M, const int64_t* labels,
                     const void* head, int64_t V, void* workspace, size_t workspace_bytes, bool h_optional = false) {
     if ((!h && !h_optional) || !rows || !labels || !head || !workspace) return PERO_ERR_NULL;
-    if (N <= 0 || M <= 0 || M > N || V <= 0 || Dh <= 0 || N > (1ll << 31) - 256 || V > (1ll << 24) || Dh > 512)
-        return PERO_ERR_BAD_SHAPE;   // Dh <= 512: the masked rows stay resident in shared memory for the sweep
+    if (N <= 0 || M <= 0 || M > N || V <= 0 || Dh <= 0 || N > (1ll << 31) - 256 || V > (1ll << 24) || Dh > 16384)
+        return PERO_ERR_BAD_SHAPE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(head) & 255)) return PERO_ERR_BAD_ALIGN;
     if (workspace_bytes < ce_ws_layout(N, M, V, Dh).total) return PERO_ERR_WORKSPACE;
     return PERO_OK;
 }
 
-int pero_masked_ce_fwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+int pero_masked_ce_gather(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M, int64_t V,
+                          void* workspace, size_t workspace_bytes, pero_stream_t stream) {
+    if (M == 0) return PERO_ERR_BAD_SHAPE;
+    if (!h || !rows || !workspace) return PERO_ERR_NULL;
+    if (N <= 0 || M < 0 || M > N || V <= 0 || Dh <= 0 || N > (1ll << 31) - 256 || Dh > 16384) return PERO_ERR_BAD_SHAPE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return PERO_ERR_BAD_ALIGN;
+    const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
+    if (workspace_bytes < l.total) return PERO_ERR_WORKSPACE;
+    return ce_gather(h, h_is_bf16, rows, (int)M, (int)Dh, l, static_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pero_masked_ce_fwd(const void* h, int flags, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
                        const int64_t* labels, const void* head, int64_t V, float* loss_sum, float* lse,
                        void* workspace, size_t workspace_bytes, pero_stream_t stream) {
     if (M == 0) return PERO_ERR_BAD_SHAPE;   // the reference returns NaN on an empty mask; the host wrapper handles it
-    int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes);
+    const int h_is_bf16 = flags & PERO_CE_H_BF16, packed = (flags & PERO_CE_LABELS_PACKED) ? 1 : 0;
+    int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes, /*h_optional=*/true);
     if (rc) return rc;
-    if (!loss_sum || !lse) return PERO_ERR_NULL;
+    if ((loss_sum == nullptr) != (lse == nullptr)) return PERO_ERR_NULL;      // both (finalize now) or neither (pero_masked_ce_loss later)
     const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
     const HeadLayout hl = head_layout(V, Dh);
     char* ws = static_cast<char*>(workspace);
     const char* hb = static_cast<const char*>(head);
-    // The gather also leaves A^T and the inverse row map in the workspace: a backward call that is handed the
-    // same workspace (h = NULL) starts directly with its GEMM.
-    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream)
-                   : launch_ce_gather<float>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream);
-    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // The gather leaves the bf16 operand A and the inverse row map in the workspace: a backward call that is handed
+    // the same workspace (h = NULL) starts directly with its GEMM.  h == NULL here: pero_masked_ce_gather already ran
+    // on this workspace for the same (h, rows).
+    if (h) {
+        rc = ce_gather(h, h_is_bf16, rows, (int)M, (int)Dh, l, ws, st);
+        if (rc) return rc;
+    }
     LseEpi::Params ep;
     ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
-    ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
+    ep.rows = rows; ep.labels = reinterpret_cast<const long long*>(labels);
     ep.pm = reinterpret_cast<float*>(ws + l.pm_off);
     ep.ps = reinterpret_cast<float*>(ws + l.ps_off);
     ep.zlab = reinterpret_cast<float*>(ws + l.zlab_off);
-    ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S;
-    rc = launch_gemm_tn<2, true, LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
-                                         /*split_mode=*/1, (int)l.S, 0, ep, reinterpret_cast<cudaStream_t>(stream), nullptr,
-                                         kSmemBudgetShared, 0, /*pdl=*/4);
-    if (rc) return rc;
+    ep.zl_in = nullptr; ep.pcnt = nullptr;
+    ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S; ep.V = (int)V; ep.packed = packed;
+    // behind its own gather: the set-up overlaps the gather, the first load waits for it (programmatic launch); the
+    // kernel behind is released when the last operand load of a CTA has been requested (bit 4)
+    rc = launch_logits_gemm<LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, /*split_mode=*/1, (int)l.S, ep, st,
+                                    kSmemBudgetShared, (h ? 4 : 0) | 16);
+    if (rc || !lse) return rc;
+    // lse / rowloss / loss_sum from the partials.  A backward GEMM launched right behind on the same workspace rebuilds
+    // the log-sum-exp from the partials itself and never reads this kernel's output.
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
-    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
-                                                                rowloss, reinterpret_cast<unsigned int*>(ws + l.ticket_off),
-                                                                loss_sum);
+    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
+                                                              rowloss, reinterpret_cast<unsigned int*>(ws + l.ticket_off),
+                                                              loss_sum);
     return (int)cudaGetLastError();
 }
 
-int pero_masked_ce_eval(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+int pero_masked_ce_loss(int64_t N, int64_t Dh, int64_t M, int64_t V, float* loss_sum, float* lse, void* workspace,
+                        size_t workspace_bytes, pero_stream_t stream) {
+    if (!loss_sum || !lse || !workspace) return PERO_ERR_NULL;
+    if (N <= 0 || M <= 0 || M > N || V <= 0 || Dh <= 0) return PERO_ERR_BAD_SHAPE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return PERO_ERR_BAD_ALIGN;
+    const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
+    if (workspace_bytes < l.total) return PERO_ERR_WORKSPACE;
+    char* ws = static_cast<char*>(workspace);
+    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(
+        reinterpret_cast<const float*>(ws + l.pm_off), reinterpret_cast<const float*>(ws + l.ps_off),
+        reinterpret_cast<const float*>(ws + l.zlab_off), (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
+        reinterpret_cast<float*>(ws + l.rowloss_off), reinterpret_cast<unsigned int*>(ws + l.ticket_off), loss_sum);
+    return (int)cudaGetLastError();
+}
+
+int pero_masked_ce_eval(const void* h, int flags, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
                         const int64_t* labels, const void* head, int64_t V, const int32_t* topk_host, int num_topk,
                         float* loss_sum, float* lse, int32_t* rank, int64_t* errors, void* workspace, size_t workspace_bytes,
                         pero_stream_t stream) {
     if (M == 0) return PERO_ERR_BAD_SHAPE;
+    const int h_is_bf16 = flags & PERO_CE_H_BF16;
     int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes);
     if (rc) return rc;
     if (!loss_sum || !lse || !errors || !topk_host) return PERO_ERR_NULL;
@@ -713,24 +833,23 @@ int pero_masked_ce_eval(const void* h, int h_is_bf16, int64_t N, int64_t Dh, con
     const char* hb = static_cast<const char*>(head);
     cudaError_t e = cudaMemsetAsync(errors, 0, (size_t)num_topk * 8, stream);
     if (e != cudaSuccess) return (int)e;
-    rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream)
-                   : launch_ce_gather<float>(h, rows, labels, N, (int)M, (int)Dh, l, ws, stream);
+    rc = ce_gather(h, h_is_bf16, rows, (int)M, (int)Dh, l, ws, stream);
     if (rc) return rc;
     EvalEpi::Params ep;
     ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
-    ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
+    ep.rows = rows; ep.labels = reinterpret_cast<const long long*>(labels); ep.V = (int)V;
     ep.pm = reinterpret_cast<float*>(ws + l.pm_off);
     ep.ps = reinterpret_cast<float*>(ws + l.ps_off);
     ep.zlab = reinterpret_cast<float*>(ws + l.zlab_off);
     float* zl_in = reinterpret_cast<float*>(ws + l.zlin_off);
     ep.zl_in = zl_in;
     ep.pcnt = reinterpret_cast<int*>(ws + l.pcnt_off);
-    ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S;
+    ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S; ep.packed = (flags & PERO_CE_LABELS_PACKED) ? 1 : 0;
     ce_label_logit_kernel<<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(ws + l.a_off), reinterpret_cast<const __nv_bfloat16*>(hb + hl.w_off), ep.colvec,
-        ep.lab, (int)M, (int)l.Dhp, zl_in);
-    rc = launch_gemm_tn<2, true, EvalEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, (int)l.Dhp, (int)l.Dhp, 1,
-                                          /*split_mode=*/1, (int)l.S, 0, ep, stream, nullptr, kSmemBudgetShared, 0, /*pdl=*/0);
+        rows, ep.labels, (int)M, (int)V, (int)l.Dhp, ep.packed, zl_in);
+    rc = launch_logits_gemm<EvalEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, /*split_mode=*/1, (int)l.S, ep, stream,
+                                     kSmemBudgetShared, /*pdl=*/0);
     if (rc) return rc;
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
     ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
@@ -741,11 +860,12 @@ int pero_masked_ce_eval(const void* h, int h_is_bf16, int64_t N, int64_t Dh, con
     return (int)cudaGetLastError();
 }
 
-int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
                              const int64_t* labels, const void* head, int64_t V, const float* lse,
                              const float* grad_scale, float inv_count, int64_t v_begin, int64_t v_end, void* d_h, float* d_W,
                              float* d_b, void* workspace, size_t workspace_bytes, pero_stream_t stream) {
     if (M == 0) return PERO_ERR_BAD_SHAPE;
+    const int h_is_bf16 = flags & PERO_CE_H_BF16, packed = (flags & PERO_CE_LABELS_PACKED) ? 1 : 0;
     int rc = ce_check(h, N, Dh, rows, M, labels, head, V, workspace, workspace_bytes, /*h_optional=*/true);
     if (rc) return rc;
     // h == NULL: the workspace is the one pero_masked_ce_fwd ran on for the same (h, rows, labels) and still holds
@@ -755,7 +875,7 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
     //                      of d_W and d_b; then, if d_h is given too (requires the full range), d_h
     //   d_W == d_b == NULL, d_h given -> d_h from the P that earlier calls left in the SAME workspace for ALL columns
     const bool dh_only = (!d_W && !d_b && d_h);
-    if (!lse || (!dh_only && (!d_W || !d_b))) return PERO_ERR_NULL;
+    if ((!lse && h) || (!dh_only && (!d_W || !d_b))) return PERO_ERR_NULL;      // h == NULL: the log-sum-exp comes from the forward's partials
     if (Dh % 4 != 0) return PERO_ERR_BAD_SHAPE;
     if (v_begin < 0 || v_end > V || v_begin >= v_end || (v_begin % 256) != 0 || (v_end != V && (v_end % 256) != 0))
         return PERO_ERR_BAD_SHAPE;
@@ -781,51 +901,68 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
     const int half_workers = device_sm_count() / 4;
     if (!dh_only) {
         if (h && v_begin == 0) {
-            rc = h_is_bf16 ? launch_ce_gather<__nv_bfloat16>(h, rows, labels, N, (int)M, (int)Dh, l, ws, st)
-                           : launch_ce_gather<float>(h, rows, labels, N, (int)M, (int)Dh, l, ws, st);
+            rc = ce_gather(h, h_is_bf16, rows, (int)M, (int)Dh, l, ws, st);
             if (rc) return rc;
         }
         const int64_t vlen = v_end - v_begin;
-        DlogitsEpi::Params ep;
-        ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off) + v_begin;
-        ep.lab = reinterpret_cast<const int*>(ws + l.lab_off);
-        ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
-        // Directly behind the forward on the same workspace (h == NULL, first range): the log-sum-exp comes from the
-        // forward's partials, so this GEMM need not wait for ce_finalize_kernel (released by it at once; waits for it
-        // before exiting).  Behind its own gather: set-up overlaps the gather, then waits for it.
-        // (every label range of a backward on the forward's workspace uses the partials, so that walking the label
-        // axis range by range gives the same bits as one call)
+        const int64_t vp_range = (v_end == V ? l.Vp - v_begin : vlen);      // the last range also writes P's zero padding columns
+        // Directly behind the forward on the same workspace (h == NULL): the log-sum-exp comes from the forward's partials
+        // (every label range of such a backward uses them, so that walking the label axis range by range gives the same
+        // bits as one call), and this GEMM need not wait for ce_finalize_kernel: it is released by it at once and only
+        // waits for it before exiting.  Behind its own gather: the set-up overlaps the gather, then waits for it.
         const bool from_partials = (h == nullptr);
-        ep.pm = from_partials ? reinterpret_cast<const float*>(ws + l.pm_off) : nullptr;
-        ep.ps = from_partials ? reinterpret_cast<const float*>(ws + l.ps_off) : nullptr;
-        ep.slots = 2 * (int)l.S; ep.Mpad = (int)l.Mpad;
-        const int dl_pdl = (!pdl_on || v_begin != 0) ? 0 : (from_partials ? 2 : 4);
-        ep.p = P + v_begin; ep.M = (int)M;
-        ep.Vp = (int)(v_end == V ? l.Vp - v_begin : vlen);      // the last range also writes P's zero padding columns
-        ep.p_pitch = (int)l.Pp; ep.col_base = (int)v_begin;
-        rc = launch_gemm_tn<2, true, DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off + (size_t)v_begin * l.Dhp * 2,
-                                                 (int)vlen, (int)l.Dhp, (int)l.Dhp, 1, 0, 1, 0, ep, st, nullptr, kSmemBudgetShared,
-                                                 0, dl_pdl);
+        // the set-up overlaps the tail of the kernel in front (this call's gather, or the forward's GEMM / finalize,
+        // which release their successor early); the first global access waits for it
+        const int dl_pdl = (!pdl_on || v_begin != 0) ? 0 : 4;
+        auto fill = [&](auto& ep) {
+            ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off) + v_begin;
+            ep.rows = rows; ep.labels = reinterpret_cast<const long long*>(labels); ep.V = (int)V; ep.packed = packed;
+            ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
+            ep.pm = from_partials ? reinterpret_cast<const float*>(ws + l.pm_off) : nullptr;
+            ep.ps = from_partials ? reinterpret_cast<const float*>(ws + l.ps_off) : nullptr;
+            ep.slots = 2 * (int)l.S; ep.Mpad = (int)l.Mpad;
+            ep.p = P + v_begin; ep.M = (int)M;
+            ep.Vp = (int)vp_range;
+            ep.p_pitch = (int)l.Pp; ep.col_base = (int)v_begin;
+        };
+        const void* wslice = hb + hl.w_off + (size_t)v_begin * l.Dhp * 2;
+        {
+            DlogitsEpi::Params ep;
+            fill(ep);
+            // store descriptor of P[:, v_begin : v_begin + vp_range]: boxes of {64 columns, 32 rows}, clipped at M rows
+            rc = make_tmap_bf16(&ep.tmap_p, P + v_begin, (uint64_t)M, (uint64_t)vp_range, (uint64_t)l.Pp, 32);
+            if (rc) return rc;
+            rc = launch_logits_gemm<DlogitsEpi>(ws + l.a_off, (int)M, (int)l.Dhp, wslice, (int)vlen, 0, 1, ep, st, kSmemBudget, dl_pdl);
+        }
         if (rc) return rc;
-
 
         // d_W [v_begin:v_end, Dh] = P[:, v_begin:v_end]^T @ A: both operands are read as stored (rows = masked
         // frames = the contraction index) through MN-major descriptors; no transposed copy of either exists.
+        const bool store_tma = PERO_KNOB("PERO_STORE_TMA", 1) != 0;
+        StoreTmaEpi::Params swt;
+        const bool dw_tma = store_tma && store_pairs &&
+                            make_tmap_f32_store(&swt.tmap_out, d_W + (size_t)v_begin * Dh, 1, (uint64_t)vlen, (uint64_t)Dh, (uint64_t)Dh,
+                                                (uint64_t)vlen * Dh) == PERO_OK;
         StoreEpi::Params sw;
         sw.out = d_W + (size_t)v_begin * Dh; sw.ld = Dh; sw.split_stride = 0; sw.rows = (int)vlen; sw.cols = (int)Dh;
-        rc = store_pairs
-                 ? launch_gemm_tn<2, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp,
-                                                            (int)l.Mp64, 1, 0, 1, side_by_side ? half_workers : 0, sw, st, nullptr,
-                                                            kSmemBudgetShared, (int)M, (side_by_side || pdl_on) ? 1 : 0)
-                 : launch_gemm_tn<1, false, StoreEpi, true>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp,
-                                                            (int)l.Mp64, 1, 0, 1, 0, sw, st, nullptr, kSmemBudgetShared, (int)M);
+        const int dw_workers = side_by_side ? half_workers : 0;
+        const int dw_pdl = (side_by_side || pdl_on) ? 1 : 0;
+        if (dw_tma)
+            rc = launch_gemm_tn<2, 0, StoreTmaEpi, 3>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp, (int)l.Mp64,
+                                                         1, 0, 1, dw_workers, swt, st, nullptr, kSmemBudgetShared, (int)M, dw_pdl);
+        else if (store_pairs)
+            rc = launch_gemm_tn<2, 0, StoreEpi, 3>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp, (int)l.Mp64,
+                                                      1, 0, 1, dw_workers, sw, st, nullptr, kSmemBudgetShared, (int)M, dw_pdl);
+        else
+            rc = launch_gemm_tn<1, 0, StoreEpi, 3>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp, (int)l.Mp64,
+                                                      1, 0, 1, 0, sw, st, nullptr, kSmemBudgetShared, (int)M);
         if (rc) return rc;
         // d_b: partial column sums of P now, unless the side-by-side schedule below runs them beside the GEMMs; the
         // final sums on their own when this call stops after d_W | d_b (they are exchanged next), otherwise by the
         // leading blocks of the scatter launch
         if (!side_by_side) {
             // beside the d_W GEMM (released by it at once, waits for it before exiting) when PDL is on
-            const int vlen8 = (int)((v_end == V ? l.Vp - v_begin : vlen) / 8);      // P's padding columns are zeros
+            const int vlen8 = (int)(vp_range / 8);      // P's padding columns are zeros
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)db_nparts); cfg.blockDim = dim3(256); cfg.stream = st;
             cudaLaunchAttribute at[1];
@@ -843,16 +980,30 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
 
     bool scatter_masked_only = false;
     if (d_h) {
-        // planes[ks] [M, Dh] = P [M, Vp] @ W^T [Dh, Vp]^T over the ks-th slice of the label axis
+        // planes[ks] [M, Dh] = P [M, Vp] @ W [V, Dh] over the ks-th slice of the label axis: P is the K-major operand, the
+        // head's one bf16 copy is read MN-major (boxes of {64 hidden channels, 64 labels}; labels beyond V read as zero)
         float* planes = reinterpret_cast<float*>(ws + l.planes_off);
+        // the number of planes actually produced is recomputed exactly as launch_gemm_tn does
+        const int dh_num_kb = (int)(l.Vp / 64);
+        const int dh_kb_per = (dh_num_kb + (int)l.KS - 1) / (int)l.KS;
+        const int dh_planes = (dh_num_kb + dh_kb_per - 1) / dh_kb_per;
+        StoreTmaEpi::Params sht;
+        const bool dh_tma = PERO_KNOB("PERO_STORE_TMA", 1) != 0 && store_pairs &&
+                            make_tmap_f32_store(&sht.tmap_out, planes, (uint64_t)dh_planes, (uint64_t)M, (uint64_t)Dh, (uint64_t)Dh,
+                                                (uint64_t)M * Dh) == PERO_OK;
         StoreEpi::Params sh;
         sh.out = planes; sh.ld = Dh; sh.split_stride = (long long)M * Dh; sh.rows = (int)M; sh.cols = (int)Dh;
-        rc = store_pairs
-                 ? launch_gemm_tn<2, false, StoreEpi>(P, (int)M, (int)l.Pp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
-                                                      1, side_by_side ? half_workers : 0, sh, st, nullptr, kSmemBudgetShared, 0,
-                                                      side_by_side ? 3 : 0)
-                 : launch_gemm_tn<1, false, StoreEpi>(P, (int)M, (int)l.Pp, hb + hl.wt_off, (int)Dh, (int)l.Vp, (int)l.Vp, (int)l.KS, 0,
-                                                      1, 0, sh, st, nullptr, kSmemBudgetShared);
+        const int dh_workers = side_by_side ? half_workers : 0;
+        const int dh_pdl = side_by_side ? 3 : 0;
+        if (dh_tma)
+            rc = launch_gemm_tn<2, 0, StoreTmaEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.KS, 0, 1,
+                                                      dh_workers, sht, st, nullptr, kSmemBudgetShared, (int)V, dh_pdl);
+        else if (store_pairs)
+            rc = launch_gemm_tn<2, 0, StoreEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.KS, 0, 1,
+                                                   dh_workers, sh, st, nullptr, kSmemBudgetShared, (int)V, dh_pdl);
+        else
+            rc = launch_gemm_tn<1, 0, StoreEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.KS, 0, 1, 0,
+                                                   sh, st, nullptr, kSmemBudgetShared, (int)V);
         if (rc) return rc;
         if (side_by_side) {
             // third member of the side-by-side group: released by the d_h GEMM as soon as that one has started
@@ -876,10 +1027,9 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
         if (blocks > 148 * 16) blocks = 148 * 16;
         const int db_blocks = dh_only ? 0 : (int)((V + 31) / 32);
         blocks += db_blocks;
-        // the number of planes actually produced is recomputed exactly as launch_gemm_tn does
-        const int num_kb = (int)(l.Vp / 64);
-        const int kb_per = (num_kb + (int)l.KS - 1) / (int)l.KS;
-        const int ks_eff = (num_kb + kb_per - 1) / kb_per;
+        const int ks_eff = dh_planes;
+        // (a plain launch on purpose: released programmatically, the ~800 CTAs of this grid park on every SM until
+        // the GEMMs in front are done and starve the kernels of the other chains -- measured, round 2)
         if (h_is_bf16)
             ce_dh_scatter_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(planes, inv, rows, N, (int)M, (int)Dh, ks_eff,
                                                                                  static_cast<__nv_bfloat16*>(d_h), db_blocks, dbpart,
@@ -893,11 +1043,11 @@ int pero_masked_ce_bwd_range(const void* h, int h_is_bf16, int64_t N, int64_t Dh
     return (int)cudaGetLastError();
 }
 
-int pero_masked_ce_bwd(const void* h, int h_is_bf16, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
+int pero_masked_ce_bwd(const void* h, int flags, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
                        const int64_t* labels, const void* head, int64_t V, const float* lse,
                        const float* grad_scale, float inv_count, void* d_h, float* d_W, float* d_b,
                        void* workspace, size_t workspace_bytes, pero_stream_t stream) {
-    return pero_masked_ce_bwd_range(h, h_is_bf16, N, Dh, rows, M, labels, head, V, lse, grad_scale, inv_count, 0, V, d_h, d_W,
+    return pero_masked_ce_bwd_range(h, flags, N, Dh, rows, M, labels, head, V, lse, grad_scale, inv_count, 0, V, d_h, d_W,
                                     d_b, workspace, workspace_bytes, stream);
 }
 

@@ -119,18 +119,22 @@ int run_assign_gemm(const __nv_bfloat16* xb, long long N, int Dp, const Codebook
     ep.packed = packed; ep.rows = (int)N; ep.index_offset = index_offset;
     const void* cb = static_cast<const char*>(codebook) + cl.cb_off;
     const int v = assign_variant_default(Dp / kBlockK);
-    // Short contractions (D <= 256) leave room for a 7-deep ring inside the budget that keeps 27 KB of shared memory
-    // free for a co-resident bandwidth-bound CTA of another chain; long ones take the whole SM.
-    const size_t budget = (Dp / kBlockK <= 4) ? kSmemBudgetShared : kSmemBudget;
+    // Short contractions (D <= 256): two resident A sets, so that the next row block's frames are loaded while the
+    // current block is still being multiplied (a worker changes row block every 32 column tiles at K = 8192).
+    const bool dbl = (v & 2) && (Dp / kBlockK <= 4) && PERO_KNOB("PERO_A_DOUBLE", 1) != 0;
+    const size_t budget = dbl ? kSmemBudget : ((Dp / kBlockK <= 4) ? kSmemBudgetShared : kSmemBudget);
     switch (v & 3) {
-        case 0: return launch_gemm_tn<1, false, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
-                                                                budget, 0, pdl);
-        case 1: return launch_gemm_tn<2, false, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
-                                                                budget, 0, pdl);
-        case 2: return launch_gemm_tn<1, true, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
-                                                                budget, 0, pdl);
-        default: return launch_gemm_tn<2, true, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
-                                                                budget, 0, pdl);
+        case 0: return launch_gemm_tn<1, 0, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
+                                                            budget, 0, pdl);
+        case 1: return launch_gemm_tn<2, 0, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
+                                                            budget, 0, pdl);
+        case 2: return launch_gemm_tn<1, 1, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
+                                                            budget, 0, pdl);
+        default:
+            if (dbl) return launch_gemm_tn<2, 2, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
+                                                             budget, 0, pdl);
+            return launch_gemm_tn<2, 1, ArgminEpi>(xb, (int)N, Dp, cb, (int)K, Dp, Dp, 1, 0, 1, 0, ep, stream, nullptr,
+                                                    budget, 0, pdl);
     }
 }
 
@@ -216,7 +220,8 @@ int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
-    int rc = run_assign_gemm(xb, N, Dp, cl, codebook, K, (int)index_offset, packed, (cudaStream_t)stream, /*pdl=*/4);
+    int rc = run_assign_gemm(xb, N, Dp, cl, codebook, K, (int)index_offset, packed, (cudaStream_t)stream,
+                             /*pdl=*/PERO_KNOB("PERO_ASSIGN_EARLY_B", 1) ? 12 : 4);
     if (rc) return rc;
     if (!packed_io && (idx || dmin)) {
         unpack_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(packed, N, reinterpret_cast<long long*>(idx), dmin);
@@ -257,25 +262,25 @@ int pero_gemm_tn_bf16(const void* a_bf16, int64_t rows_a, const void* b_bf16, in
         NullEpi::Params np; np.out = nullptr;
         unsigned long long* tl = reinterpret_cast<unsigned long long*>(out);
         const bool pair = variant & 1, res = variant & 2;
-        if (pair && res) return launch_gemm_tn<2, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
-        if (pair) return launch_gemm_tn<2, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
-        if (res) return launch_gemm_tn<1, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
-        return launch_gemm_tn<1, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
+        if (pair && res) return launch_gemm_tn<2, 1, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
+        if (pair) return launch_gemm_tn<2, 0, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
+        if (res) return launch_gemm_tn<1, 1, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
+        return launch_gemm_tn<1, 0, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream, tl);
     }
     if (variant & 12) {          // measurement only: bit2 = no TMEM reads at all, bit3 = TMEM reads without math
         NullEpi::Params np; np.out = out;
         LoadEpi::Params lp; lp.out = out;
         const bool pair = variant & 1, res = variant & 2, load = variant & 8;
         if (load) {
-            if (pair && res) return launch_gemm_tn<2, true, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
-            if (pair) return launch_gemm_tn<2, false, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
-            if (res) return launch_gemm_tn<1, true, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
-            return launch_gemm_tn<1, false, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
+            if (pair && res) return launch_gemm_tn<2, 1, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
+            if (pair) return launch_gemm_tn<2, 0, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
+            if (res) return launch_gemm_tn<1, 1, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
+            return launch_gemm_tn<1, 0, LoadEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, lp, stream);
         }
-        if (pair && res) return launch_gemm_tn<2, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
-        if (pair) return launch_gemm_tn<2, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
-        if (res) return launch_gemm_tn<1, true, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
-        return launch_gemm_tn<1, false, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
+        if (pair && res) return launch_gemm_tn<2, 1, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
+        if (pair) return launch_gemm_tn<2, 0, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
+        if (res) return launch_gemm_tn<1, 1, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
+        return launch_gemm_tn<1, 0, NullEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, np, stream);
     }
 #else
     if (variant & (4 | 8 | 16)) return PERO_ERR_UNSUPPORTED;      // measurement variants exist in the dev build only
@@ -283,16 +288,16 @@ int pero_gemm_tn_bf16(const void* a_bf16, int64_t rows_a, const void* b_bf16, in
     if (variant & 32) {          // MN-major operands: a is [kd, rows_a], b is [kd, rows_b]; out = a^T b
         const int kp = (k + 63) / 64 * 64;
         if (variant & 1)
-            return launch_gemm_tn<2, false, StoreEpi, true>(a_bf16, ra, ra, b_bf16, rb, rb, kp, num_splits, 0, 1, 0, ep, stream,
+            return launch_gemm_tn<2, 0, StoreEpi, 3>(a_bf16, ra, ra, b_bf16, rb, rb, kp, num_splits, 0, 1, 0, ep, stream,
                                                             nullptr, kSmemBudget, k);
-        return launch_gemm_tn<1, false, StoreEpi, true>(a_bf16, ra, ra, b_bf16, rb, rb, kp, num_splits, 0, 1, 0, ep, stream, nullptr,
+        return launch_gemm_tn<1, 0, StoreEpi, 3>(a_bf16, ra, ra, b_bf16, rb, rb, kp, num_splits, 0, 1, 0, ep, stream, nullptr,
                                                         kSmemBudget, k);
     }
     switch (variant & 3) {
-        case 0: return launch_gemm_tn<1, false, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, num_splits, 0, 1, 0, ep, stream);
-        case 1: return launch_gemm_tn<2, false, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, num_splits, 0, 1, 0, ep, stream);
-        case 2: return launch_gemm_tn<1, true, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, ep, stream);
-        default: return launch_gemm_tn<2, true, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, ep, stream);
+        case 0: return launch_gemm_tn<1, 0, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, num_splits, 0, 1, 0, ep, stream);
+        case 1: return launch_gemm_tn<2, 0, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, num_splits, 0, 1, 0, ep, stream);
+        case 2: return launch_gemm_tn<1, 1, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, ep, stream);
+        default: return launch_gemm_tn<2, 1, StoreEpi>(a_bf16, ra, k, b_bf16, rb, k, k, 1, 0, 1, 0, ep, stream);
     }
 }
 

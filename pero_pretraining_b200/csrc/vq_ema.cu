@@ -1,12 +1,16 @@
 // EMA codebook update (models/autoencoders.py:225-237), deterministic:
-//   1. sort (codeword, frame) pairs by codeword, frames ascending inside a codeword.  Up to 8192 frames
-//      one CTA does it in a single launch with a stable block radix sort (and emits the segment
-//      boundaries); larger batches use CUB's device radix sort (stable as well).
-//   2. chunked segmented sum of the fp32 frame rows in sorted order: every 16 sorted positions form one
-//      chunk; runs that lie inside a chunk are summed and stored directly, runs that cross chunk borders
-//      leave a head/tail partial that a second kernel adds up in chunk order.  No atomics, so the sums
-//      are bit-identical run to run, and a collapsed codebook (one codeword owning every frame, as in
-//      the reference's cold start) still spreads over all SMs.
+//   1. sort (codeword, frame) pairs by codeword, frames ascending inside a codeword.  Up to 8192 frames and
+//      16384 codewords: a stable multi-CTA counting sort in three short launches (per-CTA stable ranks +
+//      histograms, one-CTA scan, placement); otherwise a one-CTA block radix sort (<= 8192 frames) or CUB's
+//      device radix sort (stable as well).
+//   2. segmented sum of the fp32 frame rows in sorted order.  Codewords that own up to kLongSeg frames (all of
+//      them once the codebook is warm) are summed by ONE warp each, which also writes the zero rows of unused
+//      codewords and the counts.  Longer segments (a collapsed codebook: one codeword owning every frame, as in
+//      the reference's cold start) go through the chunked path: every 16 sorted positions form one chunk; runs
+//      that lie inside a chunk are summed and stored directly, runs that cross chunk borders leave a head/tail
+//      partial that a second kernel adds up in chunk order, so that such a segment still spreads over all SMs.
+//      Both launches return at once when no long segment exists.  No float atomics anywhere: the sums are
+//      bit-identical run to run.
 //   3. apply: cluster-size EMA + Laplace smoothing, ema_w EMA, weight = ema_w / size, and refresh of the
 //      bf16 operand + |c|^2 used by the next assign.
 // Row reads/writes are 16-byte vectors, coalesced along D.
@@ -25,9 +29,12 @@ namespace pero {
 constexpr int kChunk = 16;            // sorted positions per chunk
 constexpr int kSmallSortMax = 8192;   // frames handled by the single-CTA sort (8 per thread x 1024 threads)
 constexpr int kClusterBlocks = 64;    // partial sums of the cluster-size reduction
+constexpr int kLongSeg = 64;          // segments longer than this take the chunked path
+constexpr int kRankThreads = 1024;    // frames per CTA of the counting sort
+constexpr int kRankMaxBlocks = kSmallSortMax / kRankThreads;
 
 struct EmaWsLayout {
-    size_t keys_in, keys_out, vals_in, vals_out, seg, partial, cluster_partial, cub, total;
+    size_t keys_in, keys_out, vals_in, vals_out, seg, partial, cluster_partial, hist, excl, btot, flags, cub, total;
     size_t cub_bytes;
 };
 
@@ -49,6 +56,10 @@ inline EmaWsLayout ema_ws_layout(int64_t N, int64_t K, int64_t D) {
     const int64_t chunks = (N + kChunk - 1) / kChunk;
     l.partial = take((size_t)chunks * 2 * D * 4);
     l.cluster_partial = take(kClusterBlocks * 4);
+    l.hist = take(N <= kSmallSortMax ? (size_t)kRankMaxBlocks * K * 4 : 0);    // counting sort: per-CTA histograms / bases
+    l.excl = take(N <= kSmallSortMax ? (size_t)K * 4 : 0);                      // counting sort: scan inside 256-codeword blocks
+    l.btot = take(N <= kSmallSortMax ? (size_t)((K + 255) / 256) * 4 : 0);      // ... and the block sums
+    l.flags = take(256);                                                        // [0] = "a long segment exists"
     size_t cub_bytes = 0;
     if (N > kSmallSortMax) {
         cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
@@ -71,8 +82,9 @@ inline EmaWsLayout ema_ws_layout(int64_t N, int64_t K, int64_t D) {
 template <int ITEMS>
 __global__ void __launch_bounds__(1024)
 ema_sort_small_kernel(const long long* __restrict__ idx, int N, int K, int end_bit, uint32_t* __restrict__ keys_out,
-                      uint32_t* __restrict__ vals_out, int* __restrict__ seg) {
+                      uint32_t* __restrict__ vals_out, int* __restrict__ seg, int* __restrict__ flags) {
     using Sort = cub::BlockRadixSort<uint32_t, 1024, ITEMS, uint32_t>;
+    if (threadIdx.x == 0) flags[0] = 0;
     __shared__ typename Sort::TempStorage temp;
     uint32_t keys[ITEMS], vals[ITEMS];
     const uint32_t sentinel = 1u << (end_bit - 1);          // above every codeword: padding sorts last
@@ -97,19 +109,8 @@ ema_sort_small_kernel(const long long* __restrict__ idx, int N, int K, int end_b
     }
 }
 
-// Single CTA, N <= 8192 frames, K <= kBinSortMaxK codewords: counting sort in shared memory instead of the radix
-// sort above (a third of its time at the bench shape).
-//   1. histogram of the codewords (shared-memory atomics: integer counts, order-free)
-//   2. exclusive scan -> seg[k]
-//   3. every frame takes the next free slot of its codeword's segment (atomic cursor: any order inside a segment)
-//   4. the order inside a segment is then made ascending in the frame index, which is all the stable sort was for:
-//      segments of 2..32 frames by an insertion sort of their owner thread, longer ones (collapsed codebooks: a few
-//      codewords own most frames) by a block-wide ordered compaction of the frames that carry that codeword.
-// Output identical to ema_sort_small_kernel: keys_out / vals_out sorted by (codeword, frame), seg[0..K].
+// The counting sort below handles up to kBinSortMaxK codewords (its per-CTA counters live in shared memory).
 constexpr int kBinSortMaxK = 16384;
-constexpr int kBinSortThreads = 1024;
-constexpr int kBinSortItems = 8;
-constexpr int kBinLongMin = 33;
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -137,84 +138,87 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& 
     return base + incl - v;
 }
 
-__global__ void __launch_bounds__(kBinSortThreads)
-ema_bin_small_kernel(const long long* __restrict__ idx, int N, int K, uint32_t* __restrict__ keys_out,
-                     uint32_t* __restrict__ vals_out, int* __restrict__ seg) {
-    extern __shared__ uint32_t bsm[];
-    uint32_t* cursor = bsm;                         // [K]    counts, then next free slot of every segment
-    uint32_t* vals = bsm + K;                       // [kBinSortThreads * kBinSortItems]
-    uint32_t* start = vals + kBinSortThreads * kBinSortItems;   // [K] first slot of every segment
-    __shared__ int warp_sums[32];
-    __shared__ int long_list[256];
-    __shared__ int n_long;
-    const int t = threadIdx.x;
-    for (int k = t; k < K; k += kBinSortThreads) cursor[k] = 0u;
-    if (t == 0) n_long = 0;
+// ---- stable multi-CTA counting sort (N <= 8192 frames, K <= kBinSortMaxK codewords) -----------------------------------
+// Launch 1, one CTA per 1024 frames (frame i = blockIdx.x * 1024 + threadIdx.x): the stable rank of every frame among
+// the frames of ITS CTA that carry the same codeword, and the CTA's histogram.  Lanes of a warp that share a codeword
+// are found with match.any; the warps then take turns in ascending order, the lowest lane of each group reserving
+// `group size` slots of the codeword's counter in shared memory: ranks ascend with the frame index, no atomics.
+__global__ void __launch_bounds__(kRankThreads)
+ema_rank_kernel(const long long* __restrict__ idx, int N, int K, uint32_t* __restrict__ lrank, uint32_t* __restrict__ hist,
+                int* __restrict__ flags) {
+    extern __shared__ uint32_t cnt[];                 // [K]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int k = t; k < K; k += kRankThreads) cnt[k] = 0u;
+    if (blockIdx.x == 0 && t == 0) flags[0] = 0;      // cleared for ema_rowsum_kernel, two launches later
+    const int i = blockIdx.x * kRankThreads + t;
+    const int key = i < N ? (int)idx[i] : -1 - lane;   // padding lanes: distinct negative keys, groups of one
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(grp) - 1;
+    const int rank_in_warp = __popc(grp & ((1u << lane) - 1u));
+    uint32_t base = 0;
     __syncthreads();
-    int key[kBinSortItems];
+    for (int w = 0; w < kRankThreads / 32; ++w) {
+        if (warp == w && lane == leader && key >= 0) {
+            base = cnt[key];
+            cnt[key] = base + (uint32_t)__popc(grp);
+        }
+        __syncthreads();
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < N) lrank[i] = base + (uint32_t)rank_in_warp;
+    uint32_t* h = hist + (size_t)blockIdx.x * K;
+    for (int k = t; k < K; k += kRankThreads) h[k] = cnt[k];
+}
+
+// Launch 2, one CTA per 256 codewords: total[k] = frames of codeword k over all rank CTAs, its exclusive scan INSIDE the
+// CTA's 256 codewords (excl_local) and the CTA's sum (block_total).  The scan across CTAs (at most 64 values) is
+// finished by whoever needs seg[k]: seg[k] = sum(block_total[0 .. k/256)) + excl_local[k].
+__global__ void __launch_bounds__(256)
+ema_scan_local_kernel(const uint32_t* __restrict__ hist, int nblocks, int K, int* __restrict__ excl_local,
+                      int* __restrict__ block_total) {
+    __shared__ int wsum[8];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int k = blockIdx.x * 256 + t;
+    int total = 0;
+    if (k < K)
+        for (int b = 0; b < nblocks; ++b) total += (int)hist[(size_t)b * K + k];
+    int incl = total;
 #pragma unroll
-    for (int e = 0; e < kBinSortItems; ++e) {
-        const int i = e * kBinSortThreads + t;      // coalesced; frame index ascending in (e, t)
-        key[e] = i < N ? (int)idx[i] : -1;
-        if (key[e] >= 0) atomicAdd(&cursor[key[e]], 1u);
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
     }
+    if (lane == 31) wsum[w] = incl;
     __syncthreads();
-    // exclusive scan over the K bins: thread t owns bins [t * per, (t + 1) * per)
-    const int per = (K + kBinSortThreads - 1) / kBinSortThreads;
-    const int k0 = t * per, k1 = min(K, k0 + per);
-    int local = 0;
-    for (int k = k0; k < k1; ++k) local += (int)cursor[k];
-    int total;
-    int run = block_exclusive_scan(local, warp_sums, total);
-    for (int k = k0; k < k1; ++k) {
-        const int c = (int)cursor[k];
-        seg[k] = run;
-        start[k] = (uint32_t)run;
-        cursor[k] = (uint32_t)run;
-        if (c >= kBinLongMin) { const int s = atomicAdd(&n_long, 1); long_list[s] = k; }    // at most N / 33 < 256 of them
-        run += c;
-    }
-    if (t == 0) seg[K] = N;
-    __syncthreads();
-    // placement (order inside a segment: whatever the atomics give; fixed below)
+    int base = 0;
 #pragma unroll
-    for (int e = 0; e < kBinSortItems; ++e) {
-        if (key[e] >= 0) {
-            const uint32_t pos = atomicAdd(&cursor[key[e]], 1u);
-            vals[pos] = (uint32_t)(e * kBinSortThreads + t);
-            keys_out[pos] = (uint32_t)key[e];
-        }
-    }
-    __syncthreads();
-    // short segments: insertion sort by the bin's owner thread (cursor[k] is now the END of segment k)
-    for (int k = k0; k < k1; ++k) {
-        const int s0 = (int)start[k], s1 = (int)cursor[k], c = s1 - s0;
-        if (c >= 2 && c < kBinLongMin) {
-            for (int a = s0 + 1; a < s1; ++a) {
-                const uint32_t v = vals[a];
-                int b = a - 1;
-                while (b >= s0 && vals[b] > v) { vals[b + 1] = vals[b]; --b; }
-                vals[b + 1] = v;
-            }
-        }
-    }
-    __syncthreads();
-    // long segments: ordered compaction of the frames that carry codeword k, 1024 frames per round
-    const int nl = n_long;
-    for (int j = 0; j < nl; ++j) {
-        const int k = long_list[j];
-        int base = (int)start[k];
-#pragma unroll 1
-        for (int e = 0; e < kBinSortItems; ++e) {
-            const int flag = (key[e] == k) ? 1 : 0;
-            int round_total;
-            const int pre = block_exclusive_scan(flag, warp_sums, round_total);
-            if (flag) vals[base + pre] = (uint32_t)(e * kBinSortThreads + t);
-            base += round_total;
-        }
-    }
-    __syncthreads();
-    for (int p = t; p < N; p += kBinSortThreads) vals_out[p] = vals[p];
+    for (int j = 0; j < 8; ++j) if (j < w) base += wsum[j];
+    if (k < K) excl_local[k] = base + incl - total;
+    if (t == 255) block_total[blockIdx.x] = base + incl;
+}
+
+__device__ __forceinline__ int ema_block_offset(const int* __restrict__ block_total, int j) {
+    int off = 0;
+    for (int i = 0; i < j; ++i) off += __ldg(block_total + i);
+    return off;
+}
+
+// Launch 3: every frame goes to seg[its codeword] + (frames of that codeword in earlier rank CTAs) + its rank; the same
+// threads also publish seg[0 .. K] for the kernels behind.
+__global__ void __launch_bounds__(256)
+ema_place_kernel(const long long* __restrict__ idx, const uint32_t* __restrict__ lrank, const uint32_t* __restrict__ hist,
+                 const int* __restrict__ excl_local, const int* __restrict__ block_total, int N, int K,
+                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int* __restrict__ seg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) seg[i] = ema_block_offset(block_total, i >> 8) + __ldg(excl_local + i);
+    if (i == K) seg[K] = N;
+    if (i >= N) return;
+    const int key = (int)idx[i];
+    int pos = ema_block_offset(block_total, key >> 8) + __ldg(excl_local + key) + (int)lrank[i];
+    const int blk = i / kRankThreads;
+    for (int b = 0; b < blk; ++b) pos += (int)__ldg(hist + (size_t)b * K + key);
+    keys_out[pos] = (uint32_t)key;
+    vals_out[pos] = (uint32_t)i;
 }
 
 __global__ void ema_keys_kernel(const long long* __restrict__ idx, long long N, uint32_t* __restrict__ keys,
@@ -227,8 +231,10 @@ __global__ void ema_keys_kernel(const long long* __restrict__ idx, long long N, 
 
 // seg[k] = first sorted position whose key >= k; seg[K] = N.  One thread per sorted position writes the
 // (usually zero or one) boundaries that fall between its predecessor's key and its own.
-__global__ void ema_boundaries_kernel(const uint32_t* __restrict__ keys, int N, int K, int* __restrict__ seg) {
+__global__ void ema_boundaries_kernel(const uint32_t* __restrict__ keys, int N, int K, int* __restrict__ seg,
+                                      int* __restrict__ flags) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) flags[0] = 0;
     if (p > N) return;
     const int k = p < N ? (int)keys[p] : K;
     const int kprev = p == 0 ? -1 : (int)keys[p - 1];
@@ -236,37 +242,105 @@ __global__ void ema_boundaries_kernel(const uint32_t* __restrict__ keys, int N, 
 }
 
 // ------------------------------------------------------------------------------------------------ segmented sum
-// One CTA per chunk of 16 sorted positions; thread t owns 16-byte column groups t, t + blockDim, ...
-// All 16 row loads of a column group are issued before the running sums are formed.
+// One warp per codeword: counts, the zero row of an unused codeword, and -- for segments of up to kLongSeg frames --
+// the sum of the segment's frame rows in ascending frame order (lane <-> 16-byte column groups, 4 row loads in flight).
+// A longer segment is left to the chunked kernels below and raises flags[0].
+template <int VEC>
+__global__ void __launch_bounds__(256)
+ema_rowsum_kernel(const float* __restrict__ xr, const uint32_t* __restrict__ rows, const int* __restrict__ seg, int K, int D,
+                  float* __restrict__ sums, float* __restrict__ counts, int* __restrict__ flags) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= K) return;
+    const int s0 = __ldg(seg + k), s1 = __ldg(seg + k + 1), c = s1 - s0;
+    if (lane == 0) counts[k] = (float)c;
+    if (c > kLongSeg) { if (lane == 0) flags[0] = 1; return; }
+    const int groups = D / VEC;
+    float* dst = sums + (size_t)k * D;
+    for (int g0 = 0; g0 < groups; g0 += 64) {              // two column groups per lane and pass
+        const int ga = g0 + lane, gb = g0 + 32 + lane;
+        float a[VEC], b[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { a[e] = 0.f; b[e] = 0.f; }
+        int p = s0;
+        for (; p + 2 <= s1; p += 2) {                      // two frames per iteration: four independent loads
+            const float* r0 = xr + (size_t)__ldg(rows + p) * D;
+            const float* r1 = xr + (size_t)__ldg(rows + p + 1) * D;
+            if constexpr (VEC == 4) {
+                float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, y0 = x0, y1 = x0;
+                if (ga < groups) { x0 = __ldg(reinterpret_cast<const float4*>(r0) + ga); x1 = __ldg(reinterpret_cast<const float4*>(r1) + ga); }
+                if (gb < groups) { y0 = __ldg(reinterpret_cast<const float4*>(r0) + gb); y1 = __ldg(reinterpret_cast<const float4*>(r1) + gb); }
+                a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w;
+                a[0] += x1.x; a[1] += x1.y; a[2] += x1.z; a[3] += x1.w;
+                b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w;
+                b[0] += y1.x; b[1] += y1.y; b[2] += y1.z; b[3] += y1.w;
+            } else {
+                const float x0 = ga < groups ? __ldg(r0 + ga) : 0.f, x1 = ga < groups ? __ldg(r1 + ga) : 0.f;
+                const float y0 = gb < groups ? __ldg(r0 + gb) : 0.f, y1 = gb < groups ? __ldg(r1 + gb) : 0.f;
+                a[0] += x0; a[0] += x1; b[0] += y0; b[0] += y1;
+            }
+        }
+        if (p < s1) {
+            const float* r0 = xr + (size_t)__ldg(rows + p) * D;
+            if constexpr (VEC == 4) {
+                if (ga < groups) { const float4 x0 = __ldg(reinterpret_cast<const float4*>(r0) + ga); a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w; }
+                if (gb < groups) { const float4 y0 = __ldg(reinterpret_cast<const float4*>(r0) + gb); b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w; }
+            } else {
+                if (ga < groups) a[0] += __ldg(r0 + ga);
+                if (gb < groups) b[0] += __ldg(r0 + gb);
+            }
+        }
+        if constexpr (VEC == 4) {
+            if (ga < groups) reinterpret_cast<float4*>(dst)[ga] = make_float4(a[0], a[1], a[2], a[3]);
+            if (gb < groups) reinterpret_cast<float4*>(dst)[gb] = make_float4(b[0], b[1], b[2], b[3]);
+        } else {
+            if (ga < groups) dst[ga] = a[0];
+            if (gb < groups) dst[gb] = b[0];
+        }
+    }
+}
+
+// Long segments only (flags[0] != 0, else the launch returns at once).  One CTA per chunk of 16 sorted positions;
+// thread t owns 16-byte column groups t, t + blockDim, ...  All row loads of a column group are issued before the
+// running sums are formed.  Positions that belong to short segments are skipped (ema_rowsum_kernel summed them).
 template <int VEC>
 __global__ void __launch_bounds__(128)
 ema_chunk_sum_kernel(const float* __restrict__ xr, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rows,
-                     const int* __restrict__ seg, int N, int D, float* __restrict__ sums, float* __restrict__ partial) {
+                     const int* __restrict__ seg, int N, int D, float* __restrict__ sums, float* __restrict__ partial,
+                     const int* __restrict__ flags) {
+    if (flags[0] == 0) return;
     __shared__ uint32_t s_key[kChunk], s_row[kChunk];
     __shared__ int s_dst[kChunk];      // where the run ending at position p goes: -1 none, 0 sums, 1 head, 2 tail
-    const int c = blockIdx.x;
+    __shared__ int s_use[kChunk];      // position belongs to a long segment
+    __shared__ int s_any;
+    const int nchunks = (N + kChunk - 1) / kChunk;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {          // grid-stride: the launch is small when nothing is long
     const int pos0 = c * kChunk, pos1 = min(N, pos0 + kChunk), len = pos1 - pos0;
+    __syncthreads();
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
     if (threadIdx.x < kChunk) {
         const int p = threadIdx.x;
-        int dst = -1;
+        int dst = -1, use = 0;
         uint32_t k = 0, r = 0;
         if (p < len) {
             k = keys[pos0 + p]; r = rows[pos0 + p];
+            const int s0 = __ldg(seg + k), s1 = __ldg(seg + k + 1);
+            use = (s1 - s0) > kLongSeg;
             const bool run_end = (p + 1 == len) || (keys[pos0 + p + 1] != k);
-            if (run_end) {
-                const int s0 = __ldg(seg + k), s1 = __ldg(seg + k + 1);
-                dst = (s0 >= pos0 && s1 <= pos1) ? 0 : (s0 < pos0 ? 1 : 2);
-            }
+            if (use && run_end) dst = (s0 >= pos0 && s1 <= pos1) ? 0 : (s0 < pos0 ? 1 : 2);
+            if (use) s_any = 1;
         }
-        s_key[p] = k; s_row[p] = r; s_dst[p] = dst;
+        s_key[p] = k; s_row[p] = r; s_dst[p] = dst; s_use[p] = use;
     }
     __syncthreads();
+    if (!s_any) continue;
     const int groups = D / VEC;
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
         float v[kChunk][VEC];
 #pragma unroll
         for (int p = 0; p < kChunk; ++p) {
-            if (p < len) {
+            if (p < len && s_use[p]) {
                 const float* src = xr + (size_t)s_row[p] * D;
                 if constexpr (VEC == 4) {
                     const float4 x = __ldg(reinterpret_cast<const float4*>(src) + g);
@@ -281,7 +355,7 @@ ema_chunk_sum_kernel(const float* __restrict__ xr, const uint32_t* __restrict__ 
         for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
 #pragma unroll
         for (int p = 0; p < kChunk; ++p) {
-            if (p < len) {
+            if (p < len && s_use[p]) {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) acc[e] += v[p][e];
                 const int dst = s_dst[p];
@@ -295,30 +369,23 @@ ema_chunk_sum_kernel(const float* __restrict__ xr, const uint32_t* __restrict__ 
             }
         }
     }
+  }
 }
 
-// One warp per codeword: counts, zero rows for unused codewords, and the ordered sum of the chunk
-// partials of runs that crossed chunk borders.
+// Long segments only: one warp per codeword adds, in chunk order, the partials of a segment that crossed chunk borders.
 template <int VEC>
 __global__ void __launch_bounds__(256)
 ema_finalize_kernel(const int* __restrict__ seg, int K, int D, const float* __restrict__ partial,
-                    float* __restrict__ sums, float* __restrict__ counts) {
-    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                    float* __restrict__ sums, const int* __restrict__ flags) {
+    if (flags[0] == 0) return;
     const int lane = threadIdx.x & 31;
-    if (k >= K) return;
+  for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < K; k += gridDim.x * (blockDim.x >> 5)) {
     const int s0 = seg[k], s1 = seg[k + 1];
-    if (lane == 0) counts[k] = (float)(s1 - s0);
+    if (s1 - s0 <= kLongSeg) continue;
     const int groups = D / VEC;
     float* dst = sums + (size_t)k * D;
-    if (s1 == s0) {
-        for (int g = lane; g < groups; g += 32) {
-            if constexpr (VEC == 4) reinterpret_cast<float4*>(dst)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            else dst[g] = 0.f;
-        }
-        return;
-    }
     const int cf = s0 / kChunk, cl = (s1 - 1) / kChunk;
-    if (cf == cl) return;   // summed and stored by the chunk kernel
+    if (cf == cl) continue;   // summed and stored by the chunk kernel
     for (int g = lane; g < groups; g += 32) {
         float acc[VEC];
         const float* p0 = partial + ((size_t)cf * 2 + 1) * D;
@@ -340,6 +407,7 @@ ema_finalize_kernel(const int* __restrict__ seg, int K, int D, const float* __re
         if constexpr (VEC == 4) reinterpret_cast<float4*>(dst)[g] = make_float4(acc[0], acc[1], acc[2], acc[3]);
         else dst[g] = acc[0];
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ apply
@@ -365,8 +433,10 @@ ema_cluster_partial_kernel(const float* __restrict__ counts, const float* __rest
     }
 }
 
-// One warp per codeword: n = sum of the block partials (same fixed order in every warp),
-// cs <- (cs' + eps) / (n + K*eps) * n, ema_w and weight update, refreshed GEMM operand and |c|^2.
+// One warp per codeword: n = sum of the block partials (the same fixed shuffle tree in every warp, so every codeword
+// sees the same n), cs <- (cs' + eps) / (n + K*eps) * n, ema_w and weight update, refreshed GEMM operand and |c|^2.
+// kVec4 (D % 4 == 0, 16-byte aligned arrays): 16-byte row accesses.
+template <bool kVec4>
 __global__ void __launch_bounds__(256)
 ema_apply_rows_kernel(const float* __restrict__ sums, const float* __restrict__ counts, const float* __restrict__ cluster_partial,
                       int nblocks, int K, int D, int Dp, int Kp, float decay, float one_minus_decay, float eps, float k_eps,
@@ -376,24 +446,51 @@ ema_apply_rows_kernel(const float* __restrict__ sums, const float* __restrict__ 
     const int lane = threadIdx.x & 31;
     if (k >= Kp) return;
     if (k >= K) { if (cnorm && lane == 0) cnorm[k] = CUDART_INF_F; return; }
-    float n = 0.f;
-    for (int b = 0; b < nblocks; ++b) n += __ldg(cluster_partial + b);
+    float n = (lane < nblocks ? __ldg(cluster_partial + lane) : 0.f) + (lane + 32 < nblocks ? __ldg(cluster_partial + lane + 32) : 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     const float csp = __fadd_rn(__fmul_rn(cs[k], decay), __fmul_rn(one_minus_decay, counts[k]));
     const float size = __fmul_rn(__fdiv_rn(__fadd_rn(csp, eps), n + k_eps), n);
     __syncwarp();                     // every lane has read cs[k] before lane 0 overwrites it
     if (lane == 0) cs[k] = size;
     float s = 0.f;
-    for (int d = lane; d < Dp; d += 32) {
-        float wv = 0.f;
-        if (d < D) {
-            const size_t o = (size_t)k * D + d;
-            const float e = __fadd_rn(__fmul_rn(ema_w[o], decay), __fmul_rn(one_minus_decay, sums[o]));
-            ema_w[o] = e;
-            wv = __fdiv_rn(e, size);
-            weight[o] = wv;
+    if constexpr (kVec4) {
+        const size_t row = (size_t)k * D;
+        for (int g = lane; g < Dp / 4; g += 32) {
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * g < D) {
+                const float4 e0 = *reinterpret_cast<const float4*>(ema_w + row + 4 * g);
+                const float4 sm = __ldg(reinterpret_cast<const float4*>(sums + row + 4 * g));
+                float4 e;
+                e.x = __fadd_rn(__fmul_rn(e0.x, decay), __fmul_rn(one_minus_decay, sm.x));
+                e.y = __fadd_rn(__fmul_rn(e0.y, decay), __fmul_rn(one_minus_decay, sm.y));
+                e.z = __fadd_rn(__fmul_rn(e0.z, decay), __fmul_rn(one_minus_decay, sm.z));
+                e.w = __fadd_rn(__fmul_rn(e0.w, decay), __fmul_rn(one_minus_decay, sm.w));
+                *reinterpret_cast<float4*>(ema_w + row + 4 * g) = e;
+                wv = make_float4(__fdiv_rn(e.x, size), __fdiv_rn(e.y, size), __fdiv_rn(e.z, size), __fdiv_rn(e.w, size));
+                *reinterpret_cast<float4*>(weight + row + 4 * g) = wv;
+            }
+            s = fmaf(wv.x, wv.x, s); s = fmaf(wv.y, wv.y, s); s = fmaf(wv.z, wv.z, s); s = fmaf(wv.w, wv.w, s);
+            if (cb) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(wv.x, wv.y), hi = __floats2bfloat162_rn(wv.z, wv.w);
+                uint2 o;
+                o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(cb + (size_t)k * Dp + 4 * g) = o;
+            }
         }
-        s = fmaf(wv, wv, s);
-        if (cb) cb[(size_t)k * Dp + d] = __float2bfloat16_rn(wv);
+    } else {
+        for (int d = lane; d < Dp; d += 32) {
+            float wv = 0.f;
+            if (d < D) {
+                const size_t o = (size_t)k * D + d;
+                const float e = __fadd_rn(__fmul_rn(ema_w[o], decay), __fmul_rn(one_minus_decay, sums[o]));
+                ema_w[o] = e;
+                wv = __fdiv_rn(e, size);
+                weight[o] = wv;
+            }
+            s = fmaf(wv, wv, s);
+            if (cb) cb[(size_t)k * Dp + d] = __float2bfloat16_rn(wv);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -464,45 +561,58 @@ int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, i
     float* sums = sums_counts;
     float* counts = sums_counts + (size_t)K * D;
 
+    int* flags = reinterpret_cast<int*>(ws + l.flags);
     const int bin_sort = PERO_KNOB("PERO_EMA_BIN_SORT", 1);     // dev build, 0: radix sort also for the small case
-    if (bin_sort && N <= kBinSortThreads * kBinSortItems && K <= kBinSortMaxK) {
-        const size_t smem = ((size_t)2 * K + kBinSortThreads * kBinSortItems) * 4;
+    if (bin_sort && N <= kSmallSortMax && K <= kBinSortMaxK) {
+        // stable counting sort in three short launches (ranks + histograms, scan, placement); the per-frame ranks
+        // borrow keys_in, which only the CUB path uses
+        uint32_t* hist = reinterpret_cast<uint32_t*>(ws + l.hist);
+        uint32_t* lrank = keys_in;
+        const int nb = (int)((N + kRankThreads - 1) / kRankThreads);
         {
             static std::atomic<bool> attr_done[64];
             int dev = 0;
             cudaGetDevice(&dev);
             dev = (dev >= 0 && dev < 64) ? dev : 0;
             if (!attr_done[dev].load(std::memory_order_acquire)) {
-                cudaError_t e = cudaFuncSetAttribute(ema_bin_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)(((size_t)2 * kBinSortMaxK + kBinSortThreads * kBinSortItems) * 4));
+                cudaError_t e = cudaFuncSetAttribute(ema_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBinSortMaxK * 4);
                 if (e != cudaSuccess) return (int)e;
                 attr_done[dev].store(true, std::memory_order_release);
             }
         }
-        ema_bin_small_kernel<<<1, kBinSortThreads, smem, stream>>>(reinterpret_cast<const long long*>(idx), (int)N, (int)K, keys_out,
-                                                                  vals_out, seg);
+        ema_rank_kernel<<<nb, kRankThreads, (size_t)K * 4, stream>>>(reinterpret_cast<const long long*>(idx), (int)N, (int)K, lrank,
+                                                                     hist, flags);
+        int* excl = reinterpret_cast<int*>(ws + l.excl);
+        int* btot = reinterpret_cast<int*>(ws + l.btot);
+        ema_scan_local_kernel<<<(unsigned)((K + 255) / 256), 256, 0, stream>>>(hist, nb, (int)K, excl, btot);
+        const int64_t place_threads = std::max<int64_t>(N, K + 1);
+        ema_place_kernel<<<(unsigned)((place_threads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const long long*>(idx), lrank, hist,
+                                                                                      excl, btot, (int)N, (int)K, keys_out, vals_out, seg);
     } else if (N <= kSmallSortMax) {
         const int end_bit = key_bits(K) + 1;
         ema_sort_small_kernel<8><<<1, 1024, 0, stream>>>(reinterpret_cast<const long long*>(idx), (int)N, (int)K, end_bit, keys_out,
-                                                        vals_out, seg);
+                                                        vals_out, seg, flags);
     } else {
         ema_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const long long*>(idx), N, keys_in, vals_in);
         size_t cub_bytes = l.cub_bytes;
         cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)N, 0,
                                                         key_bits(K), stream);
         if (e != cudaSuccess) return (int)e;
-        ema_boundaries_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, stream>>>(keys_out, (int)N, (int)K, seg);
+        ema_boundaries_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, stream>>>(keys_out, (int)N, (int)K, seg, flags);
     }
     const unsigned chunks = (unsigned)((N + kChunk - 1) / kChunk);
     const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_rows) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(sums_counts) & 15) == 0);
+    const unsigned kblocks = (unsigned)((K + 7) / 8);
     if (vec) {
         const int threads = (int)std::min<int64_t>(128, std::max<int64_t>(32, round_up(D / 4, 32)));
-        ema_chunk_sum_kernel<4><<<chunks, threads, 0, stream>>>(x_rows, keys_out, vals_out, seg, (int)N, (int)D, sums, partial);
-        ema_finalize_kernel<4><<<(unsigned)((K + 7) / 8), 256, 0, stream>>>(seg, (int)K, (int)D, partial, sums, counts);
+        ema_rowsum_kernel<4><<<kblocks, 256, 0, stream>>>(x_rows, vals_out, seg, (int)K, (int)D, sums, counts, flags);
+        ema_chunk_sum_kernel<4><<<std::min(chunks, 2048u), threads, 0, stream>>>(x_rows, keys_out, vals_out, seg, (int)N, (int)D, sums, partial, flags);
+        ema_finalize_kernel<4><<<std::min(kblocks, 592u), 256, 0, stream>>>(seg, (int)K, (int)D, partial, sums, flags);
     } else {
-        ema_chunk_sum_kernel<1><<<chunks, 128, 0, stream>>>(x_rows, keys_out, vals_out, seg, (int)N, (int)D, sums, partial);
-        ema_finalize_kernel<1><<<(unsigned)((K + 7) / 8), 256, 0, stream>>>(seg, (int)K, (int)D, partial, sums, counts);
+        ema_rowsum_kernel<1><<<kblocks, 256, 0, stream>>>(x_rows, vals_out, seg, (int)K, (int)D, sums, counts, flags);
+        ema_chunk_sum_kernel<1><<<std::min(chunks, 2048u), 128, 0, stream>>>(x_rows, keys_out, vals_out, seg, (int)N, (int)D, sums, partial, flags);
+        ema_finalize_kernel<1><<<std::min(kblocks, 592u), 256, 0, stream>>>(seg, (int)K, (int)D, partial, sums, flags);
     }
     return (int)cudaGetLastError();
 }
@@ -532,9 +642,16 @@ int pero_vq_ema_apply(const float* sums_counts, int64_t K, int64_t D, double dec
     const int nblocks = (int)std::min<int64_t>(kClusterBlocks, (K + 255) / 256);
     ema_cluster_partial_kernel<<<nblocks, 256, 0, stream>>>(counts, ema_cluster_size, (int)K, decay_f, omd_f, cluster_partial);
     const int rows = (int)(codebook ? cl.Kp : K);
-    ema_apply_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(sums, counts, cluster_partial, nblocks, (int)K, (int)D,
-                                                                         (int)cl.Dp, rows, decay_f, omd_f, eps_f, keps_f,
-                                                                         ema_cluster_size, ema_w, weight, cb, cnorm);
+    const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(sums_counts) | reinterpret_cast<uintptr_t>(ema_w) |
+                                        reinterpret_cast<uintptr_t>(weight)) & 15) == 0;
+    if (vec4)
+        ema_apply_rows_kernel<true><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(sums, counts, cluster_partial, nblocks, (int)K,
+                                                                                   (int)D, (int)cl.Dp, rows, decay_f, omd_f, eps_f,
+                                                                                   keps_f, ema_cluster_size, ema_w, weight, cb, cnorm);
+    else
+        ema_apply_rows_kernel<false><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(sums, counts, cluster_partial, nblocks, (int)K,
+                                                                                    (int)D, (int)cl.Dp, rows, decay_f, omd_f, eps_f,
+                                                                                    keps_f, ema_cluster_size, ema_w, weight, cb, cnorm);
     return (int)cudaGetLastError();
 }
 

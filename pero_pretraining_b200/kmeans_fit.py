@@ -43,6 +43,7 @@ class MiniBatchKMeans:
         self.n_steps_ = 0
         self.inertia_ = None
         self._n_since_last_reassign = 0
+        self.check_every = 8          # fit(): the batch inertias are read back (one host sync) every this many steps
 
     # ------------------------------------------------------------------------------------------ state
     @property
@@ -160,38 +161,72 @@ class MiniBatchKMeans:
         return self
 
     # ------------------------------------------------------------------------------------------ fit
+    def _batch(self, X, bidx, on_device):
+        if on_device:
+            return X[torch.from_numpy(bidx).to(X.device)].float().contiguous()
+        if torch.is_tensor(X):
+            return self._as_device_rows(X[torch.from_numpy(bidx)])
+        return self._as_device_rows(X[bidx])
+
     def fit(self, X):
-        """MiniBatchKMeans.fit: max_iter passes' worth of uniformly sampled batches with EWA-inertia early stopping."""
+        """MiniBatchKMeans.fit of scikit-learn 1.9: `n_init` initialisations scored by their inertia on a validation
+        subsample (the best one is kept), then max_iter passes' worth of uniformly sampled batches with the two
+        early-stopping rules: EWA inertia without improvement for `max_no_improvement` steps, and (tol > 0) squared
+        centre movement below tol * mean feature variance.  The batch inertias stay on the device and are read back every
+        `check_every` steps, so the EWA rule may run up to check_every - 1 steps longer than scikit-learn would."""
         n_samples = len(X)
         on_device = torch.is_tensor(X) and X.is_cuda
         if not on_device and not torch.is_tensor(X):
             X = np.ascontiguousarray(X, dtype=np.float32)
-        self._init_centroids(X, n_samples)
         bs = min(self.batch_size, n_samples)
         self.batch_size = bs
+        init_size = min(max(self.init_size or 3 * bs, self.n_clusters), n_samples)
+        n_init = self.n_init if isinstance(self.init, str) else 1       # explicit centres: a single "initialisation"
+        if n_init > 1:
+            Xv = self._batch(X, self._rng.randint(0, n_samples, init_size), on_device)
+            best = None
+            for _ in range(n_init):
+                self._init_centroids(X, n_samples)
+                inertia = self.score_inertia(Xv)
+                if best is None or inertia < best[0]:
+                    best = (inertia, self._centers.clone())
+            self._set_centers(best[1])
+        else:
+            self._init_centroids(X, n_samples)
+        tol_abs = 0.0
+        if self.tol > 0.0:       # scikit-learn's _tolerance: tol * mean of the per-feature variances
+            Xt = X if torch.is_tensor(X) else torch.from_numpy(X)
+            tol_abs = self.tol * float(Xt.float().var(dim=0, unbiased=False).mean())
         n_steps = (self.max_iter * n_samples) // bs
         ewa, ewa_min, no_improvement = None, None, 0
+        pending, stop = [], False
+        alpha = min(bs * 2.0 / (n_samples + 1), 1.0)
         for i in range(n_steps):
-            bidx = self._rng.randint(0, n_samples, bs)
-            if on_device:
-                Xb = X[torch.from_numpy(bidx).to(X.device)].float().contiguous()
-            elif torch.is_tensor(X):
-                Xb = self._as_device_rows(X[torch.from_numpy(bidx)])
-            else:
-                Xb = self._as_device_rows(X[bidx])
-            inertia = float(self._step(Xb, self._random_reassign()).item()) / bs
+            Xb = self._batch(X, self._rng.randint(0, n_samples, bs), on_device)
+            old = self._centers.clone() if tol_abs > 0.0 else None
+            inertia = self._step(Xb, self._random_reassign())
             self.n_steps_ += 1
-            if i == 0:                      # _mini_batch_convergence ignores the first step (inertia of the init)
+            moved = ops.mse_fwd(self._centers, old, float(old.numel()), 0.0) if old is not None else None
+            pending.append((i, inertia, moved))
+            if len(pending) < self.check_every and i + 1 < n_steps:
                 continue
-            alpha = min(bs * 2.0 / (n_samples + 1), 1.0)
-            ewa = inertia if ewa is None else ewa * (1 - alpha) + inertia * alpha
-            if self.verbose:
-                print(f"Minibatch step {i + 1}/{n_steps}: mean batch inertia: {inertia}, ewa inertia: {ewa}")
-            if ewa_min is None or ewa < ewa_min:
-                ewa_min, no_improvement = ewa, 0
-            else:
-                no_improvement += 1
-            if self.max_no_improvement is not None and no_improvement >= self.max_no_improvement:
+            for j, inert_t, moved_t in pending:             # one synchronisation for the whole group
+                if j == 0:                  # _mini_batch_convergence ignores the first step (inertia of the init)
+                    continue
+                val = float(inert_t.item()) / bs
+                ewa = val if ewa is None else ewa * (1 - alpha) + val * alpha
+                if self.verbose:
+                    print(f"Minibatch step {j + 1}/{n_steps}: mean batch inertia: {val}, ewa inertia: {ewa}")
+                if moved_t is not None and float(moved_t.item()) <= tol_abs:
+                    stop = True
+                if ewa_min is None or ewa < ewa_min:
+                    ewa_min, no_improvement = ewa, 0
+                else:
+                    no_improvement += 1
+                if self.max_no_improvement is not None and no_improvement >= self.max_no_improvement:
+                    stop = True
+            pending = []
+            if stop:
                 break
         self.inertia_ = self.score_inertia(X)
         return self
@@ -223,7 +258,8 @@ def fit(vectors, k, batch_size=2 ** 14, epochs=100, random_state=None, device=No
     vectors = np.asarray(vectors, dtype=np.float32)
     rng = np.random.RandomState(random_state)
     rng.shuffle(vectors)
-    kmeans = MiniBatchKMeans(n_clusters=k, init="k-means++", batch_size=batch_size, max_iter=epochs, random_state=rng, device=device)
+    kmeans = MiniBatchKMeans(n_clusters=k, init="k-means++", batch_size=batch_size, max_iter=epochs, n_init=10, random_state=rng,
+                             device=device)
     kmeans.fit(vectors)
     print(f"Inertia:{kmeans.inertia_}")
     return kmeans

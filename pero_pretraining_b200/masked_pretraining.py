@@ -87,9 +87,8 @@ class _FusedHeadCE(torch.autograd.Function):
             h2 = h2.float()
         if not h2.is_contiguous():
             h2 = h2.contiguous()
-        lab = labels.detach().reshape(-1)
-        if lab.dtype != torch.int64:
-            lab = lab.long()
+        # the kernels read device int64 labels: coerce other dtypes / host tensors instead of reinterpreting them
+        lab = labels.detach().reshape(-1).to(device=h2.device, dtype=torch.int64)
         if not lab.is_contiguous():
             lab = lab.contiguous()
         saved, loss = [], None
@@ -194,6 +193,16 @@ class LinearHead(torch.nn.Module):
         self._peer_range = PeerRange(buf, n, torch.float32)
         return self
 
+    def invalidate(self):
+        """Forget the prepared bf16 operands.  The cache is keyed on (data_ptr, _version) of weight and bias; a write
+        through `.data` (e.g. `head.linear.weight.data.copy_(...)`) does not bump `_version`, so call this after one.
+        load_state_dict() does it by itself."""
+        self._prep_tag = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._prep_tag = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def _prepared(self):
         W, b = self.linear.weight, self.linear.bias
         if not W.is_cuda:
@@ -208,8 +217,15 @@ class LinearHead(torch.nn.Module):
         return self._prep
 
     def masked_loss(self, hidden, labels, mask, unmasked_weight=None, dp_group=None):
-        """Fused LinearHead + MaskedCrossEntropyLoss on hidden states [Nl, T, Dh] (or [N, Dh])."""
+        """Fused LinearHead + MaskedCrossEntropyLoss on hidden states [Nl, T, Dh] (or [N, Dh]).
+        Any hidden size that is a multiple of 4 takes the fused path (up to 512 the masked rows stay resident in shared
+        memory); other sizes go through the logits-in kernels on `self.linear(hidden)` (single process only)."""
         dev = hidden.device
+        if hidden.shape[-1] % 4 != 0:
+            if dp_group is not None:
+                raise ops._lib.PeroError("data-parallel masked_loss needs a hidden size that is a multiple of 4")
+            from .logits_ce import masked_ce_from_logits
+            return masked_ce_from_logits(self.linear(hidden), labels, mask, unmasked_weight)
         rows, m = _rows_from_mask(mask, labels, 1, False, dev)
         terms = [(rows, m, 1.0)]
         if unmasked_weight is not None:

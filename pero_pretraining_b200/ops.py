@@ -215,7 +215,7 @@ def vq_st_commit_bwd(g_quantized, quantized, inputs, coef, grad_loss=None):
 
 # ------------------------------------------------------------------------------------------ masked CE
 class PreparedHead:
-    """Device blob with bf16 W, bf16 W^T and the bias of a Linear(Dh -> V) head."""
+    """Device blob with the bf16 copy of W and the bias of a Linear(Dh -> V) head."""
 
     def __init__(self, V, Dh, device):
         self.V, self.Dh = int(V), int(Dh)
@@ -236,21 +236,59 @@ def _check_h(h):
     return h if h.is_contiguous() else h.contiguous()
 
 
-def masked_ce_fwd(h, rows, labels, head, loss_out=None):
-    """h [N, Dh]; rows int32 [M]; labels int64 [N].  Returns (loss_sum [1], lse [M], workspace).
-    `loss_out`: optional fp32 [1] destination (e.g. a slot of the peer-exchange range next to d_W|d_b)."""
+def masked_ce_gather(h, rows, V):
+    """Gathers the masked rows of h [N, Dh] into a fresh masked-CE workspace (bf16 GEMM operand + frame -> row map) and
+    returns it; reads neither labels nor head, so it can be issued before they exist (masked_ce_fwd(..., ws=...))."""
     L = _lib.lib()
     h = _check_h(h)
     N, Dh = h.shape
     M = rows.numel()
-    loss_sum = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=h.device)
-    lse = torch.empty(M, dtype=torch.float32, device=h.device)
-    wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
+    wsb = L.pero_masked_ce_workspace_bytes(N, M, int(V), Dh)
     ws = _ws(wsb, h.device)
-    check(L.pero_masked_ce_fwd(h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M,
-                               labels.data_ptr(), head.blob.data_ptr(), head.V, loss_sum.data_ptr(), lse.data_ptr(),
+    check(L.pero_masked_ce_gather(h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M, int(V),
+                                  ws.data_ptr(), wsb, _stream()), "pero_masked_ce_gather")
+    return ws
+
+
+def _ce_flags(h, labels_packed):
+    return (1 if h.dtype == torch.bfloat16 else 0) | (2 if labels_packed else 0)
+
+
+def masked_ce_fwd(h, rows, labels, head, loss_out=None, ws=None, finalize=True, labels_packed=False):
+    """h [N, Dh]; rows int32 [M]; labels int64 [N].  Returns (loss_sum [1], lse [M], workspace).
+    `loss_out`: optional fp32 [1] destination (e.g. a slot of the peer-exchange range next to d_W|d_b).
+    `ws`: the workspace masked_ce_gather returned for the same (h, rows): no second gather.
+    `finalize=False`: only the logits sweep; (loss_sum, lse) are None and masked_ce_loss(ws, ...) produces them later
+    (a backward with ws_from_fwd does not need them).
+    `labels_packed`: `labels` are the packed (distance, index) winners of vq_assign(packed=...)."""
+    L = _lib.lib()
+    h = _check_h(h)
+    N, Dh = h.shape
+    M = rows.numel()
+    loss_sum = lse = None
+    if finalize:
+        loss_sum = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=h.device)
+        lse = torch.empty(M, dtype=torch.float32, device=h.device)
+    wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
+    gathered = ws is not None
+    if gathered and ws.numel() < wsb:
+        raise ValueError("ws is smaller than pero_masked_ce_workspace_bytes for this shape")
+    if not gathered:
+        ws = _ws(wsb, h.device)
+    check(L.pero_masked_ce_fwd(None if gathered else h.data_ptr(), _ce_flags(h, labels_packed), N, Dh, rows.data_ptr(), M,
+                               labels.data_ptr(), head.blob.data_ptr(), head.V, _p(loss_sum), _p(lse),
                                ws.data_ptr(), wsb, _stream()), "pero_masked_ce_fwd")
     return loss_sum, lse, ws
+
+
+def masked_ce_loss(ws, N, Dh, M, V, loss_out=None):
+    """(loss_sum [1], lse [M]) from the log-sum-exp partials a masked_ce_fwd(finalize=False) left in `ws`."""
+    L = _lib.lib()
+    loss_sum = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=ws.device)
+    lse = torch.empty(int(M), dtype=torch.float32, device=ws.device)
+    check(L.pero_masked_ce_loss(int(N), int(Dh), int(M), int(V), loss_sum.data_ptr(), lse.data_ptr(), ws.data_ptr(), ws.numel(),
+                                _stream()), "pero_masked_ce_loss")
+    return loss_sum, lse
 
 
 def masked_ce_eval(h, rows, labels, head, ks=(1, 3, 10), want_rank=False):
@@ -269,7 +307,7 @@ def masked_ce_eval(h, rows, labels, head, ks=(1, 3, 10), want_rank=False):
     wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
     ws = _ws(wsb, dev)
     karr = (ctypes.c_int32 * len(ks))(*[int(k) for k in ks])
-    check(L.pero_masked_ce_eval(h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh, rows.data_ptr(), M,
+    check(L.pero_masked_ce_eval(h.data_ptr(), _ce_flags(h, False), N, Dh, rows.data_ptr(), M,
                                 labels.data_ptr(), head.blob.data_ptr(), head.V, ctypes.addressof(karr), len(ks),
                                 loss_sum.data_ptr(), lse.data_ptr(), _p(rank), errors.data_ptr(), ws.data_ptr(), wsb,
                                 _stream()), "pero_masked_ce_eval")
@@ -277,10 +315,11 @@ def masked_ce_eval(h, rows, labels, head, ks=(1, 3, 10), want_rank=False):
 
 
 def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False,
-                  want_dw=True, flat_out=None, ws_from_fwd=False, v_range=None):
+                  want_dw=True, flat_out=None, ws_from_fwd=False, v_range=None, labels_packed=False):
     """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32[, flat buffer holding d_W|d_b]).
     ws_from_fwd: `ws` is the workspace masked_ce_fwd returned for the same (h, rows, labels) and has not been
-    touched since: the gathered operands in it are reused instead of gathering again.
+    touched since: the gathered operands in it are reused instead of gathering again, and the log-sum-exp is rebuilt
+    from the forward's partials (`lse` may be None).
     v_range=(v0, v1): only label columns [v0, v1) (multiples of 256 or V): rows v0:v1 of d_W / d_b; needs
     want_dh=False, and a final call with want_dw=False for d_h once every range is done."""
     L = _lib.lib()
@@ -300,8 +339,10 @@ def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=Tru
         ws = _ws(wsb, h.device)
     gs = None if grad_scale is None else _f32c(grad_scale, "grad_scale")
     v0, v1 = (0, head.V) if v_range is None else (int(v_range[0]), int(v_range[1]))
-    check(L.pero_masked_ce_bwd_range(None if ws_from_fwd else h.data_ptr(), 1 if h.dtype == torch.bfloat16 else 0, N, Dh,
-                                     rows.data_ptr(), M, labels.data_ptr(), head.blob.data_ptr(), head.V, lse.data_ptr(), _p(gs),
+    if lse is None and not ws_from_fwd:
+        raise ValueError("lse is required unless ws_from_fwd")
+    check(L.pero_masked_ce_bwd_range(None if ws_from_fwd else h.data_ptr(), _ce_flags(h, labels_packed), N, Dh,
+                                     rows.data_ptr(), M, labels.data_ptr(), head.blob.data_ptr(), head.V, _p(lse), _p(gs),
                                      float(inv_count), v0, v1, _p(d_h), _p(d_W), _p(d_b), ws.data_ptr(), wsb,
                                      _stream()), "pero_masked_ce_bwd_range")
     return (d_h, d_W, d_b, flat) if return_flat else (d_h, d_W, d_b)
@@ -324,7 +365,11 @@ def mask_compact(mask, labels=None, want=1):
     count = torch.zeros(1, dtype=torch.int32, device=m.device)
     wsb = L.pero_mask_compact_workspace_bytes(N)
     ws = _ws(wsb, m.device)
-    lab = None if labels is None else labels.reshape(-1).contiguous()
+    lab = None
+    if labels is not None:       # the kernel reads device int64: coerce instead of reinterpreting other dtypes / CPU memory
+        lab = labels.reshape(-1).to(device=m.device, dtype=torch.int64).contiguous()
+        if lab.numel() != N:
+            raise ValueError("labels and mask must have the same number of elements")
     check(L.pero_mask_compact(m.data_ptr(), _MASK_DTYPES[m.dtype], int(want), _p(lab), N, rows.data_ptr(),
                               count.data_ptr(), ws.data_ptr(), wsb, _stream()), "pero_mask_compact")
     return rows, count

@@ -5,7 +5,7 @@ L = _lib.lib(); dev = torch.device("cuda:0")
 stream = torch.cuda.current_stream().cuda_stream
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 names = ["mma_top", "tempty_ok", "first_full", "issued", "epi_tfull", "epi_done", "prod_first", "prod_last"]
-N, K, D = 8192, 8192, 256
+N, K, D = [int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (8192, 8192, 256))]
 w = torch.randn(K, D, device=dev); xb = torch.randn(N, D, device=dev).bfloat16()
 cb = ops.PreparedCodebook(K, D, dev).prepare(w)
 packed = torch.empty(N, dtype=torch.int64, device=dev)

@@ -62,7 +62,7 @@ def test_version_strerror_and_size_queries(lib):
     assert lib.pero_vq_codebook_bytes(0, 5) == 0
     assert lib.pero_vq_assign_workspace_bytes(8192, 8192, 256) >= 8192 * 256 * 2 + 8192 * 8
     assert lib.pero_vq_ema_workspace_bytes(8192, 8192, 256) > 4 * 8192 * 4
-    assert lib.pero_head_bytes(4096, 512) >= 2 * 4096 * 512 * 2 + 4096 * 4
+    assert lib.pero_head_bytes(4096, 512) == 4096 * 512 * 2 + 4096 * 4      # ONE bf16 copy of W + the bias
     assert lib.pero_masked_ce_workspace_bytes(1024, 154, 4096, 512) > 0
     assert lib.pero_mse_workspace_bytes(10) >= 256 and lib.pero_mask_compact_workspace_bytes(1000) >= 256
 

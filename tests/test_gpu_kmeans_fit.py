@@ -44,6 +44,24 @@ def test_partial_fit_is_deterministic_and_matches_oracle_on_a_large_batch(cuda_d
     np.testing.assert_array_equal(km.counts_, w)
 
 
+def test_fit_honours_n_init_and_tol(cuda_dev):
+    """n_init initialisations scored on a validation subsample (scripts/fit_kmeans.py:21 fits with n_init=10) and
+    scikit-learn's tol rule (squared centre movement below tol * mean feature variance stops the loop)."""
+    from pero_pretraining_b200 import MiniBatchKMeans
+    rng = np.random.RandomState(11)
+    K, D, n = 32, 16, 8000
+    true = rng.randn(K, D).astype(np.float32) * 4
+    X = (true[rng.randint(0, K, n)] + 0.3 * rng.randn(n, D)).astype(np.float32)
+    one = MiniBatchKMeans(n_clusters=K, batch_size=1024, max_iter=10, n_init=1, random_state=5, device=cuda_dev).fit(X)
+    ten = MiniBatchKMeans(n_clusters=K, batch_size=1024, max_iter=10, n_init=10, random_state=5, device=cuda_dev).fit(X)
+    assert ten.inertia_ <= 1.3 * one.inertia_
+    loose = MiniBatchKMeans(n_clusters=K, batch_size=1024, max_iter=50, n_init=1, tol=0.5, max_no_improvement=None,
+                            random_state=5, device=cuda_dev).fit(X)
+    full = MiniBatchKMeans(n_clusters=K, batch_size=1024, max_iter=50, n_init=1, tol=0.0, max_no_improvement=None,
+                           random_state=5, device=cuda_dev).fit(X)
+    assert loose.n_steps_ < full.n_steps_ == (50 * n) // 1024
+
+
 def test_fit_recovers_blobs_and_exports_centres(cuda_dev, tmp_path):
     from pero_pretraining_b200 import KMeansLabeller, MiniBatchKMeans
     from sklearn.cluster import MiniBatchKMeans as SkMBK
