@@ -380,8 +380,10 @@ def dump_timeline(run, path):
             f.write(f"{e.time_range.start - t0:10.1f} {e.time_range.end - e.time_range.start:8.1f} {e.name[:110]}\n")
 
 
-def e2e_leg(batch, dev, dp, steps, warm):
-    """Public module API, host inputs: per step H2D of x / h / mask rows, D2H of the loss."""
+def e2e_leg(batch, dev, dp, steps, warm, repeats=3):
+    """Public module API, host inputs: per step H2D of x (fp32) / h (bf16: what --bfloat16 training hands the head,
+    masked_pretraining/trainer.py:57-59) / mask rows from pinned memory, D2H of the loss.  `repeats` timed loops of
+    `steps` steps each; returns (median s/step, min s/step, all, h2d bytes, d2h bytes, last loss)."""
     from pero_pretraining_b200 import LinearHead, VectorQuantizer
     c = CFG
     vq = VectorQuantizer(c["K"], c["D"], c["commitment_cost"], c["decay"], c["epsilon"]).to(dev).train()
@@ -392,12 +394,14 @@ def e2e_leg(batch, dev, dp, steps, warm):
     group = torch.distributed.group.WORLD if dp else None
     if dp:
         vq.enable_data_parallel(group)          # peer-memory exchange of the EMA sums|counts
-        head.enable_peer_exchange(group)        # ... and of d_W | d_b
-    x_host, h_host = batch["x"].pin_memory(), batch["h"].pin_memory()
+        head.enable_peer_exchange(group, alias_grads=True)      # ... and of d_W | d_b (every backward is followed by a reset)
+    else:
+        vq.enable_cuda_graph()                  # the forward's kernel sequence as one graph replay (public opt-in)
+    x_host, h_host = batch["x"].pin_memory(), batch["h"].bfloat16().pin_memory()
     gq = batch["gq"].to(dev)
     mask = batch["mask"]
-    rows_host = torch.from_numpy(np.flatnonzero(mask.reshape(-1) == 1).astype(np.int32)).pin_memory()
-    h2d = x_host.numel() * 4 + h_host.numel() * 4 + rows_host.numel() * 4
+    n_rows = int((mask.reshape(-1) == 1).sum())
+    h2d = x_host.numel() * 4 + h_host.numel() * 2 + n_rows * 4
     loss_val = None
     # Double-buffered input staging: the H2D copy of step i+1 runs on a copy stream while step i computes;
     # every step still waits for ITS OWN inputs to arrive and reads ITS OWN loss back.
@@ -418,6 +422,7 @@ def e2e_leg(batch, dev, dp, steps, warm):
     for e in consumed:
         e.record()
     stage(0)
+    labels_shape = (c["lines"], c["frames"])
 
     def step():
         i = state["i"]
@@ -428,7 +433,7 @@ def e2e_leg(batch, dev, dp, steps, warm):
         x = bufs[i & 1][0].detach().requires_grad_(True)
         h = bufs[i & 1][1].detach().requires_grad_(True)
         q, idx = vq(x)
-        loss = vq.calculate_loss(q, x) + head.masked_loss(h, idx.view(c["lines"], c["frames"]), mask, None, group)
+        loss = vq.calculate_loss(q, x) + head.masked_loss(h, idx.view(labels_shape), mask, None, group)
         head.linear.weight.grad = None
         head.linear.bias.grad = None
         torch.autograd.backward([loss, q], [None, gq])
@@ -437,19 +442,22 @@ def e2e_leg(batch, dev, dp, steps, warm):
 
     for _ in range(warm):
         step()
-    torch.cuda.synchronize()
-    if dp:
-        torch.distributed.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        loss_val = step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if dp:
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        dt = float(t.item())
-    return dt / steps, h2d, 4, loss_val
+    times = []
+    for _ in range(repeats):
+        torch.cuda.synchronize()
+        if dp:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss_val = step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dp:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            dt = float(t.item())
+        times.append(dt / steps)
+    return float(np.median(times)), float(min(times)), times, h2d, 4, loss_val
 
 
 def gemm_roofline_leg(ds, dev, iters, flush):
@@ -877,9 +885,13 @@ def our_arm(args):
     _log("roofline leg done")
     e2e = None
     if not args.skip_e2e:
-        s_per_step, h2d, d2h, _ = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup))
+        s_per_step, s_min, s_all, h2d, d2h, _ = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup))
         e2e = {"value": m_total / s_per_step, "unit": "masked frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": s_per_step * 1e3, "api": "VectorQuantizer.forward/calculate_loss + LinearHead.masked_loss + backward"}
+               "ms_per_step": s_per_step * 1e3, "ms_per_step_min": s_min * 1e3, "ms_per_step_all": [t * 1e3 for t in s_all],
+               "statistic": f"median of {len(s_all)} timed loops of {args.steps} steps",
+               "inputs": "x fp32 [64,256,1,128] + hidden states bf16 [64,128,512] + masked-row list, pinned host memory",
+               "api": ("VectorQuantizer.forward (enable_cuda_graph) / calculate_loss + LinearHead.masked_loss + backward"
+                       if not dp else "VectorQuantizer.forward (data parallel) / calculate_loss + LinearHead.masked_loss + backward")}
     _log("e2e leg done")
     # the step's graph, exchange buffers and streams are no longer needed: free them before the large configs
     launch_mode = "cuda_graph" if graph is not None else "eager"

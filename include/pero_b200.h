@@ -238,6 +238,20 @@ int pero_mask_compact(const void* mask, int mask_dtype, int want_value, const in
                       int32_t* rows, int32_t* count, void* workspace, size_t workspace_bytes,
                       pero_stream_t stream);
 
+/* ------------------------------------------------------------------ the callers either side of the head
+ * pero_mask_pixels: TransformerEncoder.mask (models/transformers.py:53-68) on the device, in place:
+ *     x[n, c, h, t*pw : (t+1)*pw] = tile[c, h, :]   for every masked frame r = n * frames_per_line + t in `rows`
+ *   x [n_lines, C, H, W] fp32, tile [C, H, patch_width] fp32 (the reference's fixed noise tile: np.random.seed(42);
+ *   np.random.rand(1, C, patch_h, patch_w)), rows = the masked-frame list of pero_masked_ce_fwd.
+ * pero_head_argmax_prepare: the head as a prepared "codebook" (pero_vq_codebook_bytes(V, Dh) bytes) such that
+ *   pero_vq_assign / pero_vq_assign_bf16 on the hidden states returns  argmax_v (h.W_v + b_v)  for every frame, lowest
+ *   index on ties (masked_pretraining/visualizer.py:32: torch.argmax(output['output'], dim=-1)) -- the [N, V] logits
+ *   of the evaluation / visualisation forward are never materialised. */
+int pero_mask_pixels(float* x, int64_t n_lines, int64_t C, int64_t H, int64_t W, const int32_t* rows, int64_t M,
+                     int64_t frames_per_line, int64_t patch_width, const float* tile, pero_stream_t stream);
+int pero_head_argmax_prepare(const float* W, const float* bias, int64_t V, int64_t Dh, void* codebook, size_t codebook_bytes,
+                             pero_stream_t stream);
+
 /* ------------------------------------------------------------------ peer-memory collectives (NVLink 5 / NVSwitch)
  * The reference is single-process; these are the two exchange steps of the sharded path:
  *   batch-sharded    SUM of the EMA buffer [K*D + K] between pero_vq_ema_accumulate and pero_vq_ema_apply

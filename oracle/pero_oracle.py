@@ -225,6 +225,29 @@ def create_mask(labels, masking_prob, rng):
     return (rng.random(labels.shape) < masking_prob).astype(int) * active
 
 
+def mask_pixels(x, mask, tile):
+    """TransformerEncoder.mask: the 8-px image column of every masked frame is overwritten with the fixed noise tile.
+    models/transformers.py:53-68 (pattern = tile repeated along the width, :34).  x [N, C, H, W], mask [N, W/8] {0,1},
+    tile [C, H, pw]; returns a new array."""
+    x = np.array(x, dtype=np.float32, copy=True)
+    mask = np.asarray(mask)
+    pw = tile.shape[2]
+    for n, t in zip(*np.nonzero(mask == 1)):
+        w0, w1 = t * pw, min((t + 1) * pw, x.shape[3])
+        x[n, :, :, w0:w1] = tile[:, :, :w1 - w0]
+    return x
+
+
+def mask_tile(in_channels=3, patch_size=(40, 8)):
+    """The reference's fixed noise tile: np.random.seed(42); np.random.rand(1, C, ph, pw).  models/transformers.py:29-32."""
+    return np.random.RandomState(42).rand(1, in_channels, patch_size[0], patch_size[1]).astype(np.float32)[0]
+
+
+def predict_labels(logits):
+    """MaskedVisualizer predictions: argmax over the label axis, first index on ties.  masked_pretraining/visualizer.py:32."""
+    return np.argmax(np.asarray(logits), axis=-1)
+
+
 def topk_errors(logits, labels, mask, ks=(1, 3, 10)):
     """Tester._update_errors: top-k error counts on masked frames.  masked_pretraining/tester.py:70-93."""
     sel = mask == 1

@@ -16,8 +16,8 @@ from .autoencoders import VQVAE, VectorQuantizer  # noqa: F401
 from .kmeans_fit import MiniBatchKMeans  # noqa: F401
 from .kmeans_labels import KMeansLabeller, kmeans_assign  # noqa: F401
 from .labels_io import LabelWriter, compute_labels, load_labels, produce_kmeans_labels, save_labels  # noqa: F401
-from .masked_pretraining import (LinearHead, MaskedCrossEntropyLoss, MaskedTransformerEncoder, create_mask,  # noqa: F401
-                                 update_errors)
+from .masked_pretraining import (LinearHead, MaskedCrossEntropyLoss, MaskedTransformerEncoder, PixelMasker,  # noqa: F401
+                                 create_mask, masked_rows, update_errors)
 from .sharding import ShardedCodebook, merge_packed, shard_bounds  # noqa: F401
 
 __version__ = "0.1.0"

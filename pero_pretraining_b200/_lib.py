@@ -62,6 +62,8 @@ SIGNATURES = {
     "pero_ce_logits_bwd": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_int, c_vp, c_vp]),
     "pero_mask_compact_workspace_bytes": (c_sz, [c_i64]),
     "pero_mask_compact": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pero_mask_pixels": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "pero_head_argmax_prepare": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
     "pero_peer_allreduce_sum_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "pero_peer_allreduce_min_i64": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "pero_peer_allreduce_emulate": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),

@@ -34,9 +34,12 @@ class _QuantizeST(torch.autograd.Function):
         weight = vq.embedding.weight.data
         if vq._dp_group is None:
             # single process: one call of the C ABI for assign -> quantize -> EMA update
-            out, idx = ops.vq_forward(x, cb, weight, vq.ema_w.data if update else None,
-                                      vq.ema_cluster_size if update else None, vq.decay, vq.epsilon, update and x.numel() > 0,
-                                      n_lines, frames, channels_first=True)
+            if vq._use_cuda_graph and x.numel() > 0:
+                out, idx = vq._graphed_forward(x, cb, update, n_lines, frames)
+            else:
+                out, idx = ops.vq_forward(x, cb, weight, vq.ema_w.data if update else None,
+                                          vq.ema_cluster_size if update else None, vq.decay, vq.epsilon, update and x.numel() > 0,
+                                          n_lines, frames, channels_first=True)
             if update and x.numel() > 0:
                 vq._codebook_tag = vq._weight_tag()
             ctx.mark_non_differentiable(idx)
@@ -131,6 +134,47 @@ class VectorQuantizer(torch.nn.Module):
         self._codebook_tag = None
         self._dp_group = None
         self._peer_range = None
+        self._use_cuda_graph = False
+        self._graphs = {}
+
+    # -- launch-bound small batches: the forward's ~12 kernel launches as one CUDA-graph replay
+    def enable_cuda_graph(self, enabled=True):
+        """Opt-in: VectorQuantizer.forward (single process) replays a CUDA graph of its kernel sequence, captured once
+        per (input shape, training/eval, state addresses), instead of launching ~12 kernels from the host; the input is
+        copied into a static buffer and the outputs are copied out of static buffers, so the usual tensor semantics
+        hold (nothing returned aliases the graph's buffers).  Worth it when the step is host-bound (8192 frames:
+        ~100 us of launches become ~25 us)."""
+        self._use_cuda_graph = bool(enabled)
+        if not enabled:
+            self._graphs = {}
+        return self
+
+    def _graphed_forward(self, x, cb, update, n_lines, frames):
+        weight = self.embedding.weight.data
+        key = (tuple(x.shape), bool(update), weight.data_ptr(), cb.blob.data_ptr(),
+               self.ema_w.data_ptr() if update else 0, self.ema_cluster_size.data_ptr() if update else 0, x.device)
+        g = self._graphs.get(key)
+        if g is None:
+            N = n_lines * frames
+            g = {"x": torch.empty_like(x), "out": torch.empty_like(x),
+                 "idx": torch.empty(N, dtype=torch.int64, device=x.device),
+                 "ws": ops.vq_forward_workspace(N, self.num_embeddings, self.embeddings_dim, update, x.device)}
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            # capture records the launches without executing them: the EMA state is not touched here
+            with torch.cuda.graph(graph, stream=side):
+                ops.vq_forward(g["x"], cb, weight, self.ema_w.data if update else None,
+                               self.ema_cluster_size if update else None, self.decay, self.epsilon, update, n_lines, frames,
+                               channels_first=True, out=g["out"], idx=g["idx"], ws=g["ws"])
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            g["graph"] = graph
+            if len(self._graphs) >= 8:        # shapes come and go (ragged last batch): keep the cache small
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = g
+        g["x"].copy_(x)
+        g["graph"].replay()
+        return g["out"].clone(), g["idx"].clone()
 
     # -- data parallel: batch-sharded frames, replicated codebook, EMA sums/counts all-reduced (SURVEY §8e)
     def enable_data_parallel(self, group=None, peer=True):

@@ -139,35 +139,52 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& 
 }
 
 // ---- stable multi-CTA counting sort (N <= 8192 frames, K <= kBinSortMaxK codewords) -----------------------------------
-// Launch 1, one CTA per 1024 frames (frame i = blockIdx.x * 1024 + threadIdx.x): the stable rank of every frame among
-// the frames of ITS CTA that carry the same codeword, and the CTA's histogram.  Lanes of a warp that share a codeword
-// are found with match.any; the warps then take turns in ascending order, the lowest lane of each group reserving
-// `group size` slots of the codeword's counter in shared memory: ranks ascend with the frame index, no atomics.
-__global__ void __launch_bounds__(kRankThreads)
+// Launch 1, one CTA of 256 threads per 1024 frames (thread t owns frames base + r * 256 + t, r = 0..3): the stable rank
+// of every frame among the frames of ITS CTA that carry the same codeword, and the CTA's histogram.  Lanes of a warp
+// that share a codeword are found with match.any; the (round, warp) pairs then take turns in ascending frame order,
+// the lowest lane of each group reserving `group size` slots of the codeword's 16-bit counter in shared memory: ranks
+// ascend with the frame index, no atomics.  256 threads, 32 registers and 2 K bytes of shared memory: the CTA fits
+// beside a resident GEMM CTA instead of waiting for a free SM.
+constexpr int kRankCtaThreads = 256;
+constexpr int kRankRounds = kRankThreads / kRankCtaThreads;
+__global__ void __launch_bounds__(kRankCtaThreads)
 ema_rank_kernel(const long long* __restrict__ idx, int N, int K, uint32_t* __restrict__ lrank, uint32_t* __restrict__ hist,
                 int* __restrict__ flags) {
-    extern __shared__ uint32_t cnt[];                 // [K]
+    extern __shared__ unsigned short cnt[];           // [K], at most 1024 per codeword
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    for (int k = t; k < K; k += kRankThreads) cnt[k] = 0u;
+    for (int k = t; k < K; k += kRankCtaThreads) cnt[k] = 0;
     if (blockIdx.x == 0 && t == 0) flags[0] = 0;      // cleared for ema_rowsum_kernel, two launches later
-    const int i = blockIdx.x * kRankThreads + t;
-    const int key = i < N ? (int)idx[i] : -1 - lane;   // padding lanes: distinct negative keys, groups of one
-    const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(grp) - 1;
-    const int rank_in_warp = __popc(grp & ((1u << lane) - 1u));
-    uint32_t base = 0;
-    __syncthreads();
-    for (int w = 0; w < kRankThreads / 32; ++w) {
-        if (warp == w && lane == leader && key >= 0) {
-            base = cnt[key];
-            cnt[key] = base + (uint32_t)__popc(grp);
-        }
-        __syncthreads();
+    int key[kRankRounds], leader[kRankRounds], rank_in_warp[kRankRounds], gsize[kRankRounds];
+    uint32_t base[kRankRounds];
+#pragma unroll
+    for (int r = 0; r < kRankRounds; ++r) {
+        const int i = blockIdx.x * kRankThreads + r * kRankCtaThreads + t;
+        key[r] = i < N ? (int)idx[i] : -1 - lane;     // padding lanes: distinct negative keys, groups of one
+        const unsigned grp = __match_any_sync(0xffffffffu, key[r]);
+        leader[r] = __ffs(grp) - 1;
+        rank_in_warp[r] = __popc(grp & ((1u << lane) - 1u));
+        gsize[r] = __popc(grp);
+        base[r] = 0;
     }
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (i < N) lrank[i] = base + (uint32_t)rank_in_warp;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRankRounds; ++r) {
+        for (int w = 0; w < kRankCtaThreads / 32; ++w) {
+            if (warp == w && lane == leader[r] && key[r] >= 0) {
+                base[r] = cnt[key[r]];
+                cnt[key[r]] = (unsigned short)(base[r] + gsize[r]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRankRounds; ++r) {
+        const uint32_t b = __shfl_sync(0xffffffffu, base[r], leader[r]);
+        const int i = blockIdx.x * kRankThreads + r * kRankCtaThreads + t;
+        if (i < N) lrank[i] = b + (uint32_t)rank_in_warp[r];
+    }
     uint32_t* h = hist + (size_t)blockIdx.x * K;
-    for (int k = t; k < K; k += kRankThreads) h[k] = cnt[k];
+    for (int k = t; k < K; k += kRankCtaThreads) h[k] = cnt[k];
 }
 
 // Launch 2, one CTA per 256 codewords: total[k] = frames of codeword k over all rank CTAs, its exclusive scan INSIDE the
@@ -575,12 +592,12 @@ int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, i
             cudaGetDevice(&dev);
             dev = (dev >= 0 && dev < 64) ? dev : 0;
             if (!attr_done[dev].load(std::memory_order_acquire)) {
-                cudaError_t e = cudaFuncSetAttribute(ema_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBinSortMaxK * 4);
+                cudaError_t e = cudaFuncSetAttribute(ema_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBinSortMaxK * 2);
                 if (e != cudaSuccess) return (int)e;
                 attr_done[dev].store(true, std::memory_order_release);
             }
         }
-        ema_rank_kernel<<<nb, kRankThreads, (size_t)K * 4, stream>>>(reinterpret_cast<const long long*>(idx), (int)N, (int)K, lrank,
+        ema_rank_kernel<<<nb, kRankCtaThreads, (size_t)K * 2, stream>>>(reinterpret_cast<const long long*>(idx), (int)N, (int)K, lrank,
                                                                      hist, flags);
         int* excl = reinterpret_cast<int*>(ws + l.excl);
         int* btot = reinterpret_cast<int*>(ws + l.btot);

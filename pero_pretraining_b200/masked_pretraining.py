@@ -13,31 +13,45 @@ import torch
 from . import ops
 
 
-_PINNED_RING = {"bufs": [], "events": [], "next": 0}
+class _RowStager:
+    """Per-device ring of (pinned host buffer, event) slots through which the ordered list of masked frames
+    reaches the GPU without a host-blocking copy: a pageable-memory H2D copy would block the host until everything
+    already queued on the stream has run.  A slot is reused only once the copy that last used it has executed (its
+    event), however far the host has run ahead of the device; nothing is allocated per step."""
+
+    def __init__(self, device, ring=8, capacity=8192):
+        self.device = device
+        self.host = [torch.empty(capacity, dtype=torch.int32).pin_memory() for _ in range(ring)]
+        self.events = [torch.cuda.Event() for _ in range(ring)]
+        self.used = [False] * ring
+        self.next = 0
+
+    def stage(self, rows):
+        i = self.next
+        self.next = (i + 1) % len(self.host)
+        n = int(rows.size)
+        if self.used[i]:
+            self.events[i].synchronize()
+        if self.host[i].numel() < n:
+            cap = int(n * 1.5) + 16
+            self.host[i] = torch.empty(cap, dtype=torch.int32).pin_memory()
+        self.host[i].numpy()[:n] = rows
+        # the device copy is a fresh tensor (it is saved for backward and must not be recycled with the ring)
+        out = torch.empty(n, dtype=torch.int32, device=self.device)
+        out.copy_(self.host[i][:n], non_blocking=True)
+        self.events[i].record(torch.cuda.current_stream(self.device))
+        self.used[i] = True
+        return out
 
 
-def _pinned_rows(rows, device, ring=8):
-    """Stage `rows` (numpy int32) through one of `ring` reusable pinned host buffers and return the device copy.
-    A pageable-memory H2D copy would block the host until everything already queued on the stream has run; a pinned
-    source keeps it asynchronous.  Each slot remembers the event recorded behind its last copy and is reused only
-    once that copy has executed, however far the host has run ahead of the device."""
-    st = _PINNED_RING
-    if len(st["bufs"]) < ring:
-        st["bufs"] = [torch.empty(max(4096, rows.size), dtype=torch.int32).pin_memory() for _ in range(ring)]
-        st["events"] = [None] * ring
-    i = st["next"]
-    st["next"] = (i + 1) % ring
-    if st["events"][i] is not None:
-        st["events"][i].synchronize()
-    if st["bufs"][i].numel() < rows.size:
-        st["bufs"][i] = torch.empty(int(rows.size * 1.5) + 16, dtype=torch.int32).pin_memory()
-    buf = st["bufs"][i][:rows.size]
-    buf.numpy()[:] = rows
-    out = buf.to(device, non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record(torch.cuda.current_stream(device))
-    st["events"][i] = ev
-    return out
+_ROW_STAGERS = {}      # device -> _RowStager (host-side staging buffers only; no model state)
+
+
+def _pinned_rows(rows, device):
+    st = _ROW_STAGERS.get(device)
+    if st is None:
+        st = _ROW_STAGERS[device] = _RowStager(device)
+    return st.stage(rows)
 
 
 def create_mask(labels, masking_prob, rng=None):
@@ -75,6 +89,38 @@ def _rows_from_mask(mask, labels, want, require_label, device):
     return rows[:m], m
 
 
+def masked_rows(mask, device, labels=None):
+    """(device int32 list of the frames with mask == 1 in ascending order, its length M) for a numpy or tensor mask: the
+    one trip of the mask to the GPU that both the pixel masking and the masked cross-entropy use."""
+    return _rows_from_mask(mask, labels, 1, False, torch.device(device))
+
+
+class PixelMasker(torch.nn.Module):
+    """TransformerEncoder.mask (models/transformers.py:27-34, 53-68) on the device: the 8-px image column of every masked
+    frame is overwritten, in place, with the reference's fixed noise tile (np.random.seed(42); np.random.rand(1, C,
+    patch_h, patch_w), reproduced here with a private RandomState so that numpy's global generator is not reseeded)."""
+
+    def __init__(self, height=40, patch_size=(40, 8), in_channels=3):
+        super().__init__()
+        self.height, self.patch_size, self.in_channels = height, patch_size, in_channels
+        tile = np.random.RandomState(42).rand(1, in_channels, patch_size[0], patch_size[1])
+        self.register_buffer("mask_tile", torch.tensor(tile[0], dtype=torch.float32), persistent=False)
+
+    def forward(self, x, mask=None, rows=None):
+        """x [N, C, H, W] float32 (modified in place and returned, like the reference); mask [N, W/8] {0,1} numpy/tensor,
+        or rows = masked_rows(mask, x.device) when the caller has staged the list already."""
+        if rows is None:
+            if mask is None:
+                return x
+            rows = masked_rows(mask, x.device)
+        r, m = rows
+        if m == 0:
+            return x
+        pw = self.patch_size[1]
+        frames = (x.shape[3] + pw - 1) // pw
+        return ops.mask_pixels_(x, r, self.mask_tile, frames)
+
+
 class _FusedHeadCE(torch.autograd.Function):
     """sum-of-terms masked CE of Linear(h) against labels; each term = (rows, weight)."""
 
@@ -98,13 +144,21 @@ class _FusedHeadCE(torch.autograd.Function):
             else:
                 loss_sum, lse, ws = torch.zeros(1, device=h2.device), None, None
             if dp_group is not None:
-                # (loss_sum, M) summed over the ranks in ONE small collective; the global count stays on the device
+                # (loss_sum, M) summed over the ranks in ONE small exchange; the global count stays on the device
                 # (scale = weight / M_global is applied by the kernels through their device-scalar argument), so the
                 # step has no host synchronisation here.  Empty global selection: 0 * (w / 0) = NaN, like the reference.
-                stats = torch.empty(2, dtype=torch.float32, device=h2.device)
-                stats[0:1].copy_(loss_sum)
-                stats[1].fill_(float(m_local))
-                torch.distributed.all_reduce(stats, group=dp_group)
+                if peer_range is not None:          # the library's own peer kernel on a 16-byte range of the peer buffer
+                    stats_range = peer_range.stats[len(saved)]
+                    stats = stats_range.tensor
+                    stats[0:1].copy_(loss_sum)
+                    stats[1].fill_(float(m_local))
+                    stats_range.all_reduce_sum_(n_blocks=1)
+                    stats = stats.clone()           # the 16-byte slot is reused by the next step
+                else:
+                    stats = torch.empty(2, dtype=torch.float32, device=h2.device)
+                    stats[0:1].copy_(loss_sum)
+                    stats[1].fill_(float(m_local))
+                    torch.distributed.all_reduce(stats, group=dp_group)
                 scale = weight / stats[1:2]                                  # [1] device tensor
                 term = (stats[0:1] * scale).view(())
             else:
@@ -156,7 +210,8 @@ class _FusedHeadCE(torch.autograd.Function):
             # every rank ends with the gradient of the single-process loss on the concatenated batch
             if peer is not None:
                 peer.all_reduce_sum_()
-                flat = flat.clone()            # the exchange range is reused by the next step
+                if not getattr(peer, "alias_grads", False):
+                    flat = flat.clone()        # the exchange range is reused by the next step
             else:
                 torch.distributed.all_reduce(flat, group=ctx.dp_group)
         d_W, d_b = flat[:head.V * head.Dh].view(head.V, head.Dh), flat[head.V * head.Dh:]
@@ -183,24 +238,32 @@ class LinearHead(torch.nn.Module):
     def forward(self, x):
         return self.linear(x)
 
-    def enable_peer_exchange(self, group=None):
-        """Data-parallel gradients d_W | d_b of masked_loss(dp_group=...) are then reduced over the ranks by
-        libpero_b200's own NVLink/NVSwitch kernel in a peer-mapped buffer instead of torch.distributed."""
+    def enable_peer_exchange(self, group=None, alias_grads=False):
+        """Data-parallel gradients d_W | d_b (and the (loss_sum, M) pair of the forward) of masked_loss(dp_group=...) are
+        then reduced over the ranks by libpero_b200's own NVLink/NVSwitch kernel in a peer-mapped buffer instead of
+        torch.distributed.
+        alias_grads=True: the gradients handed to autograd are VIEWS of the exchange range (no 16.8 MB copy per step at
+        the bench shape).  The range is overwritten by the next backward, so this is only valid when every backward is
+        followed by the optimizer step (no gradient accumulation over several backward passes)."""
         from .peer import PeerBuffer, PeerRange
         W = self.linear.weight
         n = W.shape[0] * W.shape[1] + W.shape[0]
-        buf = PeerBuffer(4 * n + 256, W.device, group)
+        buf = PeerBuffer(4 * n + 1024, W.device, group)
         self._peer_range = PeerRange(buf, n, torch.float32)
+        self._peer_range.alias_grads = bool(alias_grads)
+        self._peer_range.stats = [PeerRange(buf, 4, torch.float32) for _ in range(2)]     # one per loss term
         return self
 
     def invalidate(self):
-        """Forget the prepared bf16 operands.  The cache is keyed on (data_ptr, _version) of weight and bias; a write
+        """Forget the prepared bf16 operands.  The caches are keyed on (data_ptr, _version) of weight and bias; a write
         through `.data` (e.g. `head.linear.weight.data.copy_(...)`) does not bump `_version`, so call this after one.
         load_state_dict() does it by itself."""
         self._prep_tag = None
+        self._argmax_tag = None
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._prep_tag = None
+        self._argmax_tag = None
         return super()._load_from_state_dict(*args, **kwargs)
 
     def _prepared(self):
@@ -216,7 +279,7 @@ class LinearHead(torch.nn.Module):
             self._prep_tag = tag
         return self._prep
 
-    def masked_loss(self, hidden, labels, mask, unmasked_weight=None, dp_group=None):
+    def masked_loss(self, hidden, labels, mask, unmasked_weight=None, dp_group=None, rows=None):
         """Fused LinearHead + MaskedCrossEntropyLoss on hidden states [Nl, T, Dh] (or [N, Dh]).
         Any hidden size that is a multiple of 4 takes the fused path (up to 512 the masked rows stay resident in shared
         memory); other sizes go through the logits-in kernels on `self.linear(hidden)` (single process only)."""
@@ -226,7 +289,9 @@ class LinearHead(torch.nn.Module):
                 raise ops._lib.PeroError("data-parallel masked_loss needs a hidden size that is a multiple of 4")
             from .logits_ce import masked_ce_from_logits
             return masked_ce_from_logits(self.linear(hidden), labels, mask, unmasked_weight)
-        rows, m = _rows_from_mask(mask, labels, 1, False, dev)
+        # rows = (device int32 list of the frames with mask == 1, its length): what masked_rows(mask, device) returns,
+        # when the caller has staged it already (MaskedTransformerEncoder shares it with the pixel masking)
+        rows, m = rows if rows is not None else _rows_from_mask(mask, labels, 1, False, dev)
         terms = [(rows, m, 1.0)]
         if unmasked_weight is not None:
             rows0, m0 = _rows_from_mask(mask, labels, 0, True, dev)     # model.py:85-90
@@ -234,6 +299,22 @@ class LinearHead(torch.nn.Module):
         return _FusedHeadCE.apply(hidden, self.linear.weight, self.linear.bias, labels, self._prepared(), terms, dp_group,
                                   self._peer_range if dp_group is not None else None)
 
+
+    def argmax(self, hidden):
+        """torch.argmax(self(hidden), dim=-1) for every frame -- what MaskedVisualizer shows as predictions
+        (masked_pretraining/visualizer.py:32) -- without materialising the [N, V] logits: the head is handed to the
+        distance kernel as a codebook, arg-min of -2 (h.W_v + b_v).  Lowest label on exact ties, like torch.argmax.
+        bf16 operands: the winner may differ from the fp32 argmax where the two best logits are within bf16 rounding."""
+        W, b = self.linear.weight, self.linear.bias
+        if not W.is_cuda:
+            raise ops._lib.PeroError("LinearHead.argmax runs on a CUDA (B200) device only; there is no CPU path")
+        tag = (W.data_ptr(), W._version, None if b is None else (b.data_ptr(), b._version), W.device)
+        if getattr(self, "_argmax_tag", None) != tag:
+            self._argmax_cb = ops.head_argmax_codebook(W.detach().float(), None if b is None else b.detach().float())
+            self._argmax_tag = tag
+        h2 = hidden.detach().reshape(-1, hidden.shape[-1]).float().contiguous()
+        idx, _, _ = ops.vq_assign(h2, self._argmax_cb, h2.shape[0], 1, channels_first=False)
+        return idx.view(hidden.shape[:-1])
 
     def masked_errors(self, hidden, labels, mask, ks=(1, 3, 10)):
         """Evaluation on the masked frames without materialising logits: what Tester.test_step + _update_errors
@@ -283,12 +364,16 @@ class MaskedCrossEntropyLoss(torch.nn.Module):
 class MaskedTransformerEncoder(torch.nn.Module):
     """masked_pretraining/model.py:33-69.  `backbone(images, mask=mask)` -> [n, c, w] is the caller's module."""
 
-    def __init__(self, backbone, head, loss=None, output='auto'):
+    def __init__(self, backbone, head, loss=None, output='auto', pixel_masker=None):
+        """pixel_masker: a PixelMasker -> the input masking of the backbone (models/transformers.py:53-68) runs here, on the
+        device, from the same staged masked-frame list as the loss, and the backbone is called with mask=None (its own
+        mask() would redo the same overwrite after two more host->device trips of the mask)."""
         super().__init__()
         self.backbone = backbone
         self.head = head
         self.loss = MaskedCrossEntropyLoss() if loss is None else loss
         self.output_mode = output      # 'auto': logits for every frame only in eval mode; True / False to force
+        self.pixel_masker = pixel_masker
         self._dp_group = None
 
     def enable_data_parallel(self, group=None, peer=True):
@@ -306,15 +391,30 @@ class MaskedTransformerEncoder(torch.nn.Module):
     def encode(self, images, mask=None):
         return self.head(self.hidden(images, mask))
 
-    def forward(self, x, labels=None, mask=None):
+    def predict(self, x, mask=None):
+        """Label prediction of every frame, int64 [n, w]: torch.argmax(forward(...)['output'], dim=-1) of
+        masked_pretraining/visualizer.py:32 without the [n, w, V] logits."""
         hidden = self.hidden(x, mask)
+        if isinstance(self.head, LinearHead):
+            return self.head.argmax(hidden)
+        return torch.argmax(self.head(hidden), dim=-1)
+
+    def forward(self, x, labels=None, mask=None):
+        rows = None
+        if mask is not None and self.pixel_masker is not None:
+            rows = masked_rows(mask, x.device)
+            x = self.pixel_masker(x, rows=rows)
+            hidden = self.hidden(x, None)
+        else:
+            hidden = self.hidden(x, mask)
         want_output = (not self.training) if self.output_mode == 'auto' else bool(self.output_mode)
         output = self.head(hidden) if want_output else None
         loss = None
         if mask is not None and labels is not None:
             fused = isinstance(self.head, LinearHead) and isinstance(self.loss, MaskedCrossEntropyLoss)
             if fused:
-                loss = self.head.masked_loss(hidden.contiguous(), labels, mask, self.loss.unmasked_weight, self._dp_group)
+                loss = self.head.masked_loss(hidden.contiguous(), labels, mask, self.loss.unmasked_weight, self._dp_group,
+                                             rows=rows)
             else:
                 if output is None:
                     output = self.head(hidden)

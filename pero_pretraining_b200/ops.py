@@ -84,25 +84,32 @@ def vq_assign(x, codebook, n_lines, frames_per_line, channels_first, want_dmin=F
 
 
 def vq_forward(x, codebook, weight, ema_w, ema_cluster_size, decay, epsilon, update_ema, n_lines, frames_per_line,
-               channels_first=True):
+               channels_first=True, out=None, idx=None, ws=None):
     """The whole VectorQuantizer.forward in one call of the C ABI (pero_vq_forward): returns (quantized with the
-    layout of x, idx int64 [N]); with update_ema the EMA state, weight and the prepared codebook are updated in place."""
+    layout of x, idx int64 [N]); with update_ema the EMA state, weight and the prepared codebook are updated in place.
+    out / idx / ws: preallocated outputs and workspace (CUDA-graph capture with static buffers)."""
     L = _lib.lib()
     N = int(n_lines) * int(frames_per_line)
     K, D = codebook.K, codebook.D
     dev = x.device
-    out = torch.empty_like(x)
-    idx = torch.empty(N, dtype=torch.int64, device=dev)
+    out = torch.empty_like(x) if out is None else out
+    idx = torch.empty(N, dtype=torch.int64, device=dev) if idx is None else idx
     if N == 0:
         return out, idx
     upd = 1 if update_ema else 0
     wsb = L.pero_vq_forward_workspace_bytes(N, K, D, upd)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    if ws is None or ws.numel() < wsb:
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     check(L.pero_vq_forward(x.data_ptr(), int(n_lines), int(frames_per_line), 1 if channels_first else 0, K, D,
                             codebook.blob.data_ptr(), codebook.nbytes, weight.data_ptr(), _p(ema_w), _p(ema_cluster_size),
                             float(decay), float(epsilon), upd, out.data_ptr(), idx.data_ptr(), ws.data_ptr(), wsb, _stream()),
           "pero_vq_forward")
     return out, idx
+
+
+def vq_forward_workspace(N, K, D, update_ema, device):
+    return torch.empty(_lib.lib().pero_vq_forward_workspace_bytes(int(N), int(K), int(D), 1 if update_ema else 0), dtype=torch.uint8,
+                       device=device)
 
 
 def vq_packed_init(N, device, out=None):
@@ -346,6 +353,34 @@ def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=Tru
                                      float(inv_count), v0, v1, _p(d_h), _p(d_W), _p(d_b), ws.data_ptr(), wsb,
                                      _stream()), "pero_masked_ce_bwd_range")
     return (d_h, d_W, d_b, flat) if return_flat else (d_h, d_W, d_b)
+
+
+def head_argmax_codebook(W, bias):
+    """The head as a prepared "codebook" of the distance kernel: vq_assign(hidden_rows, blob, ...) then returns
+    argmax_v (h.W_v + b_v) per frame (pero_head_argmax_prepare)."""
+    W = _f32c(W, "W")
+    b = None if bias is None else _f32c(bias, "bias")
+    V, Dh = W.shape
+    cb = PreparedCodebook(V, Dh, W.device)
+    check(_lib.lib().pero_head_argmax_prepare(W.data_ptr(), _p(b), V, Dh, cb.blob.data_ptr(), cb.nbytes, _stream()),
+          "pero_head_argmax_prepare")
+    return cb
+
+
+def mask_pixels_(x, rows, tile, frames_per_line):
+    """In place: the 8-px column of every masked frame of the line images x [Nl, C, H, W] is overwritten with the noise
+    tile [C, H, pw] (TransformerEncoder.mask, models/transformers.py:53-68); rows: int32 masked-frame indices."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4):
+        raise TypeError("x must be a contiguous CUDA float32 [Nl, C, H, W] tensor")
+    tile = _f32c(tile, "tile")
+    Nl, C, H, W = x.shape
+    if tuple(tile.shape[:2]) != (C, H):
+        raise ValueError(f"tile must be [C={C}, H={H}, patch_width], got {tuple(tile.shape)}")
+    if rows.dtype != torch.int32 or not rows.is_cuda:
+        raise TypeError("rows must be a CUDA int32 tensor")
+    check(_lib.lib().pero_mask_pixels(x.data_ptr(), Nl, C, H, W, rows.data_ptr(), rows.numel(), int(frames_per_line),
+                                      tile.shape[2], tile.data_ptr(), _stream()), "pero_mask_pixels")
+    return x
 
 
 _MASK_DTYPES = {torch.int64: 0, torch.int32: 1, torch.uint8: 2, torch.bool: 2}

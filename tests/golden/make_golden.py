@@ -200,9 +200,37 @@ def gen_kmeans_minibatch(name, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
 
 
+def gen_pixel_mask(name, seed):
+    """TransformerEncoder.mask (models/transformers.py:53-68) executed from the reference's own code.  The class cannot
+    be constructed on a CPU-only host (its __init__ moves the pattern .to("cuda"), :34), so the unbound method runs on
+    a stand-in object that carries exactly the attributes the method reads, built the way __init__ builds them
+    (:27-34) but left on the CPU.  Also stores argmax labels of a small logits tensor (visualizer.py:32)."""
+    import types
+    from pero_pretraining.models.transformers import TransformerEncoder
+    rng = np.random.RandomState(seed)
+    N, C, H, W, pw = 3, 3, 40, 136, 8
+    np.random.seed(42)                                                                     # :30
+    mask_tile = torch.tensor(np.random.rand(1, C, 40, pw), dtype=torch.float32)              # :31-32
+    stand_in = types.SimpleNamespace(in_channels=C, height=H, mask_pattern=mask_tile.repeat(1, 1, 1, 512))   # :34 minus .to("cuda")
+    x = torch.tensor(rng.rand(N, C, H, W), dtype=torch.float32)
+    mask = (rng.rand(N, W // pw) < 0.3).astype(np.int64)
+    mask[0, 0] = 1
+    mask[2, -1] = 1
+    out = TransformerEncoder.mask(stand_in, x.clone(), mask)
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(2, 9, 50, generator=g)
+    logits[0, 0, 7] = logits[0, 0, 31] = 9.0                                                 # exact tie: first index wins
+    rec = {"x": t2n(x), "mask": mask, "masked": t2n(out), "tile": t2n(mask_tile[0]),
+           "logits": t2n(logits), "argmax": t2n(torch.argmax(logits, dim=-1))}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "kmeans_minibatch":       # only the scikit-learn fixture
         gen_kmeans_minibatch("kmeans_minibatch", seed=61)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pixel_mask":
+        gen_pixel_mask("pixel_mask", seed=71)
         sys.exit(0)
     gen_vq("vq_cold_3steps", K=64, D=16, nl=4, H=1, W=12, decay=0.99, steps=3, seed=11)
     gen_vq("vq_warm_3steps", K=48, D=32, nl=3, H=2, W=20, decay=0.99, steps=3, seed=12, spread=True)
@@ -213,6 +241,7 @@ if __name__ == "__main__":
     gen_kmeans("kmeans_assign", seed=41)
     gen_masked_ce("masked_ce", seed=51)
     gen_kmeans_minibatch("kmeans_minibatch", seed=61)
+    gen_pixel_mask("pixel_mask", seed=71)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):

@@ -151,6 +151,42 @@ def test_model_glue_train_and_eval(cuda_dev):
     assert abs(ev["loss"].item() - ref.item()) <= LOSS_RTOL * abs(ref.item())
     assert abs(out["loss"].item() - ref.item()) <= LOSS_RTOL * abs(ref.item())
     assert model(images)["loss"] is None
+    # predictions of every frame without the logits (visualizer.py:32)
+    pred = model.predict(images)
+    assert pred.shape == (4, 32) and (pred == ev["output"].argmax(-1)).float().mean().item() > 0.97
+
+
+def test_model_glue_device_pixel_masking(cuda_dev):
+    """MaskedTransformerEncoder(pixel_masker=PixelMasker()): the backbone sees exactly the pixels the reference's
+    backbone.mask() would produce (models/transformers.py:45-68), from ONE staged masked-frame list shared with the
+    loss; same loss as the path in which the backbone masks its own input."""
+    from pero_pretraining_b200 import LinearHead, MaskedTransformerEncoder, PixelMasker
+
+    class Backbone(torch.nn.Module):          # masks its own input like the reference's TransformerEncoder.forward
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 64, (40, 8), stride=(40, 8))
+            self.tile = T(O.mask_tile(3, (40, 8)))
+            self.seen = None
+
+        def forward(self, images, mask=None):
+            if mask is not None:
+                images = T(O.mask_pixels(images.cpu().numpy(), np.asarray(mask), self.tile.numpy())).to(images.device)
+            self.seen = images.detach().clone()
+            return self.conv(images).squeeze(2)
+
+    torch.manual_seed(0)
+    head = LinearHead(64, 200)
+    a = MaskedTransformerEncoder(Backbone(), head).to(cuda_dev).train()
+    b = MaskedTransformerEncoder(a.backbone, head, pixel_masker=PixelMasker()).to(cuda_dev).train()
+    images = torch.rand(4, 3, 40, 256, device=cuda_dev)
+    labels = torch.randint(0, 200, (4, 32), device=cuda_dev)
+    mask = (np.random.default_rng(1).random((4, 32)) < 0.3).astype(int)
+    la = a(images.clone(), labels, mask)["loss"]
+    seen_a = a.backbone.seen
+    lb = b(images.clone(), labels, mask)["loss"]
+    assert torch.equal(seen_a, b.backbone.seen)
+    assert torch.equal(la, lb)
 
 
 def test_mask_compact_matches_nonzero(cuda_dev):
@@ -242,3 +278,54 @@ def test_masked_errors_match_tester(cuda_dev, Nl, T_, Dh, V, p):
     assert np.array_equal(rank.cpu().numpy()[clear], ref_rank[clear])
     acc = update_errors(update_errors({}, res), res)
     assert acc["length"] == 2 * res["length"] and int(acc["errors_3"]) == 2 * int(res["errors_3"])
+
+
+def test_pixel_masking_golden_and_shared_rows(cuda_dev):
+    """PixelMasker (TransformerEncoder.mask, models/transformers.py:53-68) bit-exact against the reference's output, from a
+    numpy mask, a tensor mask and a pre-staged row list; ragged width (W not a multiple of 8) against the oracle."""
+    from pero_pretraining_b200 import PixelMasker, masked_rows
+    g = load_golden("pixel_mask")
+    pm = PixelMasker().to(cuda_dev)
+    assert torch.equal(pm.mask_tile.cpu(), T(g["tile"]))
+    for mask in (g["mask"], T(g["mask"]).to(cuda_dev)):
+        x = T(g["x"]).to(cuda_dev)
+        out = pm(x, mask)
+        assert out.data_ptr() == x.data_ptr()                   # in place, like the reference
+        assert torch.equal(out.cpu(), T(g["masked"]))
+    x = T(g["x"]).to(cuda_dev)
+    assert torch.equal(pm(x, rows=masked_rows(g["mask"], cuda_dev)).cpu(), T(g["masked"]))
+    x = T(g["x"]).to(cuda_dev)
+    assert torch.equal(pm(x, np.zeros_like(g["mask"])).cpu(), T(g["x"]))       # empty mask: untouched
+    rng = np.random.default_rng(3)
+    xr = rng.random((2, 3, 40, 77), dtype=np.float32)
+    mr = (rng.random((2, 10)) < 0.5).astype(int)
+    mr[1, 9] = 1                                                # the last, partial column
+    got = pm(T(xr).to(cuda_dev), mr).cpu().numpy()
+    np.testing.assert_array_equal(got, O.mask_pixels(xr, mr, g["tile"]))
+
+
+def test_head_argmax_without_logits(cuda_dev):
+    """LinearHead.argmax == torch.argmax(head(hidden), -1) (masked_pretraining/visualizer.py:32) except where the two best
+    logits are within bf16 rounding; exact ties -> lowest label; the golden logits reproduce exactly."""
+    from pero_pretraining_b200 import LinearHead
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for Nl, T_, Dh, V in [(4, 50, 512, 4096), (3, 17, 96, 1000), (2, 128, 768, 300)]:
+        head = LinearHead(Dh, V).to(cuda_dev)
+        h = torch.randn(Nl, T_, Dh, generator=g).to(cuda_dev)
+        got = head.argmax(h)
+        z = head(h).double()
+        ref = torch.argmax(z, dim=-1)
+        assert got.shape == ref.shape and got.dtype == torch.int64
+        top2 = torch.topk(z, 2, dim=-1).values
+        gap = (top2[..., 0] - top2[..., 1]) / top2[..., 0].abs().clamp_min(1e-6)
+        differs = got != ref
+        assert float(differs.float().mean()) < 0.02
+        assert not bool(differs.any()) or float(gap[differs].max()) < 2e-2
+    # one-hot-like head: logits are exact in bf16, duplicates resolve to the lowest label
+    head = LinearHead(64, 128).to(cuda_dev)
+    with torch.no_grad():
+        head.linear.weight.zero_(); head.linear.bias.zero_()
+        head.linear.weight[7, 3] = 2.0; head.linear.weight[31, 3] = 2.0; head.linear.weight[90, 5] = 4.0
+    h = torch.zeros(1, 3, 64, device=cuda_dev)
+    h[0, 0, 3] = 1.0; h[0, 1, 5] = 1.0
+    assert head.argmax(h).tolist() == [[7, 90, 0]]

@@ -250,6 +250,35 @@ def test_vq_ema_three_steps_vs_oracle_all_sort_branches(cuda_dev, N, K, D, branc
         assert torch.equal(i1, i2) and torch.equal(w1, w2) and torch.equal(e1, e2), f"{branch}: not bit-identical run to run"
 
 
+def test_vq_cuda_graph_forward_matches_eager_launches(cuda_dev):
+    """VectorQuantizer.enable_cuda_graph(): the replayed graph gives the same bits as the eager launches over several
+    training steps (EMA state carried through the graph's in-place updates), in eval mode, and after a shape change."""
+    from pero_pretraining_b200 import VectorQuantizer
+    g = torch.Generator(device="cpu").manual_seed(91)
+    K, D = 512, 64
+    w0 = torch.randn(K, D, generator=g)
+    xs = [torch.randn(nl, D, 1, 32, generator=g) for nl in (8, 8, 8, 5, 8)]
+
+    def run(graphed):
+        vq = VectorQuantizer(K, D, 0.25, 0.99).to(cuda_dev).train()
+        with torch.no_grad():
+            vq.embedding.weight.copy_(w0); vq.ema_w.copy_(w0); vq.ema_cluster_size.fill_(1.0)
+        vq.enable_cuda_graph(graphed)
+        outs = []
+        for i, x in enumerate(xs):
+            vq.train(i != 3)
+            xd = x.to(cuda_dev).requires_grad_(True)
+            q, idx = vq(xd)
+            (q * 2.0).sum().backward()
+            assert torch.equal(xd.grad, torch.full_like(xd, 2.0))         # straight-through identity
+            outs.append((q.detach().clone(), idx.clone(), vq.embedding.weight.detach().clone(), vq.ema_cluster_size.clone()))
+        return outs
+
+    for a, b in zip(run(False), run(True)):
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+
+
 def test_ema_accumulate_large_and_wide_codebooks(cuda_dev):
     """pero_vq_ema_accumulate beyond the single-CTA sorts: N = 65536 (config 4's frames per step), K up to 65536."""
     from pero_pretraining_b200 import ops

@@ -150,3 +150,13 @@ def test_minibatch_kmeans_step_matches_sklearn_golden():
         _, _, c, w = O.minibatch_kmeans_step(g[f"batch{i}"], c, w)
         np.testing.assert_allclose(w, g[f"counts{i}"], rtol=0, atol=0)
         np.testing.assert_allclose(c, g[f"centers{i}"], rtol=2e-6, atol=2e-6)
+
+
+def test_pixel_mask_and_predictions_match_reference():
+    """TransformerEncoder.mask (models/transformers.py:53-68) and the visualizer's argmax (visualizer.py:32) against the
+    outputs of the reference's own code (tests/golden/make_golden.py gen_pixel_mask)."""
+    g = load_golden("pixel_mask")
+    np.testing.assert_array_equal(O.mask_tile(3, (40, 8)), g["tile"])
+    np.testing.assert_array_equal(O.mask_pixels(g["x"], g["mask"], g["tile"]), g["masked"])
+    np.testing.assert_array_equal(O.predict_labels(g["logits"]), g["argmax"])
+    assert g["argmax"][0, 0] == 7          # the exact tie resolves to the first index

@@ -7,6 +7,10 @@
 `launches`: CSV of `ncu --metrics gpu__time_duration.sum --clock-control none` over bench.py; prints the last
 full step (cold-cache, serialised per-launch times: compare SHARES, not absolutes).
 `full`: `.ncu-rep` of `ncu --set full`; prints duration, tensor-pipe utilisation, DRAM bytes, registers.
+`traffic`: `.ncu-rep` holding the distance GEMM -> profiles/roofline_traffic.json (DRAM bytes per launch + a hash of the
+kernel's sources; bench.py reports `roofline.traffic` from it only while the sources are unchanged).
+
+    python tools/summarize_profiles.py traffic  gpurun_out/assign_r2.ncu-rep profiles/roofline_traffic.json
 """
 import csv
 import subprocess
@@ -66,5 +70,36 @@ def full(src, dst):
     print(f"wrote {dst}: {len(data)} kernels")
 
 
+TRAFFIC_SOURCES = ["pero_pretraining_b200/csrc/gemm_core.cuh", "pero_pretraining_b200/csrc/gemm_host.cuh",
+                   "pero_pretraining_b200/csrc/epilogues.cuh", "pero_pretraining_b200/csrc/ptx.cuh",
+                   "pero_pretraining_b200/csrc/vq_assign.cu"]
+
+
+def _bytes(value, unit):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    return float(value.replace(",", "")) * scale
+
+
+def traffic(src, dst):
+    import hashlib
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H, units, data = rows[0], rows[1], rows[2:]
+    ki, ri, wi = H.index("Kernel Name"), H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum")
+    sel = [r for r in data if "ArgminEpi" in r[ki]]
+    rd = sum(_bytes(r[ri], units[ri]) for r in sel) / len(sel)
+    wr = sum(_bytes(r[wi], units[wi]) for r in sel) / len(sel)
+    hsh = hashlib.sha256()
+    for f in TRAFFIC_SOURCES:
+        hsh.update(open(os.path.join(root, f), "rb").read())
+    rec = {"kernel": sel[0][ki][:80], "launches": len(sel), "dram_read_bytes": rd, "dram_write_bytes": wr,
+           "traffic_bytes": rd + wr, "capture": os.path.basename(src), "sources": TRAFFIC_SOURCES, "sources_sha256": hsh.hexdigest()}
+    json.dump(rec, open(dst, "w"), indent=1)
+    print(f"wrote {dst}: {rd / 1e6:.2f} MB read + {wr / 1e6:.2f} MB written per launch over {len(sel)} launches")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
