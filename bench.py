@@ -257,8 +257,13 @@ class DeviceStep:
             self.peer_ema = PeerBuffer(4 * self.n_ema + 1024, dev, n_blocks=blocks, use_multicast=mc)
             self.peer = PeerBuffer(4 * self.n_grad + 1024, dev, n_blocks=blocks, use_multicast=mc)
             self.ema_x = PeerRange(self.peer_ema, self.n_ema, torch.float32)
-            self.grad_x = PeerRange(self.peer, self.n_grad + 1, torch.float32)
+            self.grad_x = PeerRange(self.peer, c["V"] * c["Dh"], torch.float32)             # d_W
+            # d_b | loss_sum travel as a small message of their own (own buffer = own barrier words: it may overlap the
+            # d_W exchange), so that the 16.8 MB exchange starts the moment the d_W GEMM is done
+            self.peer_db = PeerBuffer(4 * (c["V"] + 4) + 1024, dev, n_blocks=2, use_multicast=mc)
+            self.db_x = PeerRange(self.peer_db, c["V"] + 4, torch.float32)
             self.s_comm_ema = torch.cuda.Stream(device=dev, priority=-1)
+            self.s_comm_db = torch.cuda.Stream(device=dev, priority=-1)
             # label-axis ranges of the head backward: each range's d_W rows are exchanged while the next is computed
             chunks = max(1, int(os.environ.get("PERO_DP_CHUNKS", "1")))
             step = max(256, (c["V"] // chunks + 255) // 256 * 256)
@@ -289,25 +294,32 @@ class DeviceStep:
         assigned = torch.cuda.Event()
         assigned.record(main)
         s_ce.wait_event(assigned)
-        # --- chain A (main stream)
+        # --- chain A (main stream): unpack, EMA sums (their exchange goes to the communication stream at once), quantize +
+        # commitment loss fwd/bwd, EMA apply.  Data parallel: ONE stream, EMA sums first, so that their exchange is out of
+        # the way before the gradient exchange needs the links (177 instead of 186 us per step at 2 GPUs).  Single GPU:
+        # the EMA update runs on its own low-priority stream beside the rest (133 instead of 143 us).
         idx, _ = ops.vq_unpack(packed)
-        s_ema.wait_stream(main)
+        split_ema = os.environ.get("PERO_STEP_SPLIT_EMA", "0" if self.dp else "1") == "1"
+        if split_ema:
+            s_ema.wait_stream(main)
+        with torch.cuda.stream(s_ema if split_ema else main):
+            if not self.dp:
+                sums = ops.vq_ema_accumulate(x_rows, idx, c["K"])
+            else:
+                sums = ops.vq_ema_accumulate(x_rows, idx, c["K"], out=self.ema_x.tensor)
+                self.s_comm_ema.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.s_comm_ema):
+                    self.ema_x.all_reduce_sum_()
         q = ops.vq_gather_st(x_rows, idx, self.weight, c["lines"], c["frames"], True)
         gathered = torch.cuda.Event()
         gathered.record(main)
         loss_c = ops.mse_fwd(q, self.x, 0.0, c["commitment_cost"])
         g_x = ops.vq_st_commit_bwd(self.gq, q, self.x, 2.0 * c["commitment_cost"] / q.numel())
-        # --- chain B
-        with torch.cuda.stream(s_ema):
-            if not self.dp:
-                sums = ops.vq_ema_accumulate(x_rows, idx, c["K"])
-            else:
-                sums = ops.vq_ema_accumulate(x_rows, idx, c["K"], out=self.ema_x.tensor)
-                self.s_comm_ema.wait_stream(s_ema)
-                with torch.cuda.stream(self.s_comm_ema):
-                    self.ema_x.all_reduce_sum_()
-                s_ema.wait_stream(self.s_comm_ema)
-            s_ema.wait_event(gathered)
+        with torch.cuda.stream(s_ema if split_ema else main):
+            if self.dp:
+                torch.cuda.current_stream().wait_stream(self.s_comm_ema)
+            if split_ema:
+                s_ema.wait_event(gathered)
             ops.vq_ema_apply(sums, self.ema_w, self.cs, self.weight, c["decay"], c["epsilon"], self.cb)
         # --- chain C
         Dh = c["Dh"]
@@ -321,25 +333,35 @@ class DeviceStep:
                 # loss_sum rides in the same exchange range as d_W | d_b.  The backward walks the label axis range by
                 # range: each range's rows of d_W are reduced over the ranks on the communication stream while the
                 # next range (and finally d_h) is computed.
-                g = self.grad_x.tensor
+                g, gb = self.grad_x.tensor, self.db_x.tensor
+                V = c["V"]
+                # the loss sum is read out of the log-sum-exp partials on a communication stream, beside the backward
+                # GEMMs, straight into its slot of the small exchange range (d_b | loss_sum)
+                self.s_comm_db.wait_stream(s_ce)
+                with torch.cuda.stream(self.s_comm_db):
+                    loss_sum, lse = ops.masked_ce_loss(ws, N, Dh, self.M, V, loss_out=gb[V:V + 1])
+                # phase 1 per label range: dlogits + d_W; each range's rows of d_W are reduced over the ranks on the
+                # communication stream while the next range (and finally d_h | d_b) is computed
                 for v0, v1 in self.v_ranges:
-                    _, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global,
-                                                          ws=ws, return_flat=True, want_dh=False, flat_out=g[:self.n_grad],
-                                                          ws_from_fwd=True, v_range=(v0, v1), labels_packed=True)
-                    last = v1 == c["V"]             # the last exchange also carries d_b | loss_sum, which follow d_W
-                    if last:
-                        loss_sum, lse = ops.masked_ce_loss(ws, N, Dh, self.M, c["V"], loss_out=g[self.n_grad:])
+                    _, d_W, _ = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global,
+                                                  ws=ws, want_dh=False, want_db=False, dw_out=g.view(V, Dh),
+                                                     ws_from_fwd=True, v_range=(v0, v1), labels_packed=True)
                     self.s_comm.wait_stream(s_ce)
                     with torch.cuda.stream(self.s_comm):
-                        numel = (self.grad_x.padded - v0 * Dh) if last else (v1 - v0) * Dh
-                        self.peer.all_reduce_sum_(self.grad_x.offset + 4 * v0 * Dh, numel)
-                d_h, _, _ = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global, ws=ws,
-                                              want_dw=False, ws_from_fwd=True, labels_packed=True)
+                        self.peer.all_reduce_sum_(self.grad_x.offset + 4 * v0 * Dh, (v1 - v0) * Dh)
+                # phase 2: d_h and d_b from the dlogits in the workspace, then the small exchange
+                d_h, _, d_b = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global, ws=ws,
+                                                want_dw=False, want_db=True, db_out=gb[:V], ws_from_fwd=True, labels_packed=True)
+                self.s_comm_db.wait_stream(s_ce)
+                with torch.cuda.stream(self.s_comm_db):
+                    self.db_x.all_reduce_sum_()
+                flat = g
         main.wait_stream(s_ema)
         main.wait_stream(s_ce)
         if self.dp:
             main.wait_stream(self.s_comm)
             main.wait_stream(self.s_comm_ema)
+            main.wait_stream(self.s_comm_db)
         self.out = dict(idx=idx, x_rows=x_rows, q=q, loss_c=loss_c, g_x=g_x, sums=sums, loss_sum=loss_sum, lse=lse, ws=ws,
                         d_h=d_h, d_W=d_W, d_b=d_b, flat=flat)
         return self.out
@@ -395,13 +417,14 @@ def e2e_leg(batch, dev, dp, steps, warm, repeats=3):
     if dp:
         vq.enable_data_parallel(group)          # peer-memory exchange of the EMA sums|counts
         head.enable_peer_exchange(group, alias_grads=True)      # ... and of d_W | d_b (every backward is followed by a reset)
-    else:
+    if os.environ.get("PERO_E2E_GRAPH", "1") != "0":
         vq.enable_cuda_graph()                  # the forward's kernel sequence as one graph replay (public opt-in)
-    x_host, h_host = batch["x"].pin_memory(), batch["h"].bfloat16().pin_memory()
+    h_src = batch["h"].bfloat16() if os.environ.get("PERO_E2E_BF16", "1") != "0" else batch["h"]
+    x_host, h_host = batch["x"].pin_memory(), h_src.pin_memory()
     gq = batch["gq"].to(dev)
     mask = batch["mask"]
     n_rows = int((mask.reshape(-1) == 1).sum())
-    h2d = x_host.numel() * 4 + h_host.numel() * 2 + n_rows * 4
+    h2d = x_host.numel() * 4 + h_host.numel() * h_host.element_size() + n_rows * 4
     loss_val = None
     # Double-buffered input staging: the H2D copy of step i+1 runs on a copy stream while step i computes;
     # every step still waits for ITS OWN inputs to arrive and reads ITS OWN loss back.
@@ -890,8 +913,8 @@ def our_arm(args):
                "ms_per_step": s_per_step * 1e3, "ms_per_step_min": s_min * 1e3, "ms_per_step_all": [t * 1e3 for t in s_all],
                "statistic": f"median of {len(s_all)} timed loops of {args.steps} steps",
                "inputs": "x fp32 [64,256,1,128] + hidden states bf16 [64,128,512] + masked-row list, pinned host memory",
-               "api": ("VectorQuantizer.forward (enable_cuda_graph) / calculate_loss + LinearHead.masked_loss + backward"
-                       if not dp else "VectorQuantizer.forward (data parallel) / calculate_loss + LinearHead.masked_loss + backward")}
+               "api": ("VectorQuantizer.forward (enable_cuda_graph" + (", data parallel" if dp else "") +
+                       ") / calculate_loss + LinearHead.masked_loss + backward")}
     _log("e2e leg done")
     # the step's graph, exchange buffers and streams are no longer needed: free them before the large configs
     launch_mode = "cuda_graph" if graph is not None else "eager"

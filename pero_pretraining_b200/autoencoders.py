@@ -31,38 +31,14 @@ class _QuantizeST(torch.autograd.Function):
             x = x.contiguous()
         cb = vq._prepared_codebook()
         update = vq.decay > 0.0 and vq.training
-        weight = vq.embedding.weight.data
-        if vq._dp_group is None:
-            # single process: one call of the C ABI for assign -> quantize -> EMA update
-            if vq._use_cuda_graph and x.numel() > 0:
-                out, idx = vq._graphed_forward(x, cb, update, n_lines, frames)
-            else:
-                out, idx = ops.vq_forward(x, cb, weight, vq.ema_w.data if update else None,
-                                          vq.ema_cluster_size if update else None, vq.decay, vq.epsilon, update and x.numel() > 0,
-                                          n_lines, frames, channels_first=True)
-            if update and x.numel() > 0:
-                vq._codebook_tag = vq._weight_tag()
-            ctx.mark_non_differentiable(idx)
-            return out.view(inputs.shape), idx
-        # data parallel: the EMA sums|counts are exchanged between accumulate and apply
-        idx, _, x_rows = ops.vq_assign(x, cb, n_lines, frames, channels_first=True, want_rows=True)
-        out = ops.vq_gather_st(x_rows, idx, weight, n_lines, frames, channels_first=True)
-        if update:
-            # Every rank enters the exchange, also one whose shard of the batch is empty (it contributes zeros): the
-            # peers are waiting for it inside their exchange kernel.
-            if vq._peer_range is not None:      # [K, D+1] SUM over ranks, in place in the peer-mapped range
-                if idx.numel() > 0:
-                    sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings, out=vq._peer_range.tensor)
-                else:
-                    sums_counts = vq._peer_range.tensor.zero_()
-                vq._peer_range.all_reduce_sum_()
-            else:
-                if idx.numel() > 0:
-                    sums_counts = ops.vq_ema_accumulate(x_rows, idx, vq.num_embeddings)
-                else:
-                    sums_counts = torch.zeros(vq.num_embeddings * (D + 1), dtype=torch.float32, device=x.device)
-                torch.distributed.all_reduce(sums_counts, group=vq._dp_group)
-            ops.vq_ema_apply(sums_counts, vq.ema_w.data, vq.ema_cluster_size, weight, vq.decay, vq.epsilon, cb)
+        # the peer-memory exchange is graph-replayable (its barrier epochs only grow); a torch.distributed all-reduce
+        # inside a captured graph is not attempted
+        graphable = vq._use_cuda_graph and x.numel() > 0 and (vq._dp_group is None or vq._peer_range is not None or not update)
+        if graphable:
+            out, idx = vq._graphed_forward(x, cb, update, n_lines, frames)
+        else:
+            out, idx = vq._eager_forward(x, cb, update, n_lines, frames)
+        if update and (x.numel() > 0 or vq._dp_group is not None):
             vq._codebook_tag = vq._weight_tag()
         ctx.mark_non_differentiable(idx)
         return out.view(inputs.shape), idx
@@ -139,8 +115,9 @@ class VectorQuantizer(torch.nn.Module):
 
     # -- launch-bound small batches: the forward's ~12 kernel launches as one CUDA-graph replay
     def enable_cuda_graph(self, enabled=True):
-        """Opt-in: VectorQuantizer.forward (single process) replays a CUDA graph of its kernel sequence, captured once
-        per (input shape, training/eval, state addresses), instead of launching ~12 kernels from the host; the input is
+        """Opt-in: VectorQuantizer.forward (single process, or data parallel with the peer-memory exchange) replays a CUDA
+        graph of its kernel sequence, captured once per (input shape, training/eval, state addresses), instead of
+        launching ~12 kernels from the host; the input is
         copied into a static buffer and the outputs are copied out of static buffers, so the usual tensor semantics
         hold (nothing returned aliases the graph's buffers).  Worth it when the step is host-bound (8192 frames:
         ~100 us of launches become ~25 us)."""
@@ -149,24 +126,50 @@ class VectorQuantizer(torch.nn.Module):
             self._graphs = {}
         return self
 
+    def _eager_forward(self, x, cb, update, n_lines, frames):
+        """assign -> quantize -> (training, decay > 0) EMA update on contiguous fp32 x [n_lines, D, frames...]."""
+        weight = self.embedding.weight.data
+        if self._dp_group is None:
+            # single process: one call of the C ABI for assign -> quantize -> EMA update
+            return ops.vq_forward(x, cb, weight, self.ema_w.data if update else None,
+                                  self.ema_cluster_size if update else None, self.decay, self.epsilon, update and x.numel() > 0,
+                                  n_lines, frames, channels_first=True)
+        # data parallel: the EMA sums|counts are exchanged between accumulate and apply
+        idx, _, x_rows = ops.vq_assign(x, cb, n_lines, frames, channels_first=True, want_rows=True)
+        out = ops.vq_gather_st(x_rows, idx, weight, n_lines, frames, channels_first=True)
+        if update:
+            # Every rank enters the exchange, also one whose shard of the batch is empty (it contributes zeros): the
+            # peers are waiting for it inside their exchange kernel.
+            if self._peer_range is not None:      # [K, D+1] SUM over ranks, in place in the peer-mapped range
+                if idx.numel() > 0:
+                    sums_counts = ops.vq_ema_accumulate(x_rows, idx, self.num_embeddings, out=self._peer_range.tensor)
+                else:
+                    sums_counts = self._peer_range.tensor.zero_()
+                self._peer_range.all_reduce_sum_()
+            else:
+                if idx.numel() > 0:
+                    sums_counts = ops.vq_ema_accumulate(x_rows, idx, self.num_embeddings)
+                else:
+                    sums_counts = torch.zeros(self.num_embeddings * (self.embeddings_dim + 1), dtype=torch.float32, device=x.device)
+                torch.distributed.all_reduce(sums_counts, group=self._dp_group)
+            ops.vq_ema_apply(sums_counts, self.ema_w.data, self.ema_cluster_size, weight, self.decay, self.epsilon, cb)
+        return out, idx
+
     def _graphed_forward(self, x, cb, update, n_lines, frames):
         weight = self.embedding.weight.data
         key = (tuple(x.shape), bool(update), weight.data_ptr(), cb.blob.data_ptr(),
-               self.ema_w.data_ptr() if update else 0, self.ema_cluster_size.data_ptr() if update else 0, x.device)
+               self.ema_w.data_ptr() if update else 0, self.ema_cluster_size.data_ptr() if update else 0, x.device,
+               self._dp_group is not None)
         g = self._graphs.get(key)
         if g is None:
-            N = n_lines * frames
-            g = {"x": torch.empty_like(x), "out": torch.empty_like(x),
-                 "idx": torch.empty(N, dtype=torch.int64, device=x.device),
-                 "ws": ops.vq_forward_workspace(N, self.num_embeddings, self.embeddings_dim, update, x.device)}
+            g = {"x": torch.empty_like(x)}
             graph = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream(device=x.device)
             side.wait_stream(torch.cuda.current_stream(x.device))
-            # capture records the launches without executing them: the EMA state is not touched here
+            # capture records the launches without executing them: the EMA state is not touched here; everything the
+            # forward allocates while being captured lives in the graph's private pool and is reused by every replay
             with torch.cuda.graph(graph, stream=side):
-                ops.vq_forward(g["x"], cb, weight, self.ema_w.data if update else None,
-                               self.ema_cluster_size if update else None, self.decay, self.epsilon, update, n_lines, frames,
-                               channels_first=True, out=g["out"], idx=g["idx"], ws=g["ws"])
+                g["out"], g["idx"] = self._eager_forward(g["x"], cb, update, n_lines, frames)
             torch.cuda.current_stream(x.device).wait_stream(side)
             g["graph"] = graph
             if len(self._graphs) >= 8:        # shapes come and go (ragged last batch): keep the cache small

@@ -874,13 +874,18 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
     //   d_W, d_b given  -> dlogits P / P^T of label columns [v_begin, v_end) into the workspace, rows [v_begin, v_end)
     //                      of d_W and d_b; then, if d_h is given too (requires the full range), d_h
     //   d_W == d_b == NULL, d_h given -> d_h from the P that earlier calls left in the SAME workspace for ALL columns
-    const bool dh_only = (!d_W && !d_b && d_h);
-    if ((!lse && h) || (!dh_only && (!d_W || !d_b))) return PERO_ERR_NULL;      // h == NULL: the log-sum-exp comes from the forward's partials
+    //   d_W given, d_b == d_h == NULL -> only dlogits + d_W of the range (the exchange of d_W starts the moment its GEMM
+    //                      is done); d_W == NULL, d_b and d_h given (full range) -> d_h AND d_b from the P in the workspace:
+    //                      the column sums run beside the d_h GEMM and are exchanged later, as a small message of their own
+    const bool dh_only = (!d_W && d_h);               // second phase: no dlogits, no d_W
+    const bool dw_only = (d_W && !d_b && !d_h);
+    const bool late_db = (dh_only && d_b);
+    if ((!lse && h) || (!dh_only && !d_W) || (!dh_only && !dw_only && !d_b)) return PERO_ERR_NULL;      // h == NULL: the log-sum-exp comes from the forward's partials
     if (Dh % 4 != 0) return PERO_ERR_BAD_SHAPE;
     if (v_begin < 0 || v_end > V || v_begin >= v_end || (v_begin % 256) != 0 || (v_end != V && (v_end % 256) != 0))
         return PERO_ERR_BAD_SHAPE;
     const bool full_range = (v_begin == 0 && v_end == V);
-    if (d_h && !dh_only && !full_range) return PERO_ERR_UNSUPPORTED;
+    if (d_h && !full_range && (!dh_only || late_db)) return PERO_ERR_UNSUPPORTED;
     const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
     const HeadLayout hl = head_layout(V, Dh);
     char* ws = static_cast<char*>(workspace);
@@ -898,6 +903,7 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
     // two tiles, and the store of one overlaps the loads of the next.
     const int pdl_on = PERO_KNOB("PERO_CE_PDL", 1);                  // dev build, 0: the gradient GEMMs run one after the other
     const bool side_by_side = pdl_on && store_pairs && !dh_only && d_h != nullptr && full_range;
+    const bool db_beside_dh = late_db && pdl_on && store_pairs;      // second phase: column sums beside the d_h GEMM
     const int half_workers = device_sm_count() / 4;
     if (!dh_only) {
         if (h && v_begin == 0) {
@@ -960,7 +966,7 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
         // d_b: partial column sums of P now, unless the side-by-side schedule below runs them beside the GEMMs; the
         // final sums on their own when this call stops after d_W | d_b (they are exchanged next), otherwise by the
         // leading blocks of the scatter launch
-        if (!side_by_side) {
+        if (!side_by_side && !dw_only) {
             // beside the d_W GEMM (released by it at once, waits for it before exiting) when PDL is on
             const int vlen8 = (int)(vp_range / 8);      // P's padding columns are zeros
             cudaLaunchConfig_t cfg = {};
@@ -973,7 +979,7 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
                                                vlen8, (int)l.Vp, dbpart, pdl_on ? 1 : 0, (uint4*)nullptr, 0ll);
             if (e != cudaSuccess) return (int)e;
         }
-        if (!d_h)
+        if (!d_h && !dw_only)
             ce_db_reduce_kernel<<<(unsigned)((vlen + 31) / 32), 256, 0, st>>>(dbpart, db_nparts, (int)l.Vp, (int)v_begin,
                                                                               (int)v_end, d_b);
     }
@@ -994,7 +1000,7 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
         StoreEpi::Params sh;
         sh.out = planes; sh.ld = Dh; sh.split_stride = (long long)M * Dh; sh.rows = (int)M; sh.cols = (int)Dh;
         const int dh_workers = side_by_side ? half_workers : 0;
-        const int dh_pdl = side_by_side ? 3 : 0;
+        const int dh_pdl = side_by_side ? 3 : (db_beside_dh ? 1 : 0);
         if (dh_tma)
             rc = launch_gemm_tn<2, 0, StoreTmaEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.KS, 0, 1,
                                                       dh_workers, sht, st, nullptr, kSmemBudgetShared, (int)V, dh_pdl);
@@ -1005,7 +1011,11 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
             rc = launch_gemm_tn<1, 0, StoreEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.KS, 0, 1, 0,
                                                    sh, st, nullptr, kSmemBudgetShared, (int)V);
         if (rc) return rc;
-        if (side_by_side) {
+        if (late_db && !db_beside_dh) {        // no programmatic launches: plain column sums behind the GEMM
+            ce_db_partial_kernel<<<(unsigned)db_nparts, 256, 0, st>>>((const __nv_bfloat16*)P, (int)M, (int)l.Pp, 0, (int)(l.Vp / 8),
+                                                                     (int)l.Vp, dbpart, 0, (uint4*)nullptr, 0ll);
+        }
+        if (side_by_side || db_beside_dh) {
             // third member of the side-by-side group: released by the d_h GEMM as soon as that one has started
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)db_nparts); cfg.blockDim = dim3(256); cfg.stream = st;
@@ -1025,7 +1035,7 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
         const long long total = (scatter_masked_only ? M : N) * (Dh / 4);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        const int db_blocks = dh_only ? 0 : (int)((V + 31) / 32);
+        const int db_blocks = (dh_only && !late_db) ? 0 : (int)((V + 31) / 32);
         blocks += db_blocks;
         const int ks_eff = dh_planes;
         // (a plain launch on purpose: released programmatically, the ~800 CTAs of this grid park on every SM until

@@ -322,23 +322,33 @@ def masked_ce_eval(h, rows, labels, head, ks=(1, 3, 10), want_rank=False):
 
 
 def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False,
-                  want_dw=True, flat_out=None, ws_from_fwd=False, v_range=None, labels_packed=False):
+                  want_dw=True, flat_out=None, ws_from_fwd=False, v_range=None, labels_packed=False, want_db=None,
+                  dw_out=None, db_out=None):
     """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32[, flat buffer holding d_W|d_b]).
     ws_from_fwd: `ws` is the workspace masked_ce_fwd returned for the same (h, rows, labels) and has not been
     touched since: the gathered operands in it are reused instead of gathering again, and the log-sum-exp is rebuilt
     from the forward's partials (`lse` may be None).
     v_range=(v0, v1): only label columns [v0, v1) (multiples of 256 or V): rows v0:v1 of d_W / d_b; needs
-    want_dh=False, and a final call with want_dw=False for d_h once every range is done."""
+    want_dh=False, and a final call with want_dw=False for d_h once every range is done.
+    Phases for a data-parallel caller (pero_masked_ce_bwd_range): want_dw only (want_db=False, want_dh=False) -> dlogits +
+    d_W, whose exchange can start the moment the GEMM is done; then want_dw=False, want_db=True, want_dh=True -> d_h and
+    d_b from the dlogits left in `ws`.  dw_out / db_out: separate destinations (e.g. two peer-exchange ranges)."""
     L = _lib.lib()
     h = _check_h(h)
     N, Dh = h.shape
     M = rows.numel()
+    if want_db is None:
+        want_db = want_dw
     d_h = torch.empty_like(h) if want_dh else None
     # d_W and d_b share one flat buffer so that data-parallel ranks all-reduce them in a single call
     flat = d_W = d_b = None
-    if want_dw:       # want_dw=False: second phase, d_h only, from the dlogits a previous call left in `ws`
+    if dw_out is not None or db_out is not None:
+        d_W = dw_out if want_dw else None
+        d_b = db_out if want_db else None
+    elif want_dw or want_db:       # neither: second phase, d_h only, from the dlogits a previous call left in `ws`
         flat = flat_out if flat_out is not None else torch.empty(head.V * Dh + head.V, dtype=torch.float32, device=h.device)
-        d_W, d_b = flat[:head.V * Dh].view(head.V, Dh), flat[head.V * Dh:]
+        d_W = flat[:head.V * Dh].view(head.V, Dh) if want_dw else None
+        d_b = flat[head.V * Dh:] if want_db else None
     wsb = L.pero_masked_ce_workspace_bytes(N, M, head.V, Dh)
     if ws_from_fwd and (ws is None or ws.numel() < wsb):
         raise ValueError("ws_from_fwd needs the forward call's workspace")

@@ -142,11 +142,12 @@ def check_dp_quantizer(dev, rank, world):
     w0 = torch.randn(K, D, generator=g)
     steps = [w0[torch.randint(0, K, (nl * T,), generator=g)].view(nl, T, D).permute(0, 2, 1).reshape(nl, D, 1, T)
              + 0.3 * torch.randn(nl, D, 1, T, generator=g) for _ in range(3)]
-    for peer in (True, False):
+    for peer, graphed in ((True, False), (True, True), (False, False)):
         vq = VectorQuantizer(K, D, 0.25, 0.99).to(dev).train()
         with torch.no_grad():
             vq.embedding.weight.copy_(w0); vq.ema_w.copy_(w0); vq.ema_cluster_size.fill_(1.0)
         vq.enable_data_parallel(peer=peer)
+        vq.enable_cuda_graph(graphed)          # the exchange kernel replays inside the captured forward
         ref = dict(weight=w0.clone(), ema_w=w0.clone(), cs=torch.ones(K))
         lo, hi = rank * nl // world, (rank + 1) * nl // world
         for x in steps:
@@ -163,7 +164,7 @@ def check_dp_quantizer(dev, rank, world):
                 assert torch.allclose(vq.ema_cluster_size.cpu(), ref["cs"], rtol=1e-5, atol=1e-6)
         copies = gather_bytes(vq.embedding.weight.detach())
         assert all(torch.equal(copies[0], c) for c in copies[1:]), "replicated codebooks diverged"
-        log(f"data-parallel VectorQuantizer OK (peer={peer})")
+        log(f"data-parallel VectorQuantizer OK (peer={peer}, cuda graph={graphed})")
 
 
 def check_dp_head(dev, rank, world):
