@@ -181,15 +181,15 @@ __device__ __forceinline__ int masked_row_of(const int* __restrict__ inv, const 
 template <bool kRank>
 struct LseEpiT {
     static constexpr bool kColVec = true;
-    static constexpr int kScratchPerWarp = 0;
+    static constexpr int kScratchPerWarp = 192;     // 8 warps x 192 B = 128 rows x (max, sum, count): half 1 -> half 0 hand-over
     struct Params {
         const float* colvec;  // bias [Vt], -inf beyond V
         const int* rows;      // [M] frame of every masked row
         const long long* labels;   // [N] label of every frame
-        float* pm; float* ps; // [2 * S, Mpad] partial max / sum(exp(z - max))
+        float* pm; float* ps; // [S, Mpad] partial max / sum(exp(z - max)) of every worker's column range
         float* zlab;          // [Mpad] logit at the label
         const float* zl_in;   // kRank: [Mpad] label logit computed ahead of the sweep
-        int* pcnt;            // kRank: [2 * S, Mpad] partial counts of logits above zl_in
+        int* pcnt;            // kRank: [S, Mpad] partial counts of logits above zl_in
         int M, Mpad, S, V, packed;
     };
     struct State { float m, s, zl, zin; int label, cnt; bool has; };
@@ -248,13 +248,30 @@ struct LseEpiT {
             }
         });
     }
+    // The two column halves of a tile belong to two threads of the CTA that own the same row: half 1 hands its partial
+    // (max, sum[, count]) to half 0 through shared memory, half 0 combines (half 0 first: a fixed order) and writes ONE
+    // slot per worker, which halves what the readers of the partials have to fetch.
     static __device__ __forceinline__ void end_rb(State& st, const Params& ep, const TileCtx& cx) {
-        const int slot = (cx.worker % ep.S) * 2 + cx.half;
-        ep.pm[(size_t)slot * ep.Mpad + cx.row] = st.m;
-        ep.ps[(size_t)slot * ep.Mpad + cx.row] = st.s;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        float* xch = reinterpret_cast<float*>(cx.scratch - warp * kScratchPerWarp);          // [128][3]
+        const int r = (warp & 3) * 32 + lane;                                                // row inside the CTA's 128
+        const int slot = cx.worker % ep.S;
         if (st.has) ep.zlab[cx.row] = st.zl;
-        else if (st.label == -2 && slot == 0) ep.zlab[cx.row] = CUDART_NAN_F;      // label outside [0, V)
-        if constexpr (kRank) ep.pcnt[(size_t)slot * ep.Mpad + cx.row] = st.cnt;
+        else if (st.label == -2 && slot == 0 && cx.half == 0) ep.zlab[cx.row] = CUDART_NAN_F;      // label outside [0, V)
+        if (cx.half == 1) {
+            xch[3 * r + 0] = st.m; xch[3 * r + 1] = st.s; xch[3 * r + 2] = __int_as_float(st.cnt);
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (cx.half == 0) {
+            const float m1 = xch[3 * r + 0], s1 = xch[3 * r + 1];
+            const float mn = fmaxf(st.m, m1);
+            float sum = 0.f;
+            if (mn > -CUDART_INF_F) sum = st.s * ex2_fast((st.m - mn) * kLog2e) + s1 * ex2_fast((m1 - mn) * kLog2e);
+            ep.pm[(size_t)slot * ep.Mpad + cx.row] = mn;
+            ep.ps[(size_t)slot * ep.Mpad + cx.row] = sum;
+            if constexpr (kRank) ep.pcnt[(size_t)slot * ep.Mpad + cx.row] = st.cnt + __float_as_int(xch[3 * r + 2]);
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");                                         // the hand-over area is free again
     }
 };
 using LseEpi = LseEpiT<false>;
@@ -288,32 +305,45 @@ struct DlogitsEpi {
     static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
         const bool ok = cx.row < ep.M;
         st.label = masked_label(ep.labels, ep.rows, cx.row, ep.M, ep.V, ep.packed);
-        if (ok && ep.pm) {
-            // The forward's per-slot partials (max, sum) of this row are combined here, in slot order and with the same
-            // arithmetic for every worker that owns the row, instead of waiting for ce_finalize_kernel: 16 loads in
-            // flight per batch, and the whole rebuild hides behind the first accumulator tile of the row block.
-            float mx = -CUDART_INF_F;
-            for (int s0 = 0; s0 < ep.slots; s0 += 16) {
-                float v[16];
+        if (ep.pm) {
+            // The forward's per-worker partials (max, sum) of this row are combined here, in slot order and with the same
+            // arithmetic for every CTA that owns the row, instead of waiting for ce_finalize_kernel.  Only the half-0
+            // thread of a row does it (all loads of a batch of 16 slots in flight at once) and hands the result to its
+            // half-1 twin through shared memory; the rebuild hides behind the first accumulator tile of the row block.
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            float* xch = reinterpret_cast<float*>(cx.scratch - warp * kScratchPerWarp);      // warp 0's staging tile: free here
+            const int r = (warp & 3) * 32 + lane;
+            if (cx.half == 0) {
+                float l2 = CUDART_INF_F;
+                if (ok) {
+                    float mx = -CUDART_INF_F, sum = 0.f;
+                    for (int s0 = 0; s0 < ep.slots; s0 += 16) {
+                        float pmv[16], psv[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = (s0 + j < ep.slots) ? __ldg(ep.pm + (size_t)(s0 + j) * ep.Mpad + cx.row) : -CUDART_INF_F;
+                        for (int j = 0; j < 16; ++j) {
+                            const bool in = s0 + j < ep.slots;
+                            pmv[j] = in ? __ldg(ep.pm + (size_t)(s0 + j) * ep.Mpad + cx.row) : -CUDART_INF_F;
+                            psv[j] = in ? __ldg(ep.ps + (size_t)(s0 + j) * ep.Mpad + cx.row) : 0.f;
+                        }
+                        float bm = mx;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j]);
-            }
-            float sum = 0.f;
-            const float mx2 = mx * kLog2e;
-            for (int s0 = 0; s0 < ep.slots; s0 += 16) {
-                float pmv[16], psv[16];
+                        for (int j = 0; j < 16; ++j) bm = fmaxf(bm, pmv[j]);
+                        if (bm > -CUDART_INF_F) {
+                            const float bm2 = bm * kLog2e;
+                            sum *= ex2_fast(fmaf(mx, kLog2e, -bm2));                            // 2^-inf = 0 on the first batch
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const bool in = s0 + j < ep.slots;
-                    pmv[j] = in ? __ldg(ep.pm + (size_t)(s0 + j) * ep.Mpad + cx.row) : -CUDART_INF_F;
-                    psv[j] = in ? __ldg(ep.ps + (size_t)(s0 + j) * ep.Mpad + cx.row) : 0.f;
+                            for (int j = 0; j < 16; ++j) sum = fmaf(psv[j], ex2_fast(fmaf(pmv[j], kLog2e, -bm2)), sum);
+                            mx = bm;
+                        }
+                    }
+                    l2 = fmaf(mx, kLog2e, log2f(sum));
                 }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) sum = fmaf(psv[j], ex2_fast(fmaf(pmv[j], kLog2e, -mx2)), sum);      // 2^-inf = 0 on empty slots
+                xch[r] = l2;
+                st.lse2 = l2;
             }
-            st.lse2 = mx2 + log2f(sum);
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (cx.half == 1) st.lse2 = xch[r];
+            asm volatile("bar.sync 3, 256;" ::: "memory");        // before the staging tile is used for stores again
         } else {
             st.lse2 = ok ? __ldg(ep.lse + cx.row) * kLog2e : CUDART_INF_F;
         }
@@ -792,7 +822,7 @@ int pero_masked_ce_fwd(const void* h, int flags, int64_t N, int64_t Dh, const in
     // lse / rowloss / loss_sum from the partials.  A backward GEMM launched right behind on the same workspace rebuilds
     // the log-sum-exp from the partials itself and never reads this kernel's output.
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
-    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
+    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, (int)l.S, lse,
                                                               rowloss, reinterpret_cast<unsigned int*>(ws + l.ticket_off),
                                                               loss_sum);
     return (int)cudaGetLastError();
@@ -808,7 +838,7 @@ int pero_masked_ce_loss(int64_t N, int64_t Dh, int64_t M, int64_t V, float* loss
     char* ws = static_cast<char*>(workspace);
     ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(
         reinterpret_cast<const float*>(ws + l.pm_off), reinterpret_cast<const float*>(ws + l.ps_off),
-        reinterpret_cast<const float*>(ws + l.zlab_off), (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
+        reinterpret_cast<const float*>(ws + l.zlab_off), (int)M, (int)l.Mpad, (int)l.S, lse,
         reinterpret_cast<float*>(ws + l.rowloss_off), reinterpret_cast<unsigned int*>(ws + l.ticket_off), loss_sum);
     return (int)cudaGetLastError();
 }
@@ -852,10 +882,10 @@ int pero_masked_ce_eval(const void* h, int flags, int64_t N, int64_t Dh, const i
                                      kSmemBudgetShared, /*pdl=*/0);
     if (rc) return rc;
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
-    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, 2 * (int)l.S, lse,
+    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, stream>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, (int)l.S, lse,
                                                                   rowloss, reinterpret_cast<unsigned int*>(ws + l.ticket_off),
                                                                   loss_sum);
-    ce_rank_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(ep.pcnt, (int)M, (int)l.Mpad, 2 * (int)l.S, ks, rank,
+    ce_rank_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(ep.pcnt, (int)M, (int)l.Mpad, (int)l.S, ks, rank,
                                                                          reinterpret_cast<unsigned long long*>(errors));
     return (int)cudaGetLastError();
 }
@@ -926,7 +956,7 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
             ep.lse = lse; ep.grad_scale = grad_scale; ep.inv_count = inv_count;
             ep.pm = from_partials ? reinterpret_cast<const float*>(ws + l.pm_off) : nullptr;
             ep.ps = from_partials ? reinterpret_cast<const float*>(ws + l.ps_off) : nullptr;
-            ep.slots = 2 * (int)l.S; ep.Mpad = (int)l.Mpad;
+            ep.slots = (int)l.S; ep.Mpad = (int)l.Mpad;
             ep.p = P + v_begin; ep.M = (int)M;
             ep.Vp = (int)vp_range;
             ep.p_pitch = (int)l.Pp; ep.col_base = (int)v_begin;
