@@ -58,6 +58,9 @@ struct GemmShape {
     int split_mode;    // 0: balanced contiguous unit ranges; 1: worker = rb * fixed_s + s
     int fixed_s;
     int num_stages;    // ring depth chosen by the host from the shared-memory budget
+#ifdef PERO_DEV_BUILD
+    int fake_b;        // timing study: B is loaded only during the first pass over the ring
+#endif
     int pdl;           // programmatic dependent launch: bit 0 = release the next kernel of the stream at once (it does
                        // not read this kernel's output), bit 1 = before exiting, wait for the previous kernel (this
                        // kernel was released early by it, does not read its output, and must not be seen to finish
@@ -220,6 +223,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // k-blocks is requested at once; the A loads (and everything else) follow the wait.
             int pre_issued = 0;
             bool waited = !late_wait;
+#ifdef PERO_DEV_BUILD
+            bool fake_started = false;
+#endif
             if constexpr (kAResident) {
                 if (late_wait) {
                     for (UnitIter ui(sh, u0, u1); ui.valid() && pre_issued < stages; ui.next()) {
@@ -270,6 +276,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sbase = ring + stage * kStageBytes;
+#ifdef PERO_DEV_BUILD
+                    if (sh.fake_b && (phase || fake_started)) {          // timing study only: stage contents are stale
+                        fake_started = true;
+                        if constexpr (kCtaGroup == 1) mbar_arrive(full_bar(stage));
+                        else { if (leader) mbar_arrive(full_bar(stage)); else mbar_arrive_remote(full_bar(stage), 0); }
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+#endif
                     {
                         // K-major operand: one box {64 k-elements, rows}.  MN-major operand: boxes of {64 MN-elements,
                         // 64 k-rows} = 8 KiB each (2 for A, kBRows / 64 for B), the contraction index running over rows.

@@ -177,6 +177,9 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     sh.split_mode = split_mode; sh.fixed_s = fixed_s < 1 ? 1 : fixed_s;
     if (PERO_KNOB("PERO_PDL", 1) == 0) pdl = 0;       // dev build: no programmatic dependent launches at all
     sh.pdl = pdl;
+#ifdef PERO_DEV_BUILD
+    sh.fake_b = PERO_KNOB("PERO_GEMM_FAKE_B", 0);
+#endif
     constexpr int kASets = kARes == 2 ? 2 : (kARes ? 1 : 0);
     if (kARes && (sh.num_ks != 1 || sh.num_kb * kASets > kMaxAKb)) return PERO_ERR_BAD_SHAPE;
     sh.num_stages = pick_stages(kCtaGroup, kASets, sh.num_kb, Epi::kScratchPerWarp, smem_budget);
