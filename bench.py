@@ -326,9 +326,12 @@ class DeviceStep:
         with torch.cuda.stream(s_ce):
             _, _, ws = ops.masked_ce_fwd(self.h, self.rows, packed, self.head, ws=ce_ws, finalize=False, labels_packed=True)
             if not self.dp:
+                # the loss is read out of the log-sum-exp partials beside the backward GEMMs, not behind them
+                self.s_comm.wait_stream(s_ce)
+                with torch.cuda.stream(self.s_comm):
+                    loss_sum, lse = ops.masked_ce_loss(ws, N, Dh, self.M, c["V"])
                 d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global, ws=ws,
                                                         return_flat=True, ws_from_fwd=True, labels_packed=True)
-                loss_sum, lse = ops.masked_ce_loss(ws, N, Dh, self.M, c["V"])
             else:
                 # loss_sum rides in the same exchange range as d_W | d_b.  The backward walks the label axis range by
                 # range: each range's rows of d_W are reduced over the ranks on the communication stream while the
@@ -358,8 +361,8 @@ class DeviceStep:
                 flat = g
         main.wait_stream(s_ema)
         main.wait_stream(s_ce)
+        main.wait_stream(self.s_comm)
         if self.dp:
-            main.wait_stream(self.s_comm)
             main.wait_stream(self.s_comm_ema)
             main.wait_stream(self.s_comm_db)
         self.out = dict(idx=idx, x_rows=x_rows, q=q, loss_c=loss_c, g_x=g_x, sums=sums, loss_sum=loss_sum, lse=lse, ws=ws,

@@ -3,14 +3,11 @@
 //      16384 codewords: a stable multi-CTA counting sort in three short launches (per-CTA stable ranks +
 //      histograms, one-CTA scan, placement); otherwise a one-CTA block radix sort (<= 8192 frames) or CUB's
 //      device radix sort (stable as well).
-//   2. segmented sum of the fp32 frame rows in sorted order.  Codewords that own up to kLongSeg frames (all of
-//      them once the codebook is warm) are summed by ONE warp each, which also writes the zero rows of unused
-//      codewords and the counts.  Longer segments (a collapsed codebook: one codeword owning every frame, as in
-//      the reference's cold start) go through the chunked path: every 16 sorted positions form one chunk; runs
-//      that lie inside a chunk are summed and stored directly, runs that cross chunk borders leave a head/tail
-//      partial that a second kernel adds up in chunk order, so that such a segment still spreads over all SMs.
-//      Both launches return at once when no long segment exists.  No float atomics anywhere: the sums are
-//      bit-identical run to run.
+//   2. segmented sum of the fp32 frame rows in sorted order, ONE launch: codewords that own up to kLongSeg frames (all
+//      of them once the codebook is warm) are summed by one warp each, which also writes the zero rows of unused
+//      codewords and the counts; a longer segment (a popular codeword, or the collapsed codebook of the reference's
+//      cold start, where one codeword owns every frame) is summed by the 8 warps of its CTA, an eighth each, and the 8
+//      partial rows are added in warp order.  No float atomics anywhere: the sums are bit-identical run to run.
 //   3. apply: cluster-size EMA + Laplace smoothing, ema_w EMA, weight = ema_w / size, and refresh of the
 //      bf16 operand + |c|^2 used by the next assign.
 // Row reads/writes are 16-byte vectors, coalesced along D.
@@ -26,15 +23,14 @@
 
 namespace pero {
 
-constexpr int kChunk = 16;            // sorted positions per chunk
 constexpr int kSmallSortMax = 8192;   // frames handled by the single-CTA sort (8 per thread x 1024 threads)
 constexpr int kClusterBlocks = 64;    // partial sums of the cluster-size reduction
-constexpr int kLongSeg = 64;          // segments longer than this take the chunked path
+constexpr int kLongSeg = 64;          // segments longer than this are summed by the whole CTA
 constexpr int kRankThreads = 1024;    // frames per CTA of the counting sort
 constexpr int kRankMaxBlocks = kSmallSortMax / kRankThreads;
 
 struct EmaWsLayout {
-    size_t keys_in, keys_out, vals_in, vals_out, seg, partial, cluster_partial, hist, excl, btot, flags, cub, total;
+    size_t keys_in, keys_out, vals_in, vals_out, seg, cluster_partial, hist, excl, btot, cub, total;
     size_t cub_bytes;
 };
 
@@ -53,13 +49,10 @@ inline EmaWsLayout ema_ws_layout(int64_t N, int64_t K, int64_t D) {
     l.vals_in = take((size_t)N * 4);
     l.vals_out = take((size_t)N * 4);
     l.seg = take((size_t)(K + 1) * 4);
-    const int64_t chunks = (N + kChunk - 1) / kChunk;
-    l.partial = take((size_t)chunks * 2 * D * 4);
     l.cluster_partial = take(kClusterBlocks * 4);
     l.hist = take(N <= kSmallSortMax ? (size_t)kRankMaxBlocks * K * 4 : 0);    // counting sort: per-CTA histograms / bases
     l.excl = take(N <= kSmallSortMax ? (size_t)K * 4 : 0);                      // counting sort: scan inside 256-codeword blocks
     l.btot = take(N <= kSmallSortMax ? (size_t)((K + 255) / 256) * 4 : 0);      // ... and the block sums
-    l.flags = take(256);                                                        // [0] = "a long segment exists"
     size_t cub_bytes = 0;
     if (N > kSmallSortMax) {
         cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
@@ -82,9 +75,8 @@ inline EmaWsLayout ema_ws_layout(int64_t N, int64_t K, int64_t D) {
 template <int ITEMS>
 __global__ void __launch_bounds__(1024)
 ema_sort_small_kernel(const long long* __restrict__ idx, int N, int K, int end_bit, uint32_t* __restrict__ keys_out,
-                      uint32_t* __restrict__ vals_out, int* __restrict__ seg, int* __restrict__ flags) {
+                      uint32_t* __restrict__ vals_out, int* __restrict__ seg) {
     using Sort = cub::BlockRadixSort<uint32_t, 1024, ITEMS, uint32_t>;
-    if (threadIdx.x == 0) flags[0] = 0;
     __shared__ typename Sort::TempStorage temp;
     uint32_t keys[ITEMS], vals[ITEMS];
     const uint32_t sentinel = 1u << (end_bit - 1);          // above every codeword: padding sorts last
@@ -148,12 +140,10 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& 
 constexpr int kRankCtaThreads = 256;
 constexpr int kRankRounds = kRankThreads / kRankCtaThreads;
 __global__ void __launch_bounds__(kRankCtaThreads)
-ema_rank_kernel(const long long* __restrict__ idx, int N, int K, uint32_t* __restrict__ lrank, uint32_t* __restrict__ hist,
-                int* __restrict__ flags) {
+ema_rank_kernel(const long long* __restrict__ idx, int N, int K, uint32_t* __restrict__ lrank, uint32_t* __restrict__ hist) {
     extern __shared__ unsigned short cnt[];           // [K], at most 1024 per codeword
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int k = t; k < K; k += kRankCtaThreads) cnt[k] = 0;
-    if (blockIdx.x == 0 && t == 0) flags[0] = 0;      // cleared for ema_rowsum_kernel, two launches later
     int key[kRankRounds], leader[kRankRounds], rank_in_warp[kRankRounds], gsize[kRankRounds];
     uint32_t base[kRankRounds];
 #pragma unroll
@@ -248,10 +238,8 @@ __global__ void ema_keys_kernel(const long long* __restrict__ idx, long long N, 
 
 // seg[k] = first sorted position whose key >= k; seg[K] = N.  One thread per sorted position writes the
 // (usually zero or one) boundaries that fall between its predecessor's key and its own.
-__global__ void ema_boundaries_kernel(const uint32_t* __restrict__ keys, int N, int K, int* __restrict__ seg,
-                                      int* __restrict__ flags) {
+__global__ void ema_boundaries_kernel(const uint32_t* __restrict__ keys, int N, int K, int* __restrict__ seg) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) flags[0] = 0;
     if (p > N) return;
     const int k = p < N ? (int)keys[p] : K;
     const int kprev = p == 0 ? -1 : (int)keys[p - 1];
@@ -259,172 +247,107 @@ __global__ void ema_boundaries_kernel(const uint32_t* __restrict__ keys, int N, 
 }
 
 // ------------------------------------------------------------------------------------------------ segmented sum
-// One warp per codeword: counts, the zero row of an unused codeword, and -- for segments of up to kLongSeg frames --
-// the sum of the segment's frame rows in ascending frame order (lane <-> 16-byte column groups, 4 row loads in flight).
-// A longer segment is left to the chunked kernels below and raises flags[0].
+// One CTA per 8 codewords.  Pass 1, one warp per codeword: counts, the zero row of an unused codeword, and -- for
+// segments of up to kLongSeg frames, i.e. all of them once the codebook is warm -- the sum of the segment's frame rows in
+// ascending frame order (lane <-> 16-byte column groups, 4 row loads in flight).  Pass 2, rare: a longer segment (a
+// popular codeword; or the collapsed codebook of the reference's cold start, where one codeword owns every frame) is
+// summed by all 8 warps of the CTA, warp w taking the w-th eighth of the segment in ascending order, and the 8
+// partial rows are added in warp order: a fixed order again, so the sums stay bit-identical run to run.  No float
+// atomics, no second launch.
+template <int VEC>
+__device__ __forceinline__ void ema_accumulate_rows(const float* __restrict__ xr, const uint32_t* __restrict__ rows, int p0, int p1,
+                                                    int D, int ga, int gb, int groups, float (&a)[VEC], float (&b)[VEC]) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { a[e] = 0.f; b[e] = 0.f; }
+    int p = p0;
+    for (; p + 2 <= p1; p += 2) {                      // two frames per iteration: four independent loads
+        const float* r0 = xr + (size_t)__ldg(rows + p) * D;
+        const float* r1 = xr + (size_t)__ldg(rows + p + 1) * D;
+        if constexpr (VEC == 4) {
+            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, y0 = x0, y1 = x0;
+            if (ga < groups) { x0 = __ldg(reinterpret_cast<const float4*>(r0) + ga); x1 = __ldg(reinterpret_cast<const float4*>(r1) + ga); }
+            if (gb < groups) { y0 = __ldg(reinterpret_cast<const float4*>(r0) + gb); y1 = __ldg(reinterpret_cast<const float4*>(r1) + gb); }
+            a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w;
+            a[0] += x1.x; a[1] += x1.y; a[2] += x1.z; a[3] += x1.w;
+            b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w;
+            b[0] += y1.x; b[1] += y1.y; b[2] += y1.z; b[3] += y1.w;
+        } else {
+            const float x0 = ga < groups ? __ldg(r0 + ga) : 0.f, x1 = ga < groups ? __ldg(r1 + ga) : 0.f;
+            const float y0 = gb < groups ? __ldg(r0 + gb) : 0.f, y1 = gb < groups ? __ldg(r1 + gb) : 0.f;
+            a[0] += x0; a[0] += x1; b[0] += y0; b[0] += y1;
+        }
+    }
+    if (p < p1) {
+        const float* r0 = xr + (size_t)__ldg(rows + p) * D;
+        if constexpr (VEC == 4) {
+            if (ga < groups) { const float4 x0 = __ldg(reinterpret_cast<const float4*>(r0) + ga); a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w; }
+            if (gb < groups) { const float4 y0 = __ldg(reinterpret_cast<const float4*>(r0) + gb); b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w; }
+        } else {
+            if (ga < groups) a[0] += __ldg(r0 + ga);
+            if (gb < groups) b[0] += __ldg(r0 + gb);
+        }
+    }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
 ema_rowsum_kernel(const float* __restrict__ xr, const uint32_t* __restrict__ rows, const int* __restrict__ seg, int K, int D,
-                  float* __restrict__ sums, float* __restrict__ counts, int* __restrict__ flags) {
-    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (k >= K) return;
-    const int s0 = __ldg(seg + k), s1 = __ldg(seg + k + 1), c = s1 - s0;
-    if (lane == 0) counts[k] = (float)c;
-    if (c > kLongSeg) { if (lane == 0) flags[0] = 1; return; }
+                  float* __restrict__ sums, float* __restrict__ counts) {
+    __shared__ float part[8][64 * VEC];               // pass 2: one partial row slab (64 column groups) per warp
+    __shared__ int long_k[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 8 + warp;
     const int groups = D / VEC;
-    float* dst = sums + (size_t)k * D;
-    for (int g0 = 0; g0 < groups; g0 += 64) {              // two column groups per lane and pass
-        const int ga = g0 + lane, gb = g0 + 32 + lane;
-        float a[VEC], b[VEC];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) { a[e] = 0.f; b[e] = 0.f; }
-        int p = s0;
-        for (; p + 2 <= s1; p += 2) {                      // two frames per iteration: four independent loads
-            const float* r0 = xr + (size_t)__ldg(rows + p) * D;
-            const float* r1 = xr + (size_t)__ldg(rows + p + 1) * D;
-            if constexpr (VEC == 4) {
-                float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, y0 = x0, y1 = x0;
-                if (ga < groups) { x0 = __ldg(reinterpret_cast<const float4*>(r0) + ga); x1 = __ldg(reinterpret_cast<const float4*>(r1) + ga); }
-                if (gb < groups) { y0 = __ldg(reinterpret_cast<const float4*>(r0) + gb); y1 = __ldg(reinterpret_cast<const float4*>(r1) + gb); }
-                a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w;
-                a[0] += x1.x; a[1] += x1.y; a[2] += x1.z; a[3] += x1.w;
-                b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w;
-                b[0] += y1.x; b[1] += y1.y; b[2] += y1.z; b[3] += y1.w;
-            } else {
-                const float x0 = ga < groups ? __ldg(r0 + ga) : 0.f, x1 = ga < groups ? __ldg(r1 + ga) : 0.f;
-                const float y0 = gb < groups ? __ldg(r0 + gb) : 0.f, y1 = gb < groups ? __ldg(r1 + gb) : 0.f;
-                a[0] += x0; a[0] += x1; b[0] += y0; b[0] += y1;
-            }
-        }
-        if (p < s1) {
-            const float* r0 = xr + (size_t)__ldg(rows + p) * D;
-            if constexpr (VEC == 4) {
-                if (ga < groups) { const float4 x0 = __ldg(reinterpret_cast<const float4*>(r0) + ga); a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w; }
-                if (gb < groups) { const float4 y0 = __ldg(reinterpret_cast<const float4*>(r0) + gb); b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w; }
-            } else {
-                if (ga < groups) a[0] += __ldg(r0 + ga);
-                if (gb < groups) b[0] += __ldg(r0 + gb);
-            }
-        }
-        if constexpr (VEC == 4) {
-            if (ga < groups) reinterpret_cast<float4*>(dst)[ga] = make_float4(a[0], a[1], a[2], a[3]);
-            if (gb < groups) reinterpret_cast<float4*>(dst)[gb] = make_float4(b[0], b[1], b[2], b[3]);
+    if (threadIdx.x < 8) long_k[threadIdx.x] = -1;
+    __syncthreads();
+    if (k < K) {
+        const int s0 = __ldg(seg + k), s1 = __ldg(seg + k + 1), c = s1 - s0;
+        if (lane == 0) counts[k] = (float)c;
+        if (c > kLongSeg) {
+            if (lane == 0) long_k[warp] = k;
         } else {
-            if (ga < groups) dst[ga] = a[0];
-            if (gb < groups) dst[gb] = b[0];
-        }
-    }
-}
-
-// Long segments only (flags[0] != 0, else the launch returns at once).  One CTA per chunk of 16 sorted positions;
-// thread t owns 16-byte column groups t, t + blockDim, ...  All row loads of a column group are issued before the
-// running sums are formed.  Positions that belong to short segments are skipped (ema_rowsum_kernel summed them).
-template <int VEC>
-__global__ void __launch_bounds__(128)
-ema_chunk_sum_kernel(const float* __restrict__ xr, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rows,
-                     const int* __restrict__ seg, int N, int D, float* __restrict__ sums, float* __restrict__ partial,
-                     const int* __restrict__ flags) {
-    if (flags[0] == 0) return;
-    __shared__ uint32_t s_key[kChunk], s_row[kChunk];
-    __shared__ int s_dst[kChunk];      // where the run ending at position p goes: -1 none, 0 sums, 1 head, 2 tail
-    __shared__ int s_use[kChunk];      // position belongs to a long segment
-    __shared__ int s_any;
-    const int nchunks = (N + kChunk - 1) / kChunk;
-  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {          // grid-stride: the launch is small when nothing is long
-    const int pos0 = c * kChunk, pos1 = min(N, pos0 + kChunk), len = pos1 - pos0;
-    __syncthreads();
-    if (threadIdx.x == 0) s_any = 0;
-    __syncthreads();
-    if (threadIdx.x < kChunk) {
-        const int p = threadIdx.x;
-        int dst = -1, use = 0;
-        uint32_t k = 0, r = 0;
-        if (p < len) {
-            k = keys[pos0 + p]; r = rows[pos0 + p];
-            const int s0 = __ldg(seg + k), s1 = __ldg(seg + k + 1);
-            use = (s1 - s0) > kLongSeg;
-            const bool run_end = (p + 1 == len) || (keys[pos0 + p + 1] != k);
-            if (use && run_end) dst = (s0 >= pos0 && s1 <= pos1) ? 0 : (s0 < pos0 ? 1 : 2);
-            if (use) s_any = 1;
-        }
-        s_key[p] = k; s_row[p] = r; s_dst[p] = dst; s_use[p] = use;
-    }
-    __syncthreads();
-    if (!s_any) continue;
-    const int groups = D / VEC;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        float v[kChunk][VEC];
-#pragma unroll
-        for (int p = 0; p < kChunk; ++p) {
-            if (p < len && s_use[p]) {
-                const float* src = xr + (size_t)s_row[p] * D;
+            float* dst = sums + (size_t)k * D;
+            for (int g0 = 0; g0 < groups; g0 += 64) {          // two column groups per lane and pass
+                const int ga = g0 + lane, gb = g0 + 32 + lane;
+                float a[VEC], b[VEC];
+                ema_accumulate_rows<VEC>(xr, rows, s0, s1, D, ga, gb, groups, a, b);
                 if constexpr (VEC == 4) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(src) + g);
-                    v[p][0] = x.x; v[p][1] = x.y; v[p][2] = x.z; v[p][3] = x.w;
+                    if (ga < groups) reinterpret_cast<float4*>(dst)[ga] = make_float4(a[0], a[1], a[2], a[3]);
+                    if (gb < groups) reinterpret_cast<float4*>(dst)[gb] = make_float4(b[0], b[1], b[2], b[3]);
                 } else {
-                    v[p][0] = __ldg(src + g);
-                }
-            }
-        }
-        float acc[VEC];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
-#pragma unroll
-        for (int p = 0; p < kChunk; ++p) {
-            if (p < len && s_use[p]) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[e] += v[p][e];
-                const int dst = s_dst[p];
-                if (dst >= 0) {
-                    float* out = dst == 0 ? sums + (size_t)s_key[p] * D : partial + ((size_t)c * 2 + (dst - 1)) * D;
-                    if constexpr (VEC == 4) reinterpret_cast<float4*>(out)[g] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                    else out[g] = acc[0];
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+                    if (ga < groups) dst[ga] = a[0];
+                    if (gb < groups) dst[gb] = b[0];
                 }
             }
         }
     }
-  }
-}
-
-// Long segments only: one warp per codeword adds, in chunk order, the partials of a segment that crossed chunk borders.
-template <int VEC>
-__global__ void __launch_bounds__(256)
-ema_finalize_kernel(const int* __restrict__ seg, int K, int D, const float* __restrict__ partial,
-                    float* __restrict__ sums, const int* __restrict__ flags) {
-    if (flags[0] == 0) return;
-    const int lane = threadIdx.x & 31;
-  for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < K; k += gridDim.x * (blockDim.x >> 5)) {
-    const int s0 = seg[k], s1 = seg[k + 1];
-    if (s1 - s0 <= kLongSeg) continue;
-    const int groups = D / VEC;
-    float* dst = sums + (size_t)k * D;
-    const int cf = s0 / kChunk, cl = (s1 - 1) / kChunk;
-    if (cf == cl) continue;   // summed and stored by the chunk kernel
-    for (int g = lane; g < groups; g += 32) {
-        float acc[VEC];
-        const float* p0 = partial + ((size_t)cf * 2 + 1) * D;
-        if constexpr (VEC == 4) {
-            const float4 x = reinterpret_cast<const float4*>(p0)[g];
-            acc[0] = x.x; acc[1] = x.y; acc[2] = x.z; acc[3] = x.w;
-        } else {
-            acc[0] = p0[g];
-        }
-        for (int c = cf + 1; c <= cl; ++c) {
-            const float* pc = partial + ((size_t)c * 2 + 0) * D;
-            if constexpr (VEC == 4) {
-                const float4 x = reinterpret_cast<const float4*>(pc)[g];
-                acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
-            } else {
-                acc[0] += pc[g];
+    __syncthreads();
+    for (int j = 0; j < 8; ++j) {
+        const int kk = long_k[j];                              // the same for every thread of the CTA
+        if (kk < 0) continue;
+        const int s0 = __ldg(seg + kk), s1 = __ldg(seg + kk + 1);
+        const int per = (s1 - s0 + 7) / 8;
+        const int p0 = min(s1, s0 + warp * per), p1 = min(s1, p0 + per);
+        float* dst = sums + (size_t)kk * D;
+        for (int g0 = 0; g0 < groups; g0 += 64) {
+            const int ga = g0 + lane, gb = g0 + 32 + lane;
+            float a[VEC], b[VEC];
+            ema_accumulate_rows<VEC>(xr, rows, p0, p1, D, ga, gb, groups, a, b);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { part[warp][lane * VEC + e] = a[e]; part[warp][(32 + lane) * VEC + e] = b[e]; }
+            __syncthreads();
+            for (int t = threadIdx.x; t < 64 * VEC; t += 256) {          // column t of the slab: the 8 partials in warp order
+                const int col = g0 * VEC + t;
+                if (col < D) {
+                    float acc = part[0][t];
+#pragma unroll
+                    for (int w = 1; w < 8; ++w) acc += part[w][t];
+                    dst[col] = acc;
+                }
             }
+            __syncthreads();
         }
-        if constexpr (VEC == 4) reinterpret_cast<float4*>(dst)[g] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        else dst[g] = acc[0];
     }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ apply
@@ -574,11 +497,9 @@ int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, i
     uint32_t* vals_in = reinterpret_cast<uint32_t*>(ws + l.vals_in);
     uint32_t* vals_out = reinterpret_cast<uint32_t*>(ws + l.vals_out);
     int* seg = reinterpret_cast<int*>(ws + l.seg);
-    float* partial = reinterpret_cast<float*>(ws + l.partial);
     float* sums = sums_counts;
     float* counts = sums_counts + (size_t)K * D;
 
-    int* flags = reinterpret_cast<int*>(ws + l.flags);
     const int bin_sort = PERO_KNOB("PERO_EMA_BIN_SORT", 1);     // dev build, 0: radix sort also for the small case
     if (bin_sort && N <= kSmallSortMax && K <= kBinSortMaxK) {
         // stable counting sort in three short launches (ranks + histograms, scan, placement); the per-frame ranks
@@ -598,7 +519,7 @@ int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, i
             }
         }
         ema_rank_kernel<<<nb, kRankCtaThreads, (size_t)K * 2, stream>>>(reinterpret_cast<const long long*>(idx), (int)N, (int)K, lrank,
-                                                                     hist, flags);
+                                                                     hist);
         int* excl = reinterpret_cast<int*>(ws + l.excl);
         int* btot = reinterpret_cast<int*>(ws + l.btot);
         ema_scan_local_kernel<<<(unsigned)((K + 255) / 256), 256, 0, stream>>>(hist, nb, (int)K, excl, btot);
@@ -608,29 +529,20 @@ int pero_vq_ema_accumulate(const float* x_rows, const int64_t* idx, int64_t N, i
     } else if (N <= kSmallSortMax) {
         const int end_bit = key_bits(K) + 1;
         ema_sort_small_kernel<8><<<1, 1024, 0, stream>>>(reinterpret_cast<const long long*>(idx), (int)N, (int)K, end_bit, keys_out,
-                                                        vals_out, seg, flags);
+                                                        vals_out, seg);
     } else {
         ema_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const long long*>(idx), N, keys_in, vals_in);
         size_t cub_bytes = l.cub_bytes;
         cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)N, 0,
                                                         key_bits(K), stream);
         if (e != cudaSuccess) return (int)e;
-        ema_boundaries_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, stream>>>(keys_out, (int)N, (int)K, seg, flags);
+        ema_boundaries_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, stream>>>(keys_out, (int)N, (int)K, seg);
     }
-    const unsigned chunks = (unsigned)((N + kChunk - 1) / kChunk);
     const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_rows) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(sums_counts) & 15) == 0);
     const unsigned kblocks = (unsigned)((K + 7) / 8);
-    if (vec) {
-        const int threads = (int)std::min<int64_t>(128, std::max<int64_t>(32, round_up(D / 4, 32)));
-        ema_rowsum_kernel<4><<<kblocks, 256, 0, stream>>>(x_rows, vals_out, seg, (int)K, (int)D, sums, counts, flags);
-        ema_chunk_sum_kernel<4><<<std::min(chunks, 2048u), threads, 0, stream>>>(x_rows, keys_out, vals_out, seg, (int)N, (int)D, sums, partial, flags);
-        ema_finalize_kernel<4><<<std::min(kblocks, 592u), 256, 0, stream>>>(seg, (int)K, (int)D, partial, sums, flags);
-    } else {
-        ema_rowsum_kernel<1><<<kblocks, 256, 0, stream>>>(x_rows, vals_out, seg, (int)K, (int)D, sums, counts, flags);
-        ema_chunk_sum_kernel<1><<<std::min(chunks, 2048u), 128, 0, stream>>>(x_rows, keys_out, vals_out, seg, (int)N, (int)D, sums, partial, flags);
-        ema_finalize_kernel<1><<<std::min(kblocks, 592u), 256, 0, stream>>>(seg, (int)K, (int)D, partial, sums, flags);
-    }
+    if (vec) ema_rowsum_kernel<4><<<kblocks, 256, 0, stream>>>(x_rows, vals_out, seg, (int)K, (int)D, sums, counts);
+    else ema_rowsum_kernel<1><<<kblocks, 256, 0, stream>>>(x_rows, vals_out, seg, (int)K, (int)D, sums, counts);
     return (int)cudaGetLastError();
 }
 
