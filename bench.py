@@ -296,8 +296,9 @@ class DeviceStep:
         s_ce.wait_event(assigned)
         # --- chain A (main stream): unpack, EMA sums (their exchange goes to the communication stream at once), quantize +
         # commitment loss fwd/bwd, EMA apply.  Data parallel: ONE stream, EMA sums first, so that their exchange is out of
-        # the way before the gradient exchange needs the links (177 instead of 186 us per step at 2 GPUs).  Single GPU:
-        # the EMA update runs on its own low-priority stream beside the rest (133 instead of 143 us).
+        # the way before the gradient exchange needs the links (175-178 us per step at 2 GPUs; 186 with the EMA update on
+        # its own stream, 189 with EMA sums first and the commitment chain on a side stream: measured, round 2).  Single
+        # GPU: the EMA update runs on its own low-priority stream beside the rest (133 instead of 143 us).
         idx, _ = ops.vq_unpack(packed)
         split_ema = os.environ.get("PERO_STEP_SPLIT_EMA", "0" if self.dp else "1") == "1"
         if split_ema:

@@ -907,9 +907,25 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
     //   d_W given, d_b == d_h == NULL -> only dlogits + d_W of the range (the exchange of d_W starts the moment its GEMM
     //                      is done); d_W == NULL, d_b and d_h given (full range) -> d_h AND d_b from the P in the workspace:
     //                      the column sums run beside the d_h GEMM and are exchanged later, as a small message of their own
+    //   d_b only (d_W == d_h == NULL) -> the column sums of the P in the workspace (full range), e.g. on a side stream
+    //                      beside the d_W / d_h GEMMs, so that d_b | loss can be exchanged early as a small message
     const bool dh_only = (!d_W && d_h);               // second phase: no dlogits, no d_W
     const bool dw_only = (d_W && !d_b && !d_h);
+    const bool db_only = (!d_W && !d_h && d_b);
     const bool late_db = (dh_only && d_b);
+    if (db_only) {
+        if (Dh % 4 != 0 || v_begin != 0 || v_end != V) return PERO_ERR_BAD_SHAPE;
+        const CeWsLayout l = ce_ws_layout(N, M, V, Dh);
+        char* ws = static_cast<char*>(workspace);
+        const __nv_bfloat16* P = reinterpret_cast<const __nv_bfloat16*>(ws + l.p_off);
+        float* dbpart = reinterpret_cast<float*>(ws + l.dbpart_off);
+        const int db_nparts = (int)((M + kDbRows - 1) / kDbRows);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        ce_db_partial_kernel<<<(unsigned)db_nparts, 256, 0, st>>>(P, (int)M, (int)l.Pp, 0, (int)(l.Vp / 8), (int)l.Vp, dbpart, 0,
+                                                                 (uint4*)nullptr, 0ll);
+        ce_db_reduce_kernel<<<(unsigned)((V + 31) / 32), 256, 0, st>>>(dbpart, db_nparts, (int)l.Vp, 0, (int)V, d_b);
+        return (int)cudaGetLastError();
+    }
     if ((!lse && h) || (!dh_only && !d_W) || (!dh_only && !dw_only && !d_b)) return PERO_ERR_NULL;      // h == NULL: the log-sum-exp comes from the forward's partials
     if (Dh % 4 != 0) return PERO_ERR_BAD_SHAPE;
     if (v_begin < 0 || v_end > V || v_begin >= v_end || (v_begin % 256) != 0 || (v_end != V && (v_end % 256) != 0))
