@@ -905,7 +905,9 @@ def our_arm(args):
                 "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": 2.0 * (N * c["D"] + c["K"] * c["D"]) + 4.0 * c["K"] + 8.0 * N,
                 "peak_source": f"{src} bf16 burst (kernel timed alone)", "kernel_us": gemm_ms * 1e3, "kernel_us_min": gemm_min * 1e3,
-                "timing": f"{gemm_sets} launches back to back on {gemm_sets} distinct operand sets (> L2 in total) between two CUDA events, x20",
+                "timing": (f"{gemm_sets} launches back to back on {gemm_sets} distinct operand sets (> L2 in total) between two CUDA "
+                           "events, x20; the launches are programmatic (each waits for its predecessor before its first global "
+                           "access), as in a label-production loop"),
                 "algorithmic_flops_per_launch": flops,
                 "step_tensor_tflops": (flops + 6.0 * ds.M * c["Dh"] * c["V"]) / (ms_per_step * 1e-3) / 1e12,
                 "step_frac_of_sustained": (flops + 6.0 * ds.M * c["Dh"] * c["V"]) / (ms_per_step * 1e-3) / 1e12 / sustained}

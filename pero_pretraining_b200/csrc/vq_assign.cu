@@ -239,8 +239,12 @@ int pero_vq_assign_bf16(const void* x_bf16, int64_t N, int64_t K, int64_t D, con
         return PERO_ERR_BAD_SHAPE;
     if ((reinterpret_cast<uintptr_t>(x_bf16) & 15) || (reinterpret_cast<uintptr_t>(codebook) & 255)) return PERO_ERR_BAD_ALIGN;
     const CodebookLayout cl = codebook_layout(K, D);
+    // Programmatic launch: the set-up (barriers, TMEM, descriptor prefetch) overlaps the tail of whatever runs in front
+    // and the first global access waits for it; the kernel behind is released at once (it cannot be co-resident anyway).
+    // A label-production loop that assigns batch after batch therefore pays the ~4 us prologue once, not per batch.
     return run_assign_gemm(static_cast<const __nv_bfloat16*>(x_bf16), N, (int)cl.Dp, cl, codebook, K, (int)index_offset,
-                           reinterpret_cast<long long*>(packed_io), (cudaStream_t)stream);
+                           reinterpret_cast<long long*>(packed_io), (cudaStream_t)stream,
+                           PERO_KNOB("PERO_ASSIGN_BF16_PDL", 1) ? (1 | 4) : 0);
 }
 
 #ifdef PERO_DEV_BUILD
