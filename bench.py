@@ -238,9 +238,14 @@ class DeviceStep:
         # that pending GEMM CTAs are scheduled ahead of the EMA chain's bandwidth-bound kernels.
         # (data parallel: the EMA chain feeds an exchange that should be out of the way before the gradient exchange
         # needs the links, so there it runs at high priority too)
-        ema_prio = int(os.environ.get("PERO_EMA_PRIO", "-1" if dp else "0"))
+        ema_prio = int(os.environ.get("PERO_EMA_PRIO", "-1"))
+        self.commit_side = os.environ.get("PERO_STEP_COMMIT_SIDE", "1") == "1"
+        self.s_commit = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PERO_COMMIT_PRIO", "0")))
         self.s_ema = torch.cuda.Stream(device=dev, priority=ema_prio)
-        self.s_ce = torch.cuda.Stream(device=dev, priority=-1)
+        # the masked-CE chain (and, at the end of the step, its scatter) is the critical path: highest priority the device
+        # offers, so that its pending CTAs are placed ahead of the EMA / commitment kernels whenever SM slots free up
+        self.s_ce = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PERO_CE_PRIO", "-5")))
+        self.s_prep = torch.cuda.Stream(device=dev, priority=0)
         self.s_comm = torch.cuda.Stream(device=dev, priority=-1)
         # Data-parallel exchange ranges (EMA sums|counts and d_W|d_b|loss_sum) live in a peer-mapped buffer and
         # are reduced in place by the library's own NVLink/NVSwitch kernel.
@@ -282,15 +287,18 @@ class DeviceStep:
         main = torch.cuda.current_stream()
         s_ema, s_ce = self.s_ema, self.s_ce
         s_ema.wait_stream(main)
-        s_ce.wait_stream(main)
-        with torch.cuda.stream(s_ce):
-            packed = ops.vq_packed_init(N, self.x.device, out=self.packed)
-            inited = torch.cuda.Event()
-            inited.record(s_ce)
-            self.head.prepare(self.W, self.b)        # head weights change every optimizer step in training
+        # The frame preparation in front of the distance GEMM is the head of the critical path: it is issued first, at
+        # high priority; the head's operand preparation and the gather of the masked hidden states (needed only behind
+        # the distance GEMM) go to a low-priority stream and fill in beside it.
+        s_prep = self.s_prep if os.environ.get("PERO_STEP_PREP_LOW", "1") == "1" else s_ce
+        s_prep.wait_stream(main)
+        packed = self.packed                         # reset by the frame preparation pass of vq_assign
+        with torch.cuda.stream(s_prep):
             ce_ws = ops.masked_ce_gather(self.h, self.rows, c["V"])
-        main.wait_event(inited)
-        _, _, x_rows = ops.vq_assign(self.x, self.cb, c["lines"], c["frames"], True, want_rows=True, packed=packed)
+            self.head.prepare(self.W, self.b)        # head weights change every optimizer step in training
+        _, _, x_rows = ops.vq_assign(self.x, self.cb, c["lines"], c["frames"], True, want_rows=True, packed=packed,
+                                     init_packed=True)
+        s_ce.wait_stream(s_prep)
         assigned = torch.cuda.Event()
         assigned.record(main)
         s_ce.wait_event(assigned)
@@ -311,11 +319,19 @@ class DeviceStep:
                 self.s_comm_ema.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(self.s_comm_ema):
                     self.ema_x.all_reduce_sum_()
-        q = ops.vq_gather_st(x_rows, idx, self.weight, c["lines"], c["frames"], True)
+        # quantize + commitment loss fwd/bwd: a short chain of bandwidth-bound kernels nothing else in the step waits for
+        # (except the EMA apply, which must not overwrite the codebook before the gather has read it).  Single GPU: on a
+        # low-priority stream of its own, so that the longer EMA chain gets the SM slots beside the GEMMs first.
+        # quantized output and the commitment loss value in one pass (the loss needs mean((q - x)^2) only): on the main
+        # stream, right behind the distance GEMM -- the EMA apply may not overwrite the codebook before this has read it
+        q, loss_c = ops.vq_gather_st_mse(x_rows, idx, self.weight, c["lines"], c["frames"], True, 0.0, c["commitment_cost"])
         gathered = torch.cuda.Event()
         gathered.record(main)
-        loss_c = ops.mse_fwd(q, self.x, 0.0, c["commitment_cost"])
-        g_x = ops.vq_st_commit_bwd(self.gq, q, self.x, 2.0 * c["commitment_cost"] / q.numel())
+        s_q = self.s_commit if (split_ema and self.commit_side) else main
+        if s_q is not main:
+            s_q.wait_stream(main)
+        with torch.cuda.stream(s_q):
+            g_x = ops.vq_st_commit_bwd(self.gq, q, self.x, 2.0 * c["commitment_cost"] / q.numel())
         with torch.cuda.stream(s_ema if split_ema else main):
             if self.dp:
                 torch.cuda.current_stream().wait_stream(self.s_comm_ema)
@@ -325,14 +341,15 @@ class DeviceStep:
         # --- chain C
         Dh = c["Dh"]
         with torch.cuda.stream(s_ce):
-            _, _, ws = ops.masked_ce_fwd(self.h, self.rows, packed, self.head, ws=ce_ws, finalize=False, labels_packed=True)
+            _, _, ws = ops.masked_ce_fwd(self.h, self.rows, packed, self.head, ws=ce_ws, finalize=False, labels_packed=True,
+                                         keep_logits=True)
             if not self.dp:
                 # the loss is read out of the log-sum-exp partials beside the backward GEMMs, not behind them
                 self.s_comm.wait_stream(s_ce)
                 with torch.cuda.stream(self.s_comm):
                     loss_sum, lse = ops.masked_ce_loss(ws, N, Dh, self.M, c["V"])
                 d_h, d_W, d_b, flat = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global, ws=ws,
-                                                        return_flat=True, ws_from_fwd=True, labels_packed=True)
+                                                        return_flat=True, ws_from_fwd=True, labels_packed=True, logits_in_ws=True)
             else:
                 # loss_sum rides in the same exchange range as d_W | d_b.  The backward walks the label axis range by
                 # range: each range's rows of d_W are reduced over the ranks on the communication stream while the
@@ -349,13 +366,14 @@ class DeviceStep:
                 for v0, v1 in self.v_ranges:
                     _, d_W, _ = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global,
                                                   ws=ws, want_dh=False, want_db=False, dw_out=g.view(V, Dh),
-                                                     ws_from_fwd=True, v_range=(v0, v1), labels_packed=True)
+                                                     ws_from_fwd=True, v_range=(v0, v1), labels_packed=True, logits_in_ws=True)
                     self.s_comm.wait_stream(s_ce)
                     with torch.cuda.stream(self.s_comm):
                         self.peer.all_reduce_sum_(self.grad_x.offset + 4 * v0 * Dh, (v1 - v0) * Dh)
                 # phase 2: d_h and d_b from the dlogits in the workspace, then the small exchange
                 d_h, _, d_b = ops.masked_ce_bwd(self.h, self.rows, packed, self.head, None, None, 1.0 / self.m_global, ws=ws,
-                                                want_dw=False, want_db=True, db_out=gb[:V], ws_from_fwd=True, labels_packed=True)
+                                                want_dw=False, want_db=True, db_out=gb[:V], ws_from_fwd=True, labels_packed=True,
+                                                logits_in_ws=True)
                 self.s_comm_db.wait_stream(s_ce)
                 with torch.cuda.stream(self.s_comm_db):
                     self.db_x.all_reduce_sum_()
@@ -363,6 +381,8 @@ class DeviceStep:
         main.wait_stream(s_ema)
         main.wait_stream(s_ce)
         main.wait_stream(self.s_comm)
+        if s_q is not main:
+            main.wait_stream(s_q)
         if self.dp:
             main.wait_stream(self.s_comm_ema)
             main.wait_stream(self.s_comm_db)
@@ -671,14 +691,15 @@ class CeChain:
         ops = self.ops
         self.head.prepare(self.W, self.b)
         if not self.dp:
-            loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, self.labels, self.head)
+            loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, self.labels, self.head, keep_logits=True)
             self.out = ops.masked_ce_bwd(self.h, self.rows, self.labels, self.head, lse, None, 1.0 / self.m_global, ws=ws,
-                                         ws_from_fwd=True)
+                                         ws_from_fwd=True, logits_in_ws=True)
         else:
             g = self.grad_x.tensor
-            loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, self.labels, self.head, loss_out=g[self.n_grad:])
+            loss_sum, lse, ws = ops.masked_ce_fwd(self.h, self.rows, self.labels, self.head, loss_out=g[self.n_grad:],
+                                                  keep_logits=True)
             self.out = ops.masked_ce_bwd(self.h, self.rows, self.labels, self.head, lse, None, 1.0 / self.m_global, ws=ws,
-                                         ws_from_fwd=True, flat_out=g[:self.n_grad], return_flat=True)
+                                         ws_from_fwd=True, flat_out=g[:self.n_grad], return_flat=True, logits_in_ws=True)
             self.grad_x.all_reduce_sum_()
         return self.out
 

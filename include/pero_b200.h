@@ -59,6 +59,8 @@ int pero_vq_codebook_prepare(const float* weight, int64_t K, int64_t D, void* co
  *   x               fp32 frames; channels_first = 1: [n_lines, D, frames_per_line] (the NCHW tensor the
  *                   quantizer receives, H*W collapsed; autoencoders.py:205-209 permutes it),
  *                   channels_first = 0: [n_lines * frames_per_line, D] rows (kmeans labeller).
+ *                   Bit 1 (PERO_ASSIGN_INIT_PACKED = 2, or'ed in): `packed_io` is reset to "empty" by the frame
+ *                   preparation pass of this call (the first / only shard of a merge): no pero_vq_packed_init launch.
  *   index_offset    added to every index (codebook shard k0 when the codebook is sharded).
  *   idx   [N] int64 or NULL, dmin [N] fp32 or NULL (|c|^2 - 2<x,c> of the winner, i.e. the squared
  *                   distance minus |x|^2), written only when `packed_io` is NULL.
@@ -68,6 +70,7 @@ int pero_vq_codebook_prepare(const float* weight, int64_t K, int64_t D, void* co
  *                   pero_vq_unpack.  Must be pre-set to INT64_MAX (pero_vq_packed_init).
  *   x_rows [N, D] fp32 or NULL: row-major copy of the frames for the gather / EMA stages.
  */
+#define PERO_ASSIGN_INIT_PACKED 2
 size_t pero_vq_assign_workspace_bytes(int64_t N, int64_t K, int64_t D);
 int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int channels_first, int64_t K,
                    int64_t D, const void* codebook, int64_t index_offset, int64_t* idx, float* dmin,
@@ -88,6 +91,13 @@ int pero_vq_unpack(const int64_t* packed, int64_t N, int64_t* idx, float* dmin, 
 int pero_vq_gather_st(const float* x_rows, const int64_t* idx, const float* weight, int64_t n_lines,
                       int64_t frames_per_line, int channels_first, int64_t K, int64_t D, float* out,
                       pero_stream_t stream);
+/* The same pass, also producing the quantisation loss of  models/autoencoders.py:193-202  (calculate_loss):
+ *     m = mean((out - x)^2),  loss_out[0] = scale_a * m + scale_b * m   (each product rounded to fp32, see pero_mse_fwd)
+ * from per-block partial sums combined in a fixed order: `out` and the frames are not read a second time. */
+size_t pero_vq_gather_st_mse_workspace_bytes(int64_t n_lines, int64_t frames_per_line, int channels_first, int64_t D);
+int pero_vq_gather_st_mse(const float* x_rows, const int64_t* idx, const float* weight, int64_t n_lines,
+                          int64_t frames_per_line, int channels_first, int64_t K, int64_t D, float* out, float scale_a,
+                          float scale_b, float* loss_out, void* workspace, size_t workspace_bytes, pero_stream_t stream);
 
 /* ------------------------------------------------------------------ EMA codebook update
  * Replaces  models/autoencoders.py:225-237.
@@ -161,7 +171,13 @@ int pero_vq_st_commit_bwd(const float* g_quantized, const float* quantized, cons
  *   flags    PERO_CE_H_BF16 (1): h is bf16 (else fp32); PERO_CE_LABELS_PACKED (2): `labels` holds the packed
  *            (distance, index) winners of pero_vq_assign instead of plain int64 labels (label = low 32 bits), so that
  *            the head of a step whose labels are that step's codeword indices can start right behind the distance
- *            GEMM, without waiting for pero_vq_unpack
+ *            GEMM, without waiting for pero_vq_unpack;
+ *            PERO_CE_KEEP_LOGITS (4): training forward -- the sweep also leaves in the workspace, as bf16, the
+ *            exponentials of the masked frames' logits relative to the maximum of their 32-label chunk, plus those
+ *            maxima in fp32 (the softmax numerators up to one fp32 factor per row and chunk; the loss is still taken
+ *            from the fp32 accumulators).  A backward on the same workspace (h = NULL) given the same flag turns them
+ *            into the dlogits in place, in one streaming pass that also yields the d_b partial sums, instead of
+ *            recomputing the logits GEMM; dlogits are rounded to bf16 once, exactly as on the recompute route.
  *   h        hidden states [N, Dh]
  *   rows     [M] int32 frame indices of the masked frames, ascending (mask == 1 order)
  *   labels   [N] int64 (only labels[rows[m]] are read, by the GEMM epilogues, not by the gather; a label outside
@@ -191,6 +207,7 @@ int pero_masked_ce_gather(const void* h, int h_is_bf16, int64_t N, int64_t Dh, c
                           void* workspace, size_t workspace_bytes, pero_stream_t stream);
 #define PERO_CE_H_BF16 1
 #define PERO_CE_LABELS_PACKED 2
+#define PERO_CE_KEEP_LOGITS 4
 int pero_masked_ce_fwd(const void* h, int flags, int64_t N, int64_t Dh, const int32_t* rows, int64_t M,
                        const int64_t* labels, const void* head, int64_t V, float* loss_sum, float* lse,
                        void* workspace, size_t workspace_bytes, pero_stream_t stream);

@@ -32,6 +32,9 @@ SIGNATURES = {
     "pero_vq_packed_init": (c_int, [c_vp, c_i64, c_vp]),
     "pero_vq_unpack": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "pero_vq_gather_st": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_vp]),
+    "pero_vq_gather_st_mse_workspace_bytes": (c_sz, [c_i64, c_i64, c_int, c_i64]),
+    "pero_vq_gather_st_mse": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_f32, c_f32, c_vp, c_vp, c_sz,
+                                      c_vp]),
     "pero_vq_ema_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pero_vq_ema_accumulate": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "pero_vq_ema_apply": (c_int, [c_vp, c_i64, c_i64, c_f64, c_f64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_sz,

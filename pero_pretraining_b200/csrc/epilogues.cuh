@@ -35,6 +35,7 @@ __device__ __forceinline__ void for_each_chunk(uint32_t taddr, Body&& body) {
 // are merged with one signed 64-bit atomicMin on (order_key(d) << 32 | index): min distance first, then
 // lowest index.
 struct ArgminEpi {
+    static constexpr int kMaxRegs = 104;
     static constexpr bool kColVec = true;
     static constexpr int kScratchPerWarp = 0;
     struct Params {
@@ -89,6 +90,7 @@ struct ArgminEpi {
 // chunk is transposed through a warp-private shared-memory tile (144-byte pitch: conflict-free both ways)
 // so that one store instruction writes 4 full 128-byte lines.
 struct StoreEpi {
+    static constexpr int kMaxRegs = 128;
     static constexpr bool kColVec = false;
     static constexpr int kScratchPerWarp = 32 * 144;
     struct Params {
@@ -140,6 +142,7 @@ struct StoreEpi {
 // and columns.  The thread-level work per chunk is 8 shared-memory stores; the global stores run asynchronously
 // while the next chunk is read from TMEM (two tiles in flight).  Needs a 16-byte aligned output with ld % 4 == 0.
 struct StoreTmaEpi {
+    static constexpr int kMaxRegs = 104;
     static constexpr bool kColVec = false;
     static constexpr int kScratchPerWarp = 2 * 4096;
     struct Params {
@@ -180,6 +183,7 @@ struct StoreTmaEpi {
 // Measurement-only epilogues (pero_debug_gemm_tn): NullEpi never touches TMEM (MMA + TMA ceiling),
 // LoadEpi only streams the accumulator out of TMEM (adds the tcgen05.ld cost).
 struct NullEpi {
+    static constexpr int kMaxRegs = 128;
     static constexpr bool kColVec = false;
     static constexpr int kScratchPerWarp = 0;
     struct Params { float* out; };
@@ -189,6 +193,7 @@ struct NullEpi {
     static __device__ __forceinline__ void end_rb(State&, const Params&, const TileCtx&) {}
 };
 struct LoadEpi {
+    static constexpr int kMaxRegs = 128;
     static constexpr bool kColVec = false;
     static constexpr int kScratchPerWarp = 0;
     struct Params { float* out; };

@@ -135,25 +135,27 @@ __device__ __forceinline__ void stamp(const GemmShape& sh, bool on, int unit, in
     if (on) sh.timeline[unit * 8 + slot] = clock64();
 }
 // debug: per-CTA wall-clock (ns) stamps after the per-unit area: [4096 + cta * 4 + slot]
-__device__ __forceinline__ void stamp_cta(const GemmShape& sh, bool on, int slot) {
+__device__ __forceinline__ void stamp_cta(const GemmShape& sh, bool on, int block, int slot) {
     if (on && sh.timeline) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        sh.timeline[4096 + blockIdx.x * 4 + slot] = t;
+        sh.timeline[4096 + block * 4 + slot] = t;
     }
 }
 
-// 128 registers per thread (384 threads -> 48 K of the SM's 64 K registers): the remaining 16 K let one CTA of a
-// bandwidth-bound kernel or of the peer-exchange kernel run on the same SM, so those kernels overlap a resident
-// GEMM instead of waiting for it (or, worse, keeping the next GEMM's CTA off the SM).
+// Epi::kMaxRegs registers per thread (104 where the epilogue fits: 384 threads -> 39 K of the SM's 64 K registers; 128
+// otherwise -> 48 K): the remaining 25 K (16 K) let two or three CTAs (one CTA) of a bandwidth-bound kernel or of the
+// peer-exchange kernel run on the same SM, so those kernels overlap a resident GEMM instead of waiting for it (or, worse,
+// keeping the next GEMM's CTA off the SM).
 // kMajor (bit 0: A, bit 1: B) marks operands that are read "transposed" (MN-major): with both bits set A is stored
 // [k][rows_a] and B [k][rows_b] (the contraction index
 // runs over the rows of the stored matrices), i.e. C = A^T B without a transposed copy of either in HBM.  TMA
 // fetches boxes of {64 contiguous MN-elements, 64 k-rows}; the UMMA descriptors are MN-major.
-template <int kCtaGroup, int kARes, class Epi, int kMajor = 0>
-__global__ void __maxnreg__(128)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmShape sh, const __grid_constant__ typename Epi::Params ep) {
+// The kernel body: `block` / `nblocks` are this CTA's index and the CTA count of ITS GEMM (a dual launch runs two
+// GEMMs in one grid, see gemm_dual_kernel).
+template <int kCtaGroup, int kARes, class Epi, int kMajor>
+__device__ __forceinline__ void gemm_tn_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmShape& sh,
+                                             const typename Epi::Params& ep, const int block, const int nblocks) {
     constexpr bool kAResident = kARes != 0;
     constexpr int kASets = kARes == 2 ? 2 : 1;
     constexpr bool kAMn = (kMajor & 1) != 0, kBMn = (kMajor & 2) != 0;
@@ -161,14 +163,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (sh.pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    stamp_cta(sh, threadIdx.x == 0, 0);
+    stamp_cta(sh, threadIdx.x == 0, block, 0);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
     const bool leader = (cta_rank == 0);
-    const int worker = blockIdx.x / kCtaGroup;
-    const int num_workers = gridDim.x / kCtaGroup;
+    const int worker = block / kCtaGroup;
+    const int num_workers = nblocks / kCtaGroup;
 
     constexpr uint32_t kBRows = kBlockN / kCtaGroup;              // B rows this CTA loads per tile
     constexpr uint32_t kBBlockBytes = kBRows * kBlockK * 2;
@@ -209,7 +211,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool late_wait = kAResident && (sh.pdl & 12) == 12;
     if ((sh.pdl & 4) && !late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    stamp_cta(sh, threadIdx.x == 0, 1);
+    stamp_cta(sh, threadIdx.x == 0, block, 1);
     int u0, u1;
     unit_range(sh, worker, num_workers, u0, u1);
     const bool tl = sh.timeline != nullptr && worker == 0 && cta_rank == 0;
@@ -431,7 +433,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             stamp(sh, tl && warp == 0 && lane == 0, it, 5);
             if (last_of_rb) Epi::end_rb(st, ep, cx);
         }
-        stamp_cta(sh, threadIdx.x == 0, 2);
+        stamp_cta(sh, threadIdx.x == 0, block, 2);
     }
 
     // ---------------------------------------------------------------- teardown
@@ -439,7 +441,30 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 10) tmem_dealloc<kCtaGroup>(tmem_base, 512);
     if (sh.pdl & 2) asm volatile("griddepcontrol.wait;" ::: "memory");
-    stamp_cta(sh, threadIdx.x == 0, 3);
+    stamp_cta(sh, threadIdx.x == 0, block, 3);
+}
+
+template <int kCtaGroup, int kARes, class Epi, int kMajor = 0>
+__global__ void __maxnreg__(Epi::kMaxRegs)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmShape sh, const __grid_constant__ typename Epi::Params ep) {
+    gemm_tn_body<kCtaGroup, kARes, Epi, kMajor>(tmap_a, tmap_b, sh, ep, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Two independent streamed GEMMs (same epilogue class, operand majorness kMajor1 / kMajor2) in ONE grid: the first
+// `ctas1` CTAs run GEMM 1, the others GEMM 2.  One launch instead of two: the pair can be a programmatic dependent of
+// the kernel in front as a whole (both halves wait for it after their set-up), which two back-to-back launches cannot
+// express -- the second would wait for the first to complete.  Used for d_W = P^T A beside d_h = P W.
+template <class Epi, int kMajor1, int kMajor2>
+__global__ void __maxnreg__(Epi::kMaxRegs)
+gemm_dual_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_b1, const GemmShape sh1,
+                 const __grid_constant__ typename Epi::Params ep1, const __grid_constant__ CUtensorMap tmap_a2,
+                 const __grid_constant__ CUtensorMap tmap_b2, const GemmShape sh2,
+                 const __grid_constant__ typename Epi::Params ep2, const int ctas1) {
+    if ((int)blockIdx.x < ctas1)
+        gemm_tn_body<2, 0, Epi, kMajor1>(tmap_a1, tmap_b1, sh1, ep1, (int)blockIdx.x, ctas1);
+    else
+        gemm_tn_body<2, 0, Epi, kMajor2>(tmap_a2, tmap_b2, sh2, ep2, (int)blockIdx.x - ctas1, (int)gridDim.x - ctas1);
 }
 
 }  // namespace pero

@@ -152,13 +152,19 @@ inline int pick_stages(int cta_group, int a_sets, int num_kb, int scratch_per_wa
 // both bits: C = A^T B.  kd is the
 // contraction length rounded up to 64 and k_rows (<= kd, 0 = kd) the rows that exist (TMA zero-fills the rest).
 // kARes: 0 = A streams through the ring with B, 1 = resident A row block, 2 = two resident A sets (num_kb <= 6).
-template <int kCtaGroup, int kARes, class Epi, int kMajor = 0>
-int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int rows_b, int pitch_b, int kd,
-                   int num_ks, int split_mode, int fixed_s, int workers, const typename Epi::Params& ep,
-                   cudaStream_t stream, unsigned long long* timeline = nullptr, size_t smem_budget = kSmemBudget,
-                   int k_rows = 0, int pdl = 0) {
-    if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
+struct GemmLaunch {
+    CUtensorMap ta, tb;
     GemmShape sh;
+    int workers;
+    size_t smem;
+};
+
+template <int kCtaGroup, int kARes, class Epi, int kMajor = 0>
+int prepare_gemm_tn(GemmLaunch& g, const void* a, int rows_a, int pitch_a, const void* b, int rows_b, int pitch_b, int kd,
+                    int num_ks, int split_mode, int fixed_s, int workers, unsigned long long* timeline = nullptr,
+                    size_t smem_budget = kSmemBudget, int k_rows = 0, int pdl = 0) {
+    if (rows_a <= 0 || rows_b <= 0 || kd <= 0 || (kd % kBlockK) != 0) return PERO_ERR_BAD_SHAPE;
+    GemmShape& sh = g.sh;
     sh.timeline = timeline;
 #ifdef PERO_DEV_BUILD
     if (!timeline && g_debug_timeline && g_debug_timeline_slots > 0) {     // debug: one 64 KiB slot per GEMM launch
@@ -189,14 +195,13 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     }
     if (sh.num_stages < 2) return PERO_ERR_BAD_SHAPE;
 
-    CUtensorMap ta, tb;
     int rc;
     const uint64_t kr = (uint64_t)(k_rows > 0 ? k_rows : kd);
-    if constexpr (kMajor & 1) rc = make_tmap_bf16(&ta, a, kr, (uint64_t)rows_a, (uint64_t)pitch_a, 64);
-    else rc = make_tmap_bf16(&ta, a, (uint64_t)rows_a, kr, (uint64_t)pitch_a, kBlockM);
+    if constexpr (kMajor & 1) rc = make_tmap_bf16(&g.ta, a, kr, (uint64_t)rows_a, (uint64_t)pitch_a, 64);
+    else rc = make_tmap_bf16(&g.ta, a, (uint64_t)rows_a, kr, (uint64_t)pitch_a, kBlockM);
     if (rc) return rc;
-    if constexpr (kMajor & 2) rc = make_tmap_bf16(&tb, b, kr, (uint64_t)rows_b, (uint64_t)pitch_b, 64);
-    else rc = make_tmap_bf16(&tb, b, (uint64_t)rows_b, kr, (uint64_t)pitch_b, kBlockN / kCtaGroup);
+    if constexpr (kMajor & 2) rc = make_tmap_bf16(&g.tb, b, kr, (uint64_t)rows_b, (uint64_t)pitch_b, 64);
+    else rc = make_tmap_bf16(&g.tb, b, (uint64_t)rows_b, kr, (uint64_t)pitch_b, kBlockN / kCtaGroup);
     if (rc) return rc;
 
     const long long units = (long long)sh.num_rb * sh.num_ct * sh.num_ks;
@@ -208,9 +213,21 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
     if (split_mode == 1) workers = sh.num_rb * sh.fixed_s;
     else if (workers <= 0 || workers > max_workers) workers = max_workers;
     if (split_mode == 0 && workers > units) workers = (int)units;
+    g.workers = workers;
+    g.smem = gemm_smem_bytes(kCtaGroup, kASets, sh.num_kb, sh.num_stages, Epi::kScratchPerWarp);
+    if (g.smem < kSmemFloor) g.smem = kSmemFloor;
+    return PERO_OK;
+}
 
-    size_t smem = gemm_smem_bytes(kCtaGroup, kASets, sh.num_kb, sh.num_stages, Epi::kScratchPerWarp);
-    if (smem < kSmemFloor) smem = kSmemFloor;
+template <int kCtaGroup, int kARes, class Epi, int kMajor = 0>
+int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int rows_b, int pitch_b, int kd,
+                   int num_ks, int split_mode, int fixed_s, int workers, const typename Epi::Params& ep,
+                   cudaStream_t stream, unsigned long long* timeline = nullptr, size_t smem_budget = kSmemBudget,
+                   int k_rows = 0, int pdl = 0) {
+    GemmLaunch g;
+    int rc = prepare_gemm_tn<kCtaGroup, kARes, Epi, kMajor>(g, a, rows_a, pitch_a, b, rows_b, pitch_b, kd, num_ks, split_mode, fixed_s,
+                                                            workers, timeline, smem_budget, k_rows, pdl);
+    if (rc) return rc;
     auto kern = gemm_tn_kernel<kCtaGroup, kARes, Epi, kMajor>;
     {
         static std::atomic<bool> attr_done[kMaxDevices];
@@ -218,20 +235,50 @@ int launch_gemm_tn(const void* a, int rows_a, int pitch_a, const void* b, int ro
         if (e != cudaSuccess) return (int)e;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(workers * kCtaGroup));
+    cfg.gridDim = dim3((unsigned)(g.workers * kCtaGroup));
     cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = g.smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCtaGroup; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (pdl & 6) {      // may start while the previous kernel of the stream is still running (see GemmShape::pdl)
+    if (g.sh.pdl & 6) {      // may start while the previous kernel of the stream is still running (see GemmShape::pdl)
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.numAttrs = 2;
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, sh, ep);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g.ta, g.tb, g.sh, ep);
+    return e == cudaSuccess ? PERO_OK : (int)e;
+}
+
+// Two prepared streamed pair-GEMMs (prepare_gemm_tn<2, 0, Epi, kMajor1 / kMajor2>) in one grid (gemm_dual_kernel): the
+// first g1.workers pairs run GEMM 1, the next g2.workers pairs GEMM 2.  The launch is programmatic when either shape
+// asks for it (pdl bits 1 / 2).
+template <class Epi, int kMajor1, int kMajor2>
+int launch_gemm_dual(const GemmLaunch& g1, const typename Epi::Params& ep1, const GemmLaunch& g2, const typename Epi::Params& ep2,
+                     cudaStream_t stream) {
+    auto kern = gemm_dual_kernel<Epi, kMajor1, kMajor2>;
+    {
+        static std::atomic<bool> attr_done[kMaxDevices];
+        cudaError_t e = ensure_max_dynamic_smem(kern, attr_done, kSmemBudget);
+        if (e != cudaSuccess) return (int)e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((g1.workers + g2.workers) * 2));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = g1.smem > g2.smem ? g1.smem : g2.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if ((g1.sh.pdl | g2.sh.pdl) & 6) {
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g1.ta, g1.tb, g1.sh, ep1, g2.ta, g2.tb, g2.sh, ep2, g1.workers * 2);
     return e == cudaSuccess ? PERO_OK : (int)e;
 }
 

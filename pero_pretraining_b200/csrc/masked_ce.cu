@@ -47,7 +47,7 @@ constexpr int kDbRows = 8;          // masked frames per partial row of the d_b 
 struct CeWsLayout {
     int64_t Dhp, Vp, Pp, Mp64, Mpad, S, KS;
     size_t a_off, lab_off, inv_off, p_off, pm_off, ps_off, zlab_off, rowloss_off, ticket_off, zlin_off, pcnt_off, dbpart_off,
-        planes_off, total;
+        planes_off, cm_off, total;
 };
 inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     CeWsLayout l;
@@ -83,6 +83,7 @@ inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
     l.pcnt_off = take((size_t)2 * S * l.Mpad * 4);      // evaluation: per-split counts of logits above the label's
     l.dbpart_off = take((size_t)((M + kDbRows - 1) / kDbRows) * l.Vp * 4);   // d_b partial column sums, one row per 8 masked frames
     l.planes_off = take((size_t)KS * M * Dh * 4);
+    l.cm_off = take((size_t)(l.Vp / 32) * l.Mpad * 4);     // PERO_CE_KEEP_LOGITS: chunk maxima of the kept exponentials
     l.total = off;
     return l;
 }
@@ -91,24 +92,41 @@ inline CeWsLayout ce_ws_layout(int64_t N, int64_t M, int64_t V, int64_t Dh) {
 __global__ void __launch_bounds__(256)
 head_prepare_kernel(const float* __restrict__ W, const float* __restrict__ bias, int V, int Dh, int Dhp, int Vt,
                     __nv_bfloat16* __restrict__ wb, float* __restrict__ bias_out) {
-    // bf16 copy of W, rows zero-padded to Dhp columns: 4 elements per thread (16-byte loads when Dh % 4 == 0)
+    // bf16 copy of W, rows zero-padded to Dhp columns: 4 elements per quad (16-byte loads when Dh % 4 == 0), 4 independent
+    // quads per thread and iteration.  The grid is small on purpose (2 CTAs per SM): the kernel is issued at the start of a
+    // step, beside the frame preparation of the quantizer, and must not take every thread slot of the machine.
     const long long quads = (long long)V * (Dhp / 4);
     const long long stride = (long long)gridDim.x * blockDim.x;
     const bool vec = (Dh & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
-        const long long v = q / (Dhp / 4);
-        const int d = (int)(q - v * (Dhp / 4)) * 4;
-        float x[4] = {0.f, 0.f, 0.f, 0.f};
-        if (vec) {
-            if (d < Dh) { const float4 t = __ldg(reinterpret_cast<const float4*>(W + v * Dh + d)); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w; }
-        } else {
+    for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < quads; q0 += 4 * stride) {
+        float x[4][4];
+        long long vv[4]; int dd[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (d + j < Dh) x[j] = __ldg(W + v * Dh + d + j);
+        for (int u = 0; u < 4; ++u) {
+            const long long q = q0 + u * stride;
+            const long long v = q / (Dhp / 4);
+            const int d = (int)(q - v * (Dhp / 4)) * 4;
+            vv[u] = v; dd[u] = d;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[u][j] = 0.f;
+            if (q < quads) {
+                if (vec) {
+                    if (d < Dh) { const float4 t = __ldg(reinterpret_cast<const float4*>(W + v * Dh + d)); x[u][0] = t.x; x[u][1] = t.y; x[u][2] = t.z; x[u][3] = t.w; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (d + j < Dh) x[u][j] = __ldg(W + v * Dh + d + j);
+                }
+            }
         }
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
-        uint2 o;
-        o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(wb + v * Dhp + d) = o;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (q0 + u * stride < quads) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(x[u][0], x[u][1]), hi = __floats2bfloat162_rn(x[u][2], x[u][3]);
+                uint2 o;
+                o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(wb + vv[u] * Dhp + dd[u]) = o;
+            }
+        }
     }
     for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < Vt; v += stride)
         bias_out[v] = v < V ? (bias ? __ldg(bias + v) : 0.f) : -CUDART_INF_F;
@@ -178,11 +196,24 @@ __device__ __forceinline__ int masked_row_of(const int* __restrict__ inv, const 
 // kRank (evaluation, masked_pretraining/tester.py:70-93): the label's logit is known before the sweep (zl_in) and
 // the epilogue also counts the labels whose logit is strictly larger — the label's 0-based rank, from which the
 // top-k errors follow without the [M, V] logits ever existing.
-template <bool kRank>
+// kStore (training forward, PERO_CE_KEEP_LOGITS): the sweep also leaves, in the workspace's P area [M, Pp], the
+// exponentials of the logits relative to the maximum of their own 32-column chunk, e = exp(z - cmax) in (0, 1], as bf16,
+// and the chunk maxima cm [Vp / 32][Mpad] in fp32.  They are the numerators of the softmax up to one fp32 factor per
+// (row, chunk): the backward turns P into the dlogits in place with a multiplication, P = e * exp(cm - lse) * scale
+// (ce_dlogits_inplace_kernel) -- no second logits GEMM and no second exponential per element, and the bf16 rounding of P
+// is a RELATIVE 2^-9 whatever the magnitude of the logits (bf16 logits would lose absolute precision as they grow).
+// The log-sum-exp itself is accumulated from the fp32 exponentials, as without kStore.
+// Staging as in DlogitsEpi: one SWIZZLE_128B tile of 32 rows x 64 columns per warp, handed to a TMA store.
+template <bool kRank, bool kStore = false>
 struct LseEpiT {
+    static constexpr int kMaxRegs = kRank ? 128 : 104;
     static constexpr bool kColVec = true;
-    static constexpr int kScratchPerWarp = 192;     // 8 warps x 192 B = 128 rows x (max, sum, count): half 1 -> half 0 hand-over
+    // 8 warps x 192 B = 128 rows x (max, sum, count): half 1 -> half 0 hand-over; kStore: the 8 staging tiles come first
+    // (1024-byte aligned, as the swizzle pattern requires), the hand-over area behind them
+    static constexpr int kTileBytes = kStore ? 4096 : 0;
+    static constexpr int kScratchPerWarp = 192 + kTileBytes;
     struct Params {
+        CUtensorMap tmap_p;   // kStore: P [M, Vp] bf16, box {64 columns, 32 rows}
         const float* colvec;  // bias [Vt], -inf beyond V
         const int* rows;      // [M] frame of every masked row
         const long long* labels;   // [N] label of every frame
@@ -191,6 +222,8 @@ struct LseEpiT {
         const float* zl_in;   // kRank: [Mpad] label logit computed ahead of the sweep
         int* pcnt;            // kRank: [S, Mpad] partial counts of logits above zl_in
         int M, Mpad, S, V, packed;
+        int Vp;               // kStore: label columns of P to write (multiple of 64)
+        float* cm;            // kStore: [Vp / 32][Mpad] chunk maxima
     };
     struct State { float m, s, zl, zin; int label, cnt; bool has; };
     static __device__ __forceinline__ void begin_rb(State& st, const Params& ep, const TileCtx& cx) {
@@ -199,8 +232,11 @@ struct LseEpiT {
         st.cnt = 0;
         st.zin = (kRank && cx.row < ep.M) ? __ldg(ep.zl_in + cx.row) : CUDART_INF_F;
     }
-    static __device__ __forceinline__ void tile(State& st, const Params&, const TileCtx& cx, uint32_t taddr) {
+    static __device__ __forceinline__ void tile(State& st, const Params& ep, const TileCtx& cx, uint32_t taddr) {
         const float4* cv = reinterpret_cast<const float4*>(cx.cv);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        // cx.scratch = base + warp * kScratchPerWarp; this warp's staging tile is base + warp * 4096
+        const uint32_t stage = smem_u32(cx.scratch) - (uint32_t)(warp * 192);
         for_each_chunk(taddr, [&](int c, const uint32_t (&r)[32]) {
             const int col = cx.col0 + c * 32;
             float z[32];
@@ -232,19 +268,65 @@ struct LseEpiT {
                 if (rel < 32u && st.zl > st.zin) above -= 1;
                 st.cnt += above;
             }
-            if (cmax > -CUDART_INF_F) {
-                const float mn = fmaxf(st.m, cmax);
-                const float mn2 = mn * kLog2e;
+            if constexpr (!kStore) {
+                if (cmax > -CUDART_INF_F) {
+                    const float mn = fmaxf(st.m, cmax);
+                    const float mn2 = mn * kLog2e;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        a0 += ex2_fast(fmaf(z[j + 0], kLog2e, -mn2));
+                        a1 += ex2_fast(fmaf(z[j + 1], kLog2e, -mn2));
+                        a2 += ex2_fast(fmaf(z[j + 2], kLog2e, -mn2));
+                        a3 += ex2_fast(fmaf(z[j + 3], kLog2e, -mn2));
+                    }
+                    st.s = st.s * ex2_fast((st.m - mn) * kLog2e) + ((a0 + a1) + (a2 + a3));
+                    st.m = mn;
+                }
+            } else {
+                // exponentials relative to the chunk's own maximum (an all-padding chunk: exp2(-inf - 0) = 0 everywhere)
+                const bool live = cmax > -CUDART_INF_F;
+                const float c2 = live ? cmax * kLog2e : 0.f;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    a0 += ex2_fast(fmaf(z[j + 0], kLog2e, -mn2));
-                    a1 += ex2_fast(fmaf(z[j + 1], kLog2e, -mn2));
-                    a2 += ex2_fast(fmaf(z[j + 2], kLog2e, -mn2));
-                    a3 += ex2_fast(fmaf(z[j + 3], kLog2e, -mn2));
+                    z[j + 0] = ex2_fast(fmaf(z[j + 0], kLog2e, -c2)); a0 += z[j + 0];
+                    z[j + 1] = ex2_fast(fmaf(z[j + 1], kLog2e, -c2)); a1 += z[j + 1];
+                    z[j + 2] = ex2_fast(fmaf(z[j + 2], kLog2e, -c2)); a2 += z[j + 2];
+                    z[j + 3] = ex2_fast(fmaf(z[j + 3], kLog2e, -c2)); a3 += z[j + 3];
                 }
-                st.s = st.s * ex2_fast((st.m - mn) * kLog2e) + ((a0 + a1) + (a2 + a3));
-                st.m = mn;
+                if (live) {
+                    const float mn = fmaxf(st.m, cmax);
+                    st.s = st.s * ex2_fast((st.m - mn) * kLog2e) + ((a0 + a1) + (a2 + a3)) * ex2_fast((cmax - mn) * kLog2e);
+                    st.m = mn;
+                }
+                if (col < ep.Vp) {                                  // warp-uniform: Vp is a multiple of 64
+                    ep.cm[(size_t)(col >> 5) * ep.Mpad + cx.row] = cmax;      // 32 consecutive rows per warp store
+                    if ((c & 1) == 0) {                             // the previous store must have read the tile
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                    }
+                    const uint32_t rowaddr = stage + (uint32_t)lane * 128u;
+                    const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __nv_bfloat162 o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(z[8 * i + 2 * j], z[8 * i + 2 * j + 1]);
+                        const uint32_t piece = (uint32_t)((c & 1) * 4 + i) ^ sw;
+                        const uint4 v = *reinterpret_cast<uint4*>(&o[0]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                     ::"r"(rowaddr + piece * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    }
+                    if (c & 1) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&ep.tmap_p, stage, col - 32, cx.row - lane);
+                            tma_store_commit();
+                        }
+                    }
+                }
             }
         });
     }
@@ -253,9 +335,11 @@ struct LseEpiT {
     // slot per worker, which halves what the readers of the partials have to fetch.
     static __device__ __forceinline__ void end_rb(State& st, const Params& ep, const TileCtx& cx) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        float* xch = reinterpret_cast<float*>(cx.scratch - warp * kScratchPerWarp);          // [128][3]
+        float* xch = reinterpret_cast<float*>(cx.scratch - warp * kScratchPerWarp + 8 * kTileBytes);     // [128][3]
         const int r = (warp & 3) * 32 + lane;                                                // row inside the CTA's 128
         const int slot = cx.worker % ep.S;
+        // the staging tile must stay valid until the last store has read it (the CTA may exit right after this)
+        if (kStore && lane == 0) tma_store_wait_read();
         if (st.has) ep.zlab[cx.row] = st.zl;
         else if (st.label == -2 && slot == 0 && cx.half == 0) ep.zlab[cx.row] = CUDART_NAN_F;      // label outside [0, V)
         if (cx.half == 1) {
@@ -275,6 +359,7 @@ struct LseEpiT {
     }
 };
 using LseEpi = LseEpiT<false>;
+using LseStoreEpi = LseEpiT<false, true>;
 using EvalEpi = LseEpiT<true>;
 
 // dlogits tile = (exp(z - lse) - [col == label]) * scale, written bf16 as P [M, Vp] only.  Both gradient GEMMs read
@@ -285,6 +370,7 @@ using EvalEpi = LseEpiT<true>;
 // descriptor): no per-row predicates, no address arithmetic, full 128-byte row segments on the way to L2
 // (16 us instead of 24 us for the kernel at the bench shape, round 2).
 struct DlogitsEpi {
+    static constexpr int kMaxRegs = 128;
     static constexpr bool kColVec = true;
     static constexpr int kScratchPerWarp = 4096;
     struct Params {
@@ -519,6 +605,7 @@ ce_db_partial_kernel(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, in
                      float* __restrict__ part, int wait_for_previous, uint4* __restrict__ zero_fill, long long zero_vec) {
     // side-by-side schedule: this kernel also clears d_h (zero_vec 16-byte words) while the gradient GEMMs run, so
     // that the scatter behind them only has to write the masked frames
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // a programmatic successor waits for this grid itself
     if (zero_fill) {
         const long long stride = (long long)gridDim.x * blockDim.x;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < zero_vec; i += stride)
@@ -549,6 +636,130 @@ ce_db_partial_kernel(const __nv_bfloat16* __restrict__ p, int M, int p_pitch, in
     // side-by-side schedule: this kernel was released early by the d_h GEMM in front of it and must not be seen to
     // finish before that one (see pero_masked_ce_bwd_range)
     if (wait_for_previous) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Backward on what the forward left in P (PERO_CE_KEEP_LOGITS: e = exp(z - cmax) per 32-column chunk, cm = the maxima):
+//   P[m, v] <- e[m, v] * exp(cm[chunk(v), m] - lse_m) * scale - [v == label_m] * scale      in place,
+// and the d_b partial column sums of the same 8 rows in the same pass (fp32 values, before the bf16 rounding).
+// One block = 8 masked rows (one row group of the d_b partials) x 2048 label columns (256 threads x 8 columns: 8
+// independent 16-byte loads in flight per thread, every warp instruction touches 512 contiguous bytes; the 8 columns of a
+// thread lie in one chunk, whose maxima for the 8 rows are 32 contiguous bytes).  One exponential per (row, thread), three
+// instructions per element, one round trip to memory per block; three blocks per SM are resident and the hardware
+// back-fills the rest.  The log-sum-exp of a row is rebuilt from the forward's per-worker partials by one warp (slots
+// in lane order, fixed shuffle tree: bit-identical from run to run and for every column range) while the loads are in
+// flight.
+__global__ void __launch_bounds__(256, 3)
+ce_dlogits_inplace_kernel(__nv_bfloat16* __restrict__ p, int M, int p_pitch, int v_begin, int v_len8, int vp,
+                          const float* __restrict__ pm, const float* __restrict__ ps, int slots, int Mpad,
+                          const float* __restrict__ cm, const int* __restrict__ rows, const long long* __restrict__ labels,
+                          int V, int packed, const float* __restrict__ grad_scale, float inv_count, float* __restrict__ part,
+                          int wait_for_previous, uint4* __restrict__ zero_fill, long long zero_vec) {
+    // launched programmatically behind the forward's GEMM (or its finalize): everything read here is theirs
+    if (wait_for_previous) asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // the gradient GEMMs set themselves up meanwhile
+    __shared__ float s_lse2[kDbRows];
+    __shared__ int s_label[kDbRows];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float scale = inv_count * (grad_scale ? __ldg(grad_scale) : 1.0f);
+    const int groups = (M + kDbRows - 1) / kDbRows;
+    // consecutive blocks are consecutive row groups of one column chunk
+    const int chunk = blockIdx.x / groups, grp = blockIdx.x - chunk * groups;
+    const int m0 = grp * kDbRows;
+    const int c = chunk * 256 + (int)threadIdx.x;
+    const bool c_ok = c < v_len8;
+    uint4 raw[kDbRows];
+#pragma unroll
+    for (int r = 0; r < kDbRows; ++r)
+        raw[r] = (m0 + r < M && c_ok) ? *(reinterpret_cast<const uint4*>(p + (size_t)(m0 + r) * p_pitch + v_begin) + c)
+                                      : make_uint4(0u, 0u, 0u, 0u);
+    // chunk maxima of the 8 rows (m0 is a multiple of 8 and Mpad of 256: rows beyond M exist in the array)
+    float cmx[kDbRows];
+    {
+        const float4* cp = reinterpret_cast<const float4*>(cm + (size_t)((v_begin + 8 * (c_ok ? c : 0)) >> 5) * Mpad + m0);
+        const float4 u = __ldg(cp), v = __ldg(cp + 1);
+        cmx[0] = u.x; cmx[1] = u.y; cmx[2] = u.z; cmx[3] = u.w; cmx[4] = v.x; cmx[5] = v.y; cmx[6] = v.z; cmx[7] = v.w;
+    }
+    {
+        const int m = m0 + warp;                   // 8 warps <-> 8 rows
+        float l2 = CUDART_INF_F;
+        if (m < M) {
+            float mx = -CUDART_INF_F, sum = 0.f;
+            for (int s0 = 0; s0 < slots; s0 += 32) {
+                const bool in = s0 + lane < slots;
+                const float pmv = in ? __ldg(pm + (size_t)(s0 + lane) * Mpad + m) : -CUDART_INF_F;
+                const float psv = in ? __ldg(ps + (size_t)(s0 + lane) * Mpad + m) : 0.f;
+                float bm = pmv;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+                bm = fmaxf(bm, mx);
+                float t = (bm > -CUDART_INF_F) ? psv * ex2_fast((pmv - bm) * kLog2e) : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                sum = ((bm > -CUDART_INF_F) ? sum * ex2_fast((mx - bm) * kLog2e) : 0.f) + t;
+                mx = bm;
+            }
+            l2 = fmaf(mx, kLog2e, log2f(sum));
+        }
+        if (lane == 0) {
+            s_lse2[warp] = l2;
+            s_label[warp] = masked_label(labels, rows, m, M, V, packed);
+        }
+    }
+    __syncthreads();
+    // every block also clears its share of d_h (zero_vec 16-byte words: the scatter behind the gradient GEMMs then writes
+    // the masked frames only); plain stores, nothing waits for them here
+    if (zero_fill) {
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < zero_vec; i += stride)
+            zero_fill[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (!c_ok) return;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int col = v_begin + 8 * c;
+    uint4* prow = reinterpret_cast<uint4*>(p + (size_t)m0 * p_pitch + v_begin) + c;
+    const int rows_here = min(kDbRows, M - m0);
+#pragma unroll
+    for (int r = 0; r < kDbRows; ++r) {
+        if (r < rows_here) {
+            // exp(cm - lse) * scale: the softmax factor of this (row, chunk); exp2(-inf) = 0 on padding chunks
+            const float f = ex2_fast(fmaf(cmx[r], kLog2e, -s_lse2[r])) * scale;
+            const uint32_t w[4] = {raw[r].x, raw[r].y, raw[r].z, raw[r].w};
+            float g[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {           // bf16 pair -> fp32: low half shifted up, high half masked
+                g[2 * j] = __uint_as_float(w[j] << 16) * f;
+                g[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u) * f;
+            }
+            const unsigned rel = (unsigned)(s_label[r] - col);
+            if (rel < 8u) {                         // the row's label lies in this thread's 8 columns (one thread in 256 per row)
+                switch (rel) {
+                    case 0: g[0] -= scale; break;
+                    case 1: g[1] -= scale; break;
+                    case 2: g[2] -= scale; break;
+                    case 3: g[3] -= scale; break;
+                    case 4: g[4] -= scale; break;
+                    case 5: g[5] -= scale; break;
+                    case 6: g[6] -= scale; break;
+                    default: g[7] -= scale; break;
+                }
+            }
+            uint4 o;
+            __nv_bfloat162 t;
+            t = __floats2bfloat162_rn(g[0], g[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(g[2], g[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(g[4], g[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(g[6], g[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
+            *prow = o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += g[j];
+        }
+        prow = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(prow) + p_pitch);
+    }
+    float4* o4 = reinterpret_cast<float4*>(part + (size_t)grp * vp + v_begin + 8 * c);
+    o4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
 // One block finishes 32 labels: thread (c = tid % 32, g = tid / 32) adds the partial rows g, g + 8, ... of label
@@ -752,8 +963,9 @@ int pero_head_prepare(const float* W, const float* bias, int64_t V, int64_t Dh, 
     if (head_bytes < l.total) return PERO_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(head) & 255) return PERO_ERR_BAD_ALIGN;
     char* base = static_cast<char*>(head);
-    long long blocks = ((long long)V * (l.Dhp / 4) + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    long long blocks = ((long long)V * (l.Dhp / 4) + 1023) / 1024;
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    if (blocks < 1) blocks = 1;
     head_prepare_kernel<<<(unsigned)blocks, 256, 0, stream>>>(W, bias, (int)V, (int)Dh, (int)l.Dhp, (int)l.Vt,
                                                             reinterpret_cast<__nv_bfloat16*>(base + l.w_off),
                                                             reinterpret_cast<float*>(base + l.bias_off));
@@ -806,23 +1018,40 @@ int pero_masked_ce_fwd(const void* h, int flags, int64_t N, int64_t Dh, const in
         rc = ce_gather(h, h_is_bf16, rows, (int)M, (int)Dh, l, ws, st);
         if (rc) return rc;
     }
-    LseEpi::Params ep;
-    ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
-    ep.rows = rows; ep.labels = reinterpret_cast<const long long*>(labels);
-    ep.pm = reinterpret_cast<float*>(ws + l.pm_off);
-    ep.ps = reinterpret_cast<float*>(ws + l.ps_off);
-    ep.zlab = reinterpret_cast<float*>(ws + l.zlab_off);
-    ep.zl_in = nullptr; ep.pcnt = nullptr;
-    ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S; ep.V = (int)V; ep.packed = packed;
+    auto fill = [&](auto& ep) {
+        ep.colvec = reinterpret_cast<const float*>(hb + hl.bias_off);
+        ep.rows = rows; ep.labels = reinterpret_cast<const long long*>(labels);
+        ep.pm = reinterpret_cast<float*>(ws + l.pm_off);
+        ep.ps = reinterpret_cast<float*>(ws + l.ps_off);
+        ep.zlab = reinterpret_cast<float*>(ws + l.zlab_off);
+        ep.zl_in = nullptr; ep.pcnt = nullptr;
+        ep.M = (int)M; ep.Mpad = (int)l.Mpad; ep.S = (int)l.S; ep.V = (int)V; ep.packed = packed; ep.Vp = (int)l.Vp;
+        ep.cm = reinterpret_cast<float*>(ws + l.cm_off);
+    };
     // behind its own gather: the set-up overlaps the gather, the first load waits for it (programmatic launch); the
     // kernel behind is released when the last operand load of a CTA has been requested (bit 4)
-    rc = launch_logits_gemm<LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, /*split_mode=*/1, (int)l.S, ep, st,
-                                    kSmemBudgetShared, (h ? 4 : 0) | 16);
+    float* pm = reinterpret_cast<float*>(ws + l.pm_off);
+    float* ps = reinterpret_cast<float*>(ws + l.ps_off);
+    float* zlab = reinterpret_cast<float*>(ws + l.zlab_off);
+    if (flags & PERO_CE_KEEP_LOGITS) {
+        // training forward: the bf16 logits stay in the workspace (P area); the backward converts them in place
+        LseStoreEpi::Params ep;
+        fill(ep);
+        rc = make_tmap_bf16(&ep.tmap_p, ws + l.p_off, (uint64_t)M, (uint64_t)l.Vp, (uint64_t)l.Pp, 32);
+        if (rc) return rc;
+        rc = launch_logits_gemm<LseStoreEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, /*split_mode=*/1, (int)l.S, ep,
+                                             st, kSmemBudget, (h ? 4 : 0) | 16);
+    } else {
+        LseEpi::Params ep;
+        fill(ep);
+        rc = launch_logits_gemm<LseEpi>(ws + l.a_off, (int)M, (int)l.Dhp, hb + hl.w_off, (int)V, /*split_mode=*/1, (int)l.S, ep, st,
+                                        kSmemBudgetShared, (h ? 4 : 0) | 16);
+    }
     if (rc || !lse) return rc;
     // lse / rowloss / loss_sum from the partials.  A backward GEMM launched right behind on the same workspace rebuilds
     // the log-sum-exp from the partials itself and never reads this kernel's output.
     float* rowloss = reinterpret_cast<float*>(ws + l.rowloss_off);
-    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(ep.pm, ep.ps, ep.zlab, (int)M, (int)l.Mpad, (int)l.S, lse,
+    ce_finalize_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(pm, ps, zlab, (int)M, (int)l.Mpad, (int)l.S, lse,
                                                               rowloss, reinterpret_cast<unsigned int*>(ws + l.ticket_off),
                                                               loss_sum);
     return (int)cudaGetLastError();
@@ -921,8 +1150,10 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
         float* dbpart = reinterpret_cast<float*>(ws + l.dbpart_off);
         const int db_nparts = (int)((M + kDbRows - 1) / kDbRows);
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-        ce_db_partial_kernel<<<(unsigned)db_nparts, 256, 0, st>>>(P, (int)M, (int)l.Pp, 0, (int)(l.Vp / 8), (int)l.Vp, dbpart, 0,
-                                                                 (uint4*)nullptr, 0ll);
+        // (PERO_CE_KEEP_LOGITS: the in-place dlogits pass of the earlier calls has left the partial sums already)
+        if (!(h == nullptr && (flags & PERO_CE_KEEP_LOGITS)))
+            ce_db_partial_kernel<<<(unsigned)db_nparts, 256, 0, st>>>(P, (int)M, (int)l.Pp, 0, (int)(l.Vp / 8), (int)l.Vp, dbpart, 0,
+                                                                     (uint4*)nullptr, 0ll);
         ce_db_reduce_kernel<<<(unsigned)((V + 31) / 32), 256, 0, st>>>(dbpart, db_nparts, (int)l.Vp, 0, (int)V, d_b);
         return (int)cudaGetLastError();
     }
@@ -950,7 +1181,41 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
     const int pdl_on = PERO_KNOB("PERO_CE_PDL", 1);                  // dev build, 0: the gradient GEMMs run one after the other
     const bool side_by_side = pdl_on && store_pairs && !dh_only && d_h != nullptr && full_range;
     const bool db_beside_dh = late_db && pdl_on && store_pairs;      // second phase: column sums beside the d_h GEMM
-    const int half_workers = device_sm_count() / 4;
+    // Side by side, the two GEMMs share the SM pairs: the split of the pairs and the number of label-axis slices of d_h are
+    // chosen together so that both halves finish at the same time (k-block steps of the slowest worker), with as few d_h
+    // planes as that allows (the planes are written by the GEMM and read again by the scatter).
+    int ks_use = (int)l.KS, dw_share = device_sm_count() / 4, dh_share = device_sm_count() / 4;
+    if (side_by_side) {
+        const int T = device_sm_count() / 2;
+        const long long u_w = ((V + 255) / 256) * ((Dh + 255) / 256), kb_w = l.Mp64 / 64;
+        const long long t_h = ((M + 255) / 256) * ((Dh + 255) / 256), kb_h = l.Vp / 64;
+        long long best = -1;
+        for (int ks = 1; ks <= (int)l.KS; ++ks) {
+            const long long kbps = (kb_h + ks - 1) / ks, planes_n = (kb_h + kbps - 1) / kbps, units_h = t_h * planes_n;
+            for (int wh = 1; wh < T; ++wh) {
+                const int ww = T - wh;
+                const long long tw = ((u_w + ww - 1) / ww) * kb_w, th = ((units_h + wh - 1) / wh) * kbps;
+                const long long cost = std::max(tw, th) * 64 + planes_n;        // time first, then fewer planes
+                if (best < 0 || cost < best) { best = cost; ks_use = ks; dw_share = ww; dh_share = wh; }
+            }
+        }
+    }
+    // PERO_CE_KEEP_LOGITS (with h == NULL): the forward left the bf16 logits in P; the first phase converts them in place
+    // and produces the d_b partial sums in the same pass, so no later phase has to compute them
+    const bool logits_in_ws = (h == nullptr) && (flags & PERO_CE_KEEP_LOGITS) != 0;
+    bool use_dual = false, dh_cleared = false;
+    GemmLaunch dual_w, dual_h;
+    StoreTmaEpi::Params dual_ep_w;
+    // d_h = P W runs as split-K planes [ks][M, Dh] over slices of the label axis
+    float* planes = reinterpret_cast<float*>(ws + l.planes_off);
+    // the number of planes actually produced is recomputed exactly as launch_gemm_tn does
+    const int dh_num_kb = (int)(l.Vp / 64);
+    const int dh_kb_per = (dh_num_kb + ks_use - 1) / ks_use;
+    const int dh_planes = (dh_num_kb + dh_kb_per - 1) / dh_kb_per;
+    StoreTmaEpi::Params sht;
+    const bool dh_tma = d_h != nullptr && PERO_KNOB("PERO_STORE_TMA", 1) != 0 && store_pairs &&
+                        make_tmap_f32_store(&sht.tmap_out, planes, (uint64_t)dh_planes, (uint64_t)M, (uint64_t)Dh, (uint64_t)Dh,
+                                            (uint64_t)M * Dh) == PERO_OK;
     if (!dh_only) {
         if (h && v_begin == 0) {
             rc = ce_gather(h, h_is_bf16, rows, (int)M, (int)Dh, l, ws, st);
@@ -978,7 +1243,29 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
             ep.p_pitch = (int)l.Pp; ep.col_base = (int)v_begin;
         };
         const void* wslice = hb + hl.w_off + (size_t)v_begin * l.Dhp * 2;
-        {
+        if (logits_in_ws) {
+            // (side by side: the pass also clears d_h, so that the scatter only writes the masked frames)
+            const long long zero_bytes = (long long)N * Dh * (h_is_bf16 ? 2 : 4);
+            dh_cleared = side_by_side && (zero_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_h) & 15) == 0);
+            // the forward left the softmax numerators in P: one in-place streaming pass (+ the d_b partial sums of the
+            // range) instead of the logits GEMM; launched programmatically behind the kernel in front
+            cudaLaunchConfig_t cfg = {};
+            const long long tasks = (long long)db_nparts * ((vp_range / 8 + 255) / 256);
+            if (tasks > (1ll << 30)) return PERO_ERR_BAD_SHAPE;
+            const int grid = (int)tasks;
+            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = pdl_on ? 1 : 0;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, ce_dlogits_inplace_kernel, P, (int)M, (int)l.Pp, (int)v_begin, (int)(vp_range / 8),
+                                               (int)l.Vp, reinterpret_cast<const float*>(ws + l.pm_off),
+                                               reinterpret_cast<const float*>(ws + l.ps_off), (int)l.S, (int)l.Mpad,
+                                               reinterpret_cast<const float*>(ws + l.cm_off), (const int*)rows, reinterpret_cast<const long long*>(labels), (int)V, packed, grad_scale,
+                                               inv_count, dbpart, pdl_on ? 1 : 0, dh_cleared ? static_cast<uint4*>(d_h) : (uint4*)nullptr,
+                                               dh_cleared ? zero_bytes / 16 : 0ll);
+            if (e != cudaSuccess) return (int)e;
+        } else {
             DlogitsEpi::Params ep;
             fill(ep);
             // store descriptor of P[:, v_begin : v_begin + vp_range]: boxes of {64 columns, 32 rows}, clipped at M rows
@@ -997,9 +1284,17 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
                                                 (uint64_t)vlen * Dh) == PERO_OK;
         StoreEpi::Params sw;
         sw.out = d_W + (size_t)v_begin * Dh; sw.ld = Dh; sw.split_stride = 0; sw.rows = (int)vlen; sw.cols = (int)Dh;
-        const int dw_workers = side_by_side ? half_workers : 0;
-        const int dw_pdl = (side_by_side || pdl_on) ? 1 : 0;
-        if (dw_tma)
+        const int dw_workers = side_by_side ? dw_share : 0;
+        // behind the in-place dlogits pass the gradient GEMMs are programmatic dependents: set-up during its tail, first
+        // load after it (bit 2)
+        const int dw_pdl = ((side_by_side || pdl_on) ? 1 : 0) | ((logits_in_ws && pdl_on) ? 4 : 0);
+        use_dual = side_by_side && dw_tma && dh_tma && PERO_KNOB("PERO_CE_DUAL", 1) != 0;
+        if (use_dual) {
+            // d_W and d_h in ONE grid (gemm_dual_kernel), launched below once the d_h half is prepared
+            dual_ep_w = swt;
+            rc = prepare_gemm_tn<2, 0, StoreTmaEpi, 3>(dual_w, P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp,
+                                                       (int)l.Mp64, 1, 0, 1, dw_workers, nullptr, kSmemBudgetShared, (int)M, dw_pdl);
+        } else if (dw_tma)
             rc = launch_gemm_tn<2, 0, StoreTmaEpi, 3>(P + v_begin, (int)vlen, (int)l.Pp, ws + l.a_off, (int)Dh, (int)l.Dhp, (int)l.Mp64,
                                                          1, 0, 1, dw_workers, swt, st, nullptr, kSmemBudgetShared, (int)M, dw_pdl);
         else if (store_pairs)
@@ -1012,7 +1307,7 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
         // d_b: partial column sums of P now, unless the side-by-side schedule below runs them beside the GEMMs; the
         // final sums on their own when this call stops after d_W | d_b (they are exchanged next), otherwise by the
         // leading blocks of the scatter launch
-        if (!side_by_side && !dw_only) {
+        if (!side_by_side && !dw_only && !logits_in_ws) {
             // beside the d_W GEMM (released by it at once, waits for it before exiting) when PDL is on
             const int vlen8 = (int)(vp_range / 8);      // P's padding columns are zeros
             cudaLaunchConfig_t cfg = {};
@@ -1034,34 +1329,32 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
     if (d_h) {
         // planes[ks] [M, Dh] = P [M, Vp] @ W [V, Dh] over the ks-th slice of the label axis: P is the K-major operand, the
         // head's one bf16 copy is read MN-major (boxes of {64 hidden channels, 64 labels}; labels beyond V read as zero)
-        float* planes = reinterpret_cast<float*>(ws + l.planes_off);
-        // the number of planes actually produced is recomputed exactly as launch_gemm_tn does
-        const int dh_num_kb = (int)(l.Vp / 64);
-        const int dh_kb_per = (dh_num_kb + (int)l.KS - 1) / (int)l.KS;
-        const int dh_planes = (dh_num_kb + dh_kb_per - 1) / dh_kb_per;
-        StoreTmaEpi::Params sht;
-        const bool dh_tma = PERO_KNOB("PERO_STORE_TMA", 1) != 0 && store_pairs &&
-                            make_tmap_f32_store(&sht.tmap_out, planes, (uint64_t)dh_planes, (uint64_t)M, (uint64_t)Dh, (uint64_t)Dh,
-                                                (uint64_t)M * Dh) == PERO_OK;
         StoreEpi::Params sh;
         sh.out = planes; sh.ld = Dh; sh.split_stride = (long long)M * Dh; sh.rows = (int)M; sh.cols = (int)Dh;
-        const int dh_workers = side_by_side ? half_workers : 0;
+        const int dh_workers = side_by_side ? dh_share : 0;
         const int dh_pdl = side_by_side ? 3 : (db_beside_dh ? 1 : 0);
-        if (dh_tma)
-            rc = launch_gemm_tn<2, 0, StoreTmaEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.KS, 0, 1,
+        if (use_dual) {
+            rc = prepare_gemm_tn<2, 0, StoreTmaEpi, 2>(dual_h, P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp,
+                                                       ks_use, 0, 1, dh_workers, nullptr, kSmemBudgetShared, (int)V, dual_w.sh.pdl);
+            if (rc) return rc;
+            rc = launch_gemm_dual<StoreTmaEpi, 3, 2>(dual_w, dual_ep_w, dual_h, sht, st);
+        } else if (dh_tma)
+            rc = launch_gemm_tn<2, 0, StoreTmaEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, ks_use, 0, 1,
                                                       dh_workers, sht, st, nullptr, kSmemBudgetShared, (int)V, dh_pdl);
         else if (store_pairs)
-            rc = launch_gemm_tn<2, 0, StoreEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.KS, 0, 1,
+            rc = launch_gemm_tn<2, 0, StoreEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, ks_use, 0, 1,
                                                    dh_workers, sh, st, nullptr, kSmemBudgetShared, (int)V, dh_pdl);
         else
-            rc = launch_gemm_tn<1, 0, StoreEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, (int)l.KS, 0, 1, 0,
+            rc = launch_gemm_tn<1, 0, StoreEpi, 2>(P, (int)M, (int)l.Pp, hb + hl.w_off, (int)Dh, (int)l.Dhp, (int)l.Vp, ks_use, 0, 1, 0,
                                                    sh, st, nullptr, kSmemBudgetShared, (int)V);
         if (rc) return rc;
-        if (late_db && !db_beside_dh) {        // no programmatic launches: plain column sums behind the GEMM
+        if (late_db && !db_beside_dh && !logits_in_ws) {        // no programmatic launches: plain column sums behind the GEMM
             ce_db_partial_kernel<<<(unsigned)db_nparts, 256, 0, st>>>((const __nv_bfloat16*)P, (int)M, (int)l.Pp, 0, (int)(l.Vp / 8),
                                                                      (int)l.Vp, dbpart, 0, (uint4*)nullptr, 0ll);
         }
-        if (side_by_side || db_beside_dh) {
+        if (dh_cleared) {
+            scatter_masked_only = true;
+        } else if (side_by_side || db_beside_dh) {
             // third member of the side-by-side group: released by the d_h GEMM as soon as that one has started
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)db_nparts); cfg.blockDim = dim3(256); cfg.stream = st;
@@ -1073,8 +1366,9 @@ int pero_masked_ce_bwd_range(const void* h, int flags, int64_t N, int64_t Dh, co
             const bool can_zero = (((long long)N * Dh * (h_is_bf16 ? 2 : 4)) % 16 == 0) &&    // whole 16-byte words
                                   ((reinterpret_cast<uintptr_t>(d_h) & 15) == 0);
             scatter_masked_only = can_zero;
+            // (logits_in_ws: the partial sums exist already and this launch only clears d_h)
             cudaError_t e = cudaLaunchKernelEx(&cfg, ce_db_partial_kernel, (const __nv_bfloat16*)P, (int)M, (int)l.Pp, 0,
-                                               (int)(l.Vp / 8), (int)l.Vp, dbpart, 1,
+                                               logits_in_ws ? 0 : (int)(l.Vp / 8), (int)l.Vp, dbpart, 1,
                                                can_zero ? static_cast<uint4*>(d_h) : (uint4*)nullptr, can_zero ? zero_vec : 0ll);
             if (e != cudaSuccess) return (int)e;
         }

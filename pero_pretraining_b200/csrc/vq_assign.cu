@@ -191,6 +191,8 @@ int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int
     if (n_lines < 0 || frames_per_line < 0) return PERO_ERR_BAD_SHAPE;
     const int64_t N = n_lines * frames_per_line;
     if (N == 0) return PERO_OK;
+    const bool init_packed = (channels_first & PERO_ASSIGN_INIT_PACKED) != 0;
+    channels_first &= 1;
     if (!x || !codebook || !workspace) return PERO_ERR_NULL;
     if (K <= 0 || D <= 0 || N > (1ll << 31) - 256 || K + index_offset > (1ll << 31) - 1 || index_offset < 0 || D > 65536)
         return PERO_ERR_BAD_SHAPE;
@@ -203,19 +205,20 @@ int pero_vq_assign(const float* x, int64_t n_lines, int64_t frames_per_line, int
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + wl.xb_off);
     long long* packed_ws = reinterpret_cast<long long*>(ws + wl.packed_off);
     long long* packed = packed_io ? reinterpret_cast<long long*>(packed_io) : packed_ws;
+    long long* packed_reset = packed_io ? (init_packed ? packed : nullptr) : packed_ws;      // reset by the preparation pass
     const int Dp = (int)cl.Dp;
 
     if (channels_first) {
         if (n_lines > 65535) return PERO_ERR_BAD_SHAPE;
         dim3 grid((unsigned)((frames_per_line + 31) / 32), (unsigned)(Dp / 64), (unsigned)n_lines);
         frames_prepare_cf_kernel<<<grid, 256, 0, stream>>>(x, (int)D, Dp, (int)frames_per_line, N, xb, x_rows,
-                                                           packed_io ? nullptr : packed_ws);
+                                                           packed_reset);
     } else {
         const long long pairs = N * (Dp / 2);
         long long blocks = (pairs + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         frames_prepare_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, (int)D, Dp, N, xb, x_rows,
-                                                                         packed_io ? nullptr : packed_ws);
+                                                                         packed_reset);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

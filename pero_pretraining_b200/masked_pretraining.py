@@ -138,9 +138,13 @@ class _FusedHeadCE(torch.autograd.Function):
         if not lab.is_contiguous():
             lab = lab.contiguous()
         saved, loss = [], None
+        # a forward that will be differentiated leaves the softmax numerators of the masked frames in its workspace (bf16,
+        # relative to per-chunk maxima); the backward scales them in place instead of running the logits GEMM again
+        keep = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        ctx.keep_logits = keep
         for rows, m_local, weight in terms:
             if m_local > 0:
-                loss_sum, lse, ws = ops.masked_ce_fwd(h2, rows, lab, head_prep)
+                loss_sum, lse, ws = ops.masked_ce_fwd(h2, rows, lab, head_prep, keep_logits=keep)
             else:
                 loss_sum, lse, ws = torch.zeros(1, device=h2.device), None, None
             if dp_group is not None:
@@ -193,15 +197,20 @@ class _FusedHeadCE(torch.autograd.Function):
                 gs, inv = g * scale, 1.0
             else:
                 gs, inv = g, scale
-            # the forward's workspace still holds the gathered operands of this term: no second gather
+            # the forward's workspace still holds the gathered operands of this term: no second gather.  The in-place
+            # conversion of the kept logits consumes them: a second backward through the same graph (retain_graph)
+            # recomputes from h and the saved log-sum-exp instead.
+            fresh = not getattr(ctx, "ws_consumed", False)
             dh_t, _, _, flat_t = ops.masked_ce_bwd(h2, rows, lab, head, lse, gs, inv, want_dh=want_dh,
-                                                   return_flat=True, ws=ws, ws_from_fwd=True,
+                                                   return_flat=True, ws=ws if fresh else None, ws_from_fwd=fresh,
+                                                   logits_in_ws=ctx.keep_logits and fresh,
                                                    flat_out=peer.tensor if (first and peer is not None) else None)
             d_h = dh_t if d_h is None else (d_h + dh_t if dh_t is not None else d_h)
             if first:
                 flat = flat_t
             else:
                 flat.add_(flat_t)
+        ctx.ws_consumed = True
         if flat is None:
             flat = peer.tensor.zero_() if peer is not None else torch.zeros(head.V * head.Dh + head.V, device=h2.device)
             if want_dh:

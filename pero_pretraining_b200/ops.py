@@ -62,9 +62,11 @@ class PreparedCodebook:
 
 
 def vq_assign(x, codebook, n_lines, frames_per_line, channels_first, want_dmin=False, want_rows=False,
-              index_offset=0, packed=None):
+              index_offset=0, packed=None, init_packed=False):
     """Nearest-codeword indices.  x: [n_lines, D, frames] (channels_first) or [N, D].
-    Returns (idx int64 [N] or None, dmin or None, x_rows or None)."""
+    Returns (idx int64 [N] or None, dmin or None, x_rows or None).
+    packed: min-merge the packed (distance, index) winners into this int64 [N] buffer instead (pre-set by vq_packed_init,
+    or reset by this call's frame preparation pass when init_packed)."""
     L = _lib.lib()
     x = _f32c(x, "x")
     N = int(n_lines) * int(frames_per_line)
@@ -77,7 +79,7 @@ def vq_assign(x, codebook, n_lines, frames_per_line, channels_first, want_dmin=F
         return idx, dmin, x_rows
     wsb = L.pero_vq_assign_workspace_bytes(N, K, D)
     ws = _ws(wsb, dev)
-    check(L.pero_vq_assign(x.data_ptr(), int(n_lines), int(frames_per_line), 1 if channels_first else 0, K, D,
+    check(L.pero_vq_assign(x.data_ptr(), int(n_lines), int(frames_per_line), (1 if channels_first else 0) | (2 if init_packed else 0), K, D,
                            codebook.blob.data_ptr(), int(index_offset), _p(idx), _p(dmin), _p(packed), _p(x_rows),
                            ws.data_ptr(), wsb, _stream()), "pero_vq_assign")
     return idx, dmin, x_rows
@@ -136,6 +138,24 @@ def vq_gather_st(x_rows, idx, weight, n_lines, frames_per_line, channels_first):
                                        int(frames_per_line), 1 if channels_first else 0, K, D, out.data_ptr(),
                                        _stream()), "pero_vq_gather_st")
     return out
+
+
+def vq_gather_st_mse(x_rows, idx, weight, n_lines, frames_per_line, channels_first, scale_a=1.0, scale_b=0.0):
+    """(out = x + (weight[idx] - x), the 0-dim loss scale_a * m + scale_b * m with m = mean((out - x)^2)) in one pass
+    (pero_vq_gather_st_mse): VectorQuantizer.forward's output and calculate_loss's value without re-reading either."""
+    L = _lib.lib()
+    w = _f32c(weight, "weight")
+    K, D = w.shape
+    cf = 1 if channels_first else 0
+    shape = (int(n_lines), D, int(frames_per_line)) if channels_first else (int(n_lines) * int(frames_per_line), D)
+    out = torch.empty(shape, dtype=torch.float32, device=w.device)
+    loss = torch.empty((), dtype=torch.float32, device=w.device)
+    wsb = L.pero_vq_gather_st_mse_workspace_bytes(int(n_lines), int(frames_per_line), cf, D)
+    ws = _ws(wsb, w.device)
+    check(L.pero_vq_gather_st_mse(x_rows.data_ptr(), idx.data_ptr(), w.data_ptr(), int(n_lines), int(frames_per_line), cf, K, D,
+                                  out.data_ptr(), float(scale_a), float(scale_b), loss.data_ptr(), ws.data_ptr(), wsb, _stream()),
+          "pero_vq_gather_st_mse")
+    return out, loss
 
 
 def vq_ema_accumulate(x_rows, idx, K, out=None):
@@ -257,17 +277,19 @@ def masked_ce_gather(h, rows, V):
     return ws
 
 
-def _ce_flags(h, labels_packed):
-    return (1 if h.dtype == torch.bfloat16 else 0) | (2 if labels_packed else 0)
+def _ce_flags(h, labels_packed, keep_logits=False):
+    return (1 if h.dtype == torch.bfloat16 else 0) | (2 if labels_packed else 0) | (4 if keep_logits else 0)
 
 
-def masked_ce_fwd(h, rows, labels, head, loss_out=None, ws=None, finalize=True, labels_packed=False):
+def masked_ce_fwd(h, rows, labels, head, loss_out=None, ws=None, finalize=True, labels_packed=False, keep_logits=False):
     """h [N, Dh]; rows int32 [M]; labels int64 [N].  Returns (loss_sum [1], lse [M], workspace).
     `loss_out`: optional fp32 [1] destination (e.g. a slot of the peer-exchange range next to d_W|d_b).
     `ws`: the workspace masked_ce_gather returned for the same (h, rows): no second gather.
     `finalize=False`: only the logits sweep; (loss_sum, lse) are None and masked_ce_loss(ws, ...) produces them later
     (a backward with ws_from_fwd does not need them).
-    `labels_packed`: `labels` are the packed (distance, index) winners of vq_assign(packed=...)."""
+    `labels_packed`: `labels` are the packed (distance, index) winners of vq_assign(packed=...).
+    `keep_logits`: training forward (PERO_CE_KEEP_LOGITS): the softmax numerators of the masked frames (bf16, relative to
+    per-chunk maxima) stay in `ws`; pass logits_in_ws=True to the masked_ce_bwd(ws_from_fwd=True) that follows."""
     L = _lib.lib()
     h = _check_h(h)
     N, Dh = h.shape
@@ -282,7 +304,7 @@ def masked_ce_fwd(h, rows, labels, head, loss_out=None, ws=None, finalize=True, 
         raise ValueError("ws is smaller than pero_masked_ce_workspace_bytes for this shape")
     if not gathered:
         ws = _ws(wsb, h.device)
-    check(L.pero_masked_ce_fwd(None if gathered else h.data_ptr(), _ce_flags(h, labels_packed), N, Dh, rows.data_ptr(), M,
+    check(L.pero_masked_ce_fwd(None if gathered else h.data_ptr(), _ce_flags(h, labels_packed, keep_logits), N, Dh, rows.data_ptr(), M,
                                labels.data_ptr(), head.blob.data_ptr(), head.V, _p(loss_sum), _p(lse),
                                ws.data_ptr(), wsb, _stream()), "pero_masked_ce_fwd")
     return loss_sum, lse, ws
@@ -323,7 +345,7 @@ def masked_ce_eval(h, rows, labels, head, ks=(1, 3, 10), want_rank=False):
 
 def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=True, ws=None, return_flat=False,
                   want_dw=True, flat_out=None, ws_from_fwd=False, v_range=None, labels_packed=False, want_db=None,
-                  dw_out=None, db_out=None):
+                  dw_out=None, db_out=None, logits_in_ws=False):
     """Returns (d_h [N, Dh] like h or None, d_W [V, Dh] fp32, d_b [V] fp32[, flat buffer holding d_W|d_b]).
     ws_from_fwd: `ws` is the workspace masked_ce_fwd returned for the same (h, rows, labels) and has not been
     touched since: the gathered operands in it are reused instead of gathering again, and the log-sum-exp is rebuilt
@@ -332,7 +354,8 @@ def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=Tru
     want_dh=False, and a final call with want_dw=False for d_h once every range is done.
     Phases for a data-parallel caller (pero_masked_ce_bwd_range): want_dw only (want_db=False, want_dh=False) -> dlogits +
     d_W, whose exchange can start the moment the GEMM is done; then want_dw=False, want_db=True, want_dh=True -> d_h and
-    d_b from the dlogits left in `ws`.  dw_out / db_out: separate destinations (e.g. two peer-exchange ranges)."""
+    d_b from the dlogits left in `ws`.  dw_out / db_out: separate destinations (e.g. two peer-exchange ranges).
+    logits_in_ws (with ws_from_fwd): the forward ran with keep_logits=True; every phase of this backward must say so."""
     L = _lib.lib()
     h = _check_h(h)
     N, Dh = h.shape
@@ -358,7 +381,9 @@ def masked_ce_bwd(h, rows, labels, head, lse, grad_scale, inv_count, want_dh=Tru
     v0, v1 = (0, head.V) if v_range is None else (int(v_range[0]), int(v_range[1]))
     if lse is None and not ws_from_fwd:
         raise ValueError("lse is required unless ws_from_fwd")
-    check(L.pero_masked_ce_bwd_range(None if ws_from_fwd else h.data_ptr(), _ce_flags(h, labels_packed), N, Dh,
+    if logits_in_ws and not ws_from_fwd:
+        raise ValueError("logits_in_ws needs ws_from_fwd")
+    check(L.pero_masked_ce_bwd_range(None if ws_from_fwd else h.data_ptr(), _ce_flags(h, labels_packed, logits_in_ws), N, Dh,
                                      rows.data_ptr(), M, labels.data_ptr(), head.blob.data_ptr(), head.V, _p(lse), _p(gs),
                                      float(inv_count), v0, v1, _p(d_h), _p(d_W), _p(d_b), ws.data_ptr(), wsb,
                                      _stream()), "pero_masked_ce_bwd_range")

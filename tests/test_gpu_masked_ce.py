@@ -203,9 +203,11 @@ def test_mask_compact_matches_nonzero(cuda_dev):
         assert int(count0) == ref0.numel() and torch.equal(rows0[:ref0.numel()].long(), ref0)
 
 
-def test_backward_by_label_ranges_equals_full_backward(cuda_dev):
+@pytest.mark.parametrize("keep", [False, True])
+def test_backward_by_label_ranges_equals_full_backward(cuda_dev, keep):
     """pero_masked_ce_bwd_range: walking the label axis range by range (what the data-parallel step does to overlap
-    the exchange of d_W with the next range) gives bit-identical d_W, d_b and d_h."""
+    the exchange of d_W with the next range) gives bit-identical d_W and d_b, and d_h to fp32 summation order -- with the logits GEMM recomputed
+    (keep=False) and with the forward's bf16 logits converted in place (keep=True, PERO_CE_KEEP_LOGITS)."""
     from pero_pretraining_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(5)
     N, Dh, V, M = 1024, 512, 1300, 150
@@ -215,20 +217,59 @@ def test_backward_by_label_ranges_equals_full_backward(cuda_dev):
     labels = torch.randint(0, V, (N,), generator=g).to(cuda_dev)
     rows = torch.sort(torch.randperm(N, generator=g)[:M]).values.int().to(cuda_dev)
     head = ops.PreparedHead(V, Dh, cuda_dev).prepare(W, b)
-    loss_sum, lse, ws = ops.masked_ce_fwd(h, rows, labels, head)
-    d_h, d_W, d_b = ops.masked_ce_bwd(h, rows, labels, head, lse, None, 1.0 / M, ws=ws, ws_from_fwd=True)
-    loss_sum2, lse2, ws2 = ops.masked_ce_fwd(h, rows, labels, head)
+    loss_sum, lse, ws = ops.masked_ce_fwd(h, rows, labels, head, keep_logits=keep)
+    d_h, d_W, d_b = ops.masked_ce_bwd(h, rows, labels, head, lse, None, 1.0 / M, ws=ws, ws_from_fwd=True, logits_in_ws=keep)
+    loss_sum2, lse2, ws2 = ops.masked_ce_fwd(h, rows, labels, head, keep_logits=keep)
     assert torch.equal(lse, lse2) and torch.equal(loss_sum, loss_sum2)
     flat = torch.full((V * Dh + V,), float("nan"), device=cuda_dev)
     for v0, v1 in ((0, 512), (512, 1024), (1024, V)):
         ops.masked_ce_bwd(h, rows, labels, head, lse2, None, 1.0 / M, ws=ws2, ws_from_fwd=True, want_dh=False, flat_out=flat,
-                          return_flat=True, v_range=(v0, v1))
+                          return_flat=True, v_range=(v0, v1), logits_in_ws=keep)
     d_h2, _, _ = ops.masked_ce_bwd(h, rows, labels, head, lse2, None, 1.0 / M, ws=ws2, want_dw=False)
     assert torch.equal(flat[:V * Dh].view(V, Dh), d_W)
     assert torch.equal(flat[V * Dh:], d_b)
-    assert torch.equal(d_h2, d_h)
+    # d_h = dlogits @ W is summed over label-axis slices whose number depends on how many SM pairs the GEMM has to itself
+    # (alone here, beside the d_W GEMM in the one-call backward): same dlogits bits, fp32 summation order differs
+    assert torch.equal(d_h2 == 0, d_h == 0)
+    assert float((d_h2 - d_h).abs().max()) <= 2e-6 * float(d_h.abs().max())
+    d_h3, _, _ = ops.masked_ce_bwd(h, rows, labels, head, lse2, None, 1.0 / M, ws=ws2, want_dw=False)
+    assert torch.equal(d_h3, d_h2)                    # and bit-identical from run to run
     with pytest.raises(Exception):                    # ranges must start on a multiple of 256
         ops.masked_ce_bwd(h, rows, labels, head, lse2, None, 1.0 / M, ws=ws2, want_dh=False, v_range=(100, 512))
+
+
+@pytest.mark.parametrize("N,Dh,V,M,dtype", [(8192, 512, 8192, 1245, torch.float32), (1024, 512, 4096, 150, torch.bfloat16),
+                                             (300, 96, 1000, 77, torch.float32), (64, 576, 300, 64, torch.float32)])
+def test_kept_logits_backward_matches_recompute_backward(cuda_dev, N, Dh, V, M, dtype):
+    """The two backward routes of the fused head -- logits GEMM recomputed, or the forward's kept softmax numerators
+    (bf16, relative to per-chunk maxima) scaled in place -- agree within the bf16 tolerance of the path (both round the
+    dlogits to bf16 once more or less), give the same loss terms, and the in-place route's d_b sums to zero."""
+    from pero_pretraining_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(N + V)
+    h = torch.randn(N, Dh, generator=g).to(cuda_dev).to(dtype)
+    W = (torch.randn(V, Dh, generator=g) * 0.08).to(cuda_dev)        # logits up to ~ +-8
+    b = (torch.randn(V, generator=g) * 0.1).to(cuda_dev)
+    labels = torch.randint(0, V, (N,), generator=g).to(cuda_dev)
+    rows = torch.sort(torch.randperm(N, generator=g)[:M]).values.int().to(cuda_dev)
+    head = ops.PreparedHead(V, Dh, cuda_dev).prepare(W, b)
+    out = {}
+    for keep in (False, True):
+        loss_sum, lse, ws = ops.masked_ce_fwd(h, rows, labels, head, keep_logits=keep)
+        out[keep] = (loss_sum.clone(), lse.clone()) + tuple(
+            t.float().clone() for t in ops.masked_ce_bwd(h, rows, labels, head, lse, None, 1.0 / M, ws=ws, ws_from_fwd=True,
+                                                         logits_in_ws=keep))
+    # the loss comes from the fp32 accumulators on both routes (summed chunk by chunk on the kept route: last-bit differences)
+    assert torch.allclose(out[False][0], out[True][0], rtol=1e-5) and torch.allclose(out[False][1], out[True][1], rtol=1e-5, atol=1e-5)
+    for i, what in ((2, "d_h"), (3, "d_W"), (4, "d_b")):
+        a, c = out[False][i].double(), out[True][i].double()
+        err = (a - c).abs().max().item()
+        assert err <= GRAD_RTOL * max(a.abs().max().item(), 1e-12), f"{what}: {err:.3e} vs {a.abs().max().item():.3e}"
+    # rows that are not masked get exactly zero gradient on both routes
+    unmasked = torch.ones(N, dtype=torch.bool, device=cuda_dev)
+    unmasked[rows.long()] = False
+    assert float(out[True][2][unmasked].abs().max()) == 0.0 if bool(unmasked.any()) else True
+    # gradient of the bias = sum over the masked frames of (softmax - onehot) / M: the columns sum to zero overall
+    assert abs(float(out[True][4].double().sum())) < 1e-3
 
 
 @pytest.mark.parametrize("Nl,T_,Dh,V,p", [(8, 128, 512, 4096, 0.15), (5, 37, 96, 1000, 0.5), (3, 50, 512, 257, 0.3)])

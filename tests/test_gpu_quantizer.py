@@ -316,6 +316,15 @@ def test_gather_st_and_mse_kernels(cuda_dev):
         ref = rows + (w[idx] - rows)
         assert torch.equal(out, ref.view(nl, T_, D).permute(0, 2, 1).contiguous())
         assert torch.equal(ops.vq_gather_st(rows, idx, w, nl, T_, False), ref)
+        # one pass for the quantized output AND the quantisation loss: same output bits, loss = the separate kernel's value
+        for cf in (True, False):
+            out2, loss2 = ops.vq_gather_st_mse(rows, idx, w, nl, T_, cf, 1.0, 0.25)
+            want = out if cf else ref
+            assert torch.equal(out2, want)
+            xs = x if cf else rows
+            np.testing.assert_allclose(loss2.item(), 1.25 * ((want.double() - xs.double()) ** 2).mean().item(), rtol=2e-6)
+            np.testing.assert_allclose(loss2.item(), ops.mse_fwd(want, xs, 1.0, 0.25).item(), rtol=2e-6)
+            assert torch.equal(loss2, ops.vq_gather_st_mse(rows, idx, w, nl, T_, cf, 1.0, 0.25)[1])      # deterministic
     a = torch.randn(1000003, generator=g).to(cuda_dev)
     b = torch.randn(1000003, generator=g).to(cuda_dev)
     m1, m2 = ops.mse_fwd(a, b, 0.0, 0.25), ops.mse_fwd(a, b, 0.0, 0.25)
