@@ -426,10 +426,16 @@ def dump_timeline(run, path):
             f.write(f"{e.time_range.start - t0:10.1f} {e.time_range.end - e.time_range.start:8.1f} {e.name[:110]}\n")
 
 
-def e2e_leg(batch, dev, dp, steps, warm, repeats=3):
+def e2e_leg(batch, dev, dp, steps, warm, repeats=3, loss_read="pipelined", single_thread_autograd=True):
     """Public module API, host inputs: per step H2D of x (fp32) / h (bf16: what --bfloat16 training hands the head,
     masked_pretraining/trainer.py:57-59) / mask rows from pinned memory, D2H of the loss.  `repeats` timed loops of
-    `steps` steps each; returns (median s/step, min s/step, all, h2d bytes, d2h bytes, last loss)."""
+    `steps` steps each; returns (median s/step, min s/step, all, h2d bytes, d2h bytes, last loss).
+    loss_read: "sync" = `loss.item()` at the end of every step (the host waits for the device before it starts launching
+    the next step); "pipelined" = every step's loss is copied D2H into pinned memory asynchronously and read by the host
+    one step later (the usual logging pattern of a training loop: the host keeps launching while the device finishes);
+    every step's loss is still read inside the timed region, the last one behind the closing synchronize.
+    single_thread_autograd: `torch.autograd.set_multithreading_enabled(False)` -- the backward of this step is three
+    custom nodes on one device; running them in the calling thread saves the hand-off to the engine's device thread."""
     from pero_pretraining_b200 import LinearHead, VectorQuantizer
     c = CFG
     vq = VectorQuantizer(c["K"], c["D"], c["commitment_cost"], c["decay"], c["epsilon"]).to(dev).train()
@@ -470,6 +476,9 @@ def e2e_leg(batch, dev, dp, steps, warm, repeats=3):
         e.record()
     stage(0)
     labels_shape = (c["lines"], c["frames"])
+    pipelined = loss_read == "pipelined"
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
     def step():
         i = state["i"]
@@ -485,8 +494,23 @@ def e2e_leg(batch, dev, dp, steps, warm, repeats=3):
         head.linear.bias.grad = None
         torch.autograd.backward([loss, q], [None, gq])
         consumed[i & 1].record(main)
-        return float(loss.item())                      # D2H read of the step's result
+        if not pipelined:
+            return float(loss.item())                  # D2H read of the step's result
+        loss_host[i & 1].copy_(loss.detach(), non_blocking=True)      # D2H of this step's result, read one step later
+        loss_ready[i & 1].record(main)
+        if i == 0:
+            return None
+        loss_ready[(i - 1) & 1].synchronize()
+        return float(loss_host[(i - 1) & 1])
 
+    def last_loss():
+        i = state["i"] - 1
+        loss_ready[i & 1].synchronize()
+        return float(loss_host[i & 1])
+
+    prev_mt = torch.autograd.is_multithreading_enabled()
+    if single_thread_autograd:
+        torch.autograd.set_multithreading_enabled(False)
     for _ in range(warm):
         step()
     times = []
@@ -497,6 +521,8 @@ def e2e_leg(batch, dev, dp, steps, warm, repeats=3):
         t0 = time.perf_counter()
         for _ in range(steps):
             loss_val = step()
+        if pipelined:
+            loss_val = last_loss()                     # the last step's loss: read inside the timed region too
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if dp:
@@ -504,6 +530,7 @@ def e2e_leg(batch, dev, dp, steps, warm, repeats=3):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             dt = float(t.item())
         times.append(dt / steps)
+    torch.autograd.set_multithreading_enabled(prev_mt)
     return float(np.median(times)), float(min(times)), times, h2d, 4, loss_val
 
 
@@ -935,10 +962,22 @@ def our_arm(args):
     _log("roofline leg done")
     e2e = None
     if not args.skip_e2e:
-        s_per_step, s_min, s_all, h2d, d2h, _ = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup))
+        st_autograd = os.environ.get("PERO_E2E_ST", "1") != "0"
+        loss_read = os.environ.get("PERO_E2E_LOSS", "pipelined")
+        # the same loop with a blocking `loss.item()` per step, reported beside the headline for comparison
+        sync_s, sync_min, _, _, _, sync_loss = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup), loss_read="sync",
+                                                       single_thread_autograd=st_autograd)
+        s_per_step, s_min, s_all, h2d, d2h, e2e_loss = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup),
+                                                               loss_read=loss_read, single_thread_autograd=st_autograd)
         e2e = {"value": m_total / s_per_step, "unit": "masked frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": s_per_step * 1e3, "ms_per_step_min": s_min * 1e3, "ms_per_step_all": [t * 1e3 for t in s_all],
                "statistic": f"median of {len(s_all)} timed loops of {args.steps} steps",
+               "loss_read": ("every step's loss copied D2H into pinned memory asynchronously and read by the host one step "
+                             "later, the last one before the closing synchronize" if loss_read == "pipelined" else
+                             "blocking loss.item() at the end of every step"),
+               "ms_per_step_blocking_loss_read": sync_s * 1e3, "ms_per_step_blocking_loss_read_min": sync_min * 1e3,
+               "autograd": "single-threaded (torch.autograd.set_multithreading_enabled(False))" if st_autograd else "default",
+               "last_loss": e2e_loss, "last_loss_blocking": sync_loss,
                "inputs": "x fp32 [64,256,1,128] + hidden states bf16 [64,128,512] + masked-row list, pinned host memory",
                "api": ("VectorQuantizer.forward (enable_cuda_graph" + (", data parallel" if dp else "") +
                        ") / calculate_loss + LinearHead.masked_loss + backward")}

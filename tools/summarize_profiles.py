@@ -34,7 +34,7 @@ def launches(src, dst):
         tot += v / 1000.0
     with open(dst, "w") as f:
         f.write(f"# Launch list of one bench step (ncu gpu__time_duration.sum, --clock-control none)\n\n")
-        f.write(f"Source: `{src}`; command: `python bench.py --steps 2 --warmup 1 --no-graph --skip-cpu --skip-e2e`.\n")
+        f.write(f"Source: `{src}`; command: `python bench.py --steps 2 --warmup 1 --no-graph --skip-cpu --skip-e2e --skip-configs --skip-gpu-baseline`.\n")
         f.write("Per-launch times under ncu are cold-cache and serialised: read the SHARE column.\n\n")
         f.write("| # | kernel | us | share |\n|---|---|---|---|\n")
         for k, (n, v) in enumerate(out):
