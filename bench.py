@@ -238,7 +238,7 @@ class DeviceStep:
         # that pending GEMM CTAs are scheduled ahead of the EMA chain's bandwidth-bound kernels.
         # (data parallel: the EMA chain feeds an exchange that should be out of the way before the gradient exchange
         # needs the links, so there it runs at high priority too)
-        ema_prio = int(os.environ.get("PERO_EMA_PRIO", "-1"))
+        ema_prio = int(os.environ.get("PERO_EMA_PRIO", "-2"))
         self.commit_side = os.environ.get("PERO_STEP_COMMIT_SIDE", "1") == "1"
         self.s_commit = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PERO_COMMIT_PRIO", "0")))
         self.s_ema = torch.cuda.Stream(device=dev, priority=ema_prio)
@@ -324,11 +324,15 @@ class DeviceStep:
         # low-priority stream of its own, so that the longer EMA chain gets the SM slots beside the GEMMs first.
         # quantized output and the commitment loss value in one pass (the loss needs mean((q - x)^2) only): on the main
         # stream, right behind the distance GEMM -- the EMA apply may not overwrite the codebook before this has read it
-        q, loss_c = ops.vq_gather_st_mse(x_rows, idx, self.weight, c["lines"], c["frames"], True, 0.0, c["commitment_cost"])
-        gathered = torch.cuda.Event()
-        gathered.record(main)
         s_q = self.s_commit if (split_ema and self.commit_side) else main
-        if s_q is not main:
+        gather_side = s_q is not main and os.environ.get("PERO_STEP_GATHER_SIDE", "1") == "1"
+        if gather_side:
+            s_q.wait_stream(main)
+        with torch.cuda.stream(s_q if gather_side else main):
+            q, loss_c = ops.vq_gather_st_mse(x_rows, idx, self.weight, c["lines"], c["frames"], True, 0.0, c["commitment_cost"])
+            gathered = torch.cuda.Event()
+            gathered.record(torch.cuda.current_stream())
+        if s_q is not main and not gather_side:
             s_q.wait_stream(main)
         with torch.cuda.stream(s_q):
             g_x = ops.vq_st_commit_bwd(self.gq, q, self.x, 2.0 * c["commitment_cost"] / q.numel())

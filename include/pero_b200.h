@@ -304,6 +304,26 @@ int pero_peer_allreduce_min_i64(void* const* peer_bufs, void* multicast_base, in
 int pero_peer_allreduce_emulate(void* const* bufs_on_one_device, int world, int op, int64_t offset_bytes, int64_t n_elems,
                                 int n_blocks, pero_stream_t stream);
 
+/* ------------------------------------------------------------------ 1x1 projections around the quantizer
+ * Replaces  models/autoencoders.py:114-115, 143-147  (VQVAE.encoder_projection_layer / decoder_projection_layer, the two
+ * 1x1 Conv2d layers of VQVAE.quantize).  A 1x1 convolution is y[n, :] = W x[n, :] + b over the N = n_lines *
+ * frames_per_line frames.
+ * pero_proj_forward: x fp32, channels_first = 1: [n_lines, C, frames_per_line] (the NCHW tensor with H*W collapsed),
+ *   0: rows [N, C]; weight [D, C] (the conv weight [D, C, 1, 1]), bias [D] or NULL.  fp32-grade arithmetic on the tensor
+ *   cores: every operand is split into bf16 hi + lo parts, three partial products, fp32 accumulation (error ~2^-16
+ *   relative).  Outputs, each optional (at least one): out_rows fp32 [N, D]; out_bf16 bf16 [N, Dp] (Dp = D rounded up
+ *   to 64, zero padded): exactly the operand pero_vq_assign_bf16 reads, so the projected NCHW tensor never exists;
+ *   packed_reset [N] int64 or NULL is set to "empty" (saves the pero_vq_packed_init launch in front of the assign).
+ * pero_gather_rows_cf: out[l, c, t] = table[idx[l * frames_per_line + t], c]  (table [K, C] fp32, out channels-first):
+ *   with table = pero_proj_forward(codebook rows, decoder weight, bias) this is decoder_projection_layer(quantized),
+ *   because the 1x1 projection commutes with the row gather.  Indices are clamped to [0, K). */
+size_t pero_proj_workspace_bytes(int64_t N, int64_t C, int64_t D);
+int pero_proj_forward(const float* x, int64_t n_lines, int64_t frames_per_line, int channels_first, int64_t C,
+                      const float* weight, const float* bias, int64_t D, float* out_rows, void* out_bf16,
+                      int64_t* packed_reset, void* workspace, size_t workspace_bytes, pero_stream_t stream);
+int pero_gather_rows_cf(const float* table, const int64_t* idx, int64_t n_lines, int64_t frames_per_line, int64_t K,
+                        int64_t C, float* out, pero_stream_t stream);
+
 /* ------------------------------------------------------------------ the GEMM core on its own (parity-test entry)
  * C[rows_a, rows_b] = A @ B^T through the same tcgen05 core every contraction of the path uses (bf16 operands with row
  * pitch `kd`, fp32 out [num_splits, rows_a, rows_b], one plane per contraction split).  variant: bit0 = CTA pairs

@@ -70,6 +70,9 @@ SIGNATURES = {
     "pero_peer_allreduce_sum_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "pero_peer_allreduce_min_i64": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "pero_peer_allreduce_emulate": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
+    "pero_proj_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
+    "pero_proj_forward": (c_int, [c_vp, c_i64, c_i64, c_int, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pero_gather_rows_cf": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "pero_gemm_tn_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
 }
 # present only in a dev build of the library (make DEV=1): bound when the symbol exists

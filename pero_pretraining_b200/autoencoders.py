@@ -48,6 +48,75 @@ class _QuantizeST(torch.autograd.Function):
         return g_out, None
 
 
+class _ProjectedQuantize(torch.autograd.Function):
+    """VQVAE.quantize (models/autoencoders.py:142-147) as one node: encoder 1x1 projection -> assign -> quantize ->
+    decoder 1x1 projection (+ EMA side effect).  Forward, all in libpero_b200: the encoder projection is a split-bf16
+    tensor-core GEMM whose epilogue writes the distance GEMM's operand directly (the projected NCHW tensor never exists);
+    the decoder projection is applied to the K codewords and the output is a row gather of that projected codebook
+    (W_d e[idx] + b_d == (E W_d^T + b_d)[idx]).  Backward: the straight-through estimator makes it two dense layers
+    back to back, d_tokens -> W_d -> W_e -> d_features; those are plain matrix products (torch.matmul, fp32)."""
+
+    @staticmethod
+    def forward(ctx, feats, w_enc, b_enc, w_dec, b_dec, vq):
+        n_lines, C = feats.shape[0], feats.shape[1]
+        frames = 1
+        for s in feats.shape[2:]:
+            frames *= s
+        N = n_lines * frames
+        x = feats.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        if not x.is_contiguous():
+            x = x.contiguous()
+        D, Cd = vq.embeddings_dim, w_dec.shape[0]
+        we, wd = w_enc.detach().reshape(D, C), w_dec.detach().reshape(Cd, D)
+        be = None if b_enc is None else b_enc.detach()
+        bd = None if b_dec is None else b_dec.detach()
+        cb = vq._prepared_codebook()
+        weight = vq.embedding.weight.data
+        update = vq.decay > 0.0 and vq.training
+        packed = torch.empty(N, dtype=torch.int64, device=x.device)
+        need_grad = any(ctx.needs_input_grad[:5])
+        x_rows, xb = ops.proj_forward(x, we, be, n_lines, frames, True, want_rows=update or need_grad, want_bf16=True, packed=packed)
+        if N > 0:
+            ops.vq_assign_bf16(xb, cb, packed)
+        idx, _ = ops.vq_unpack(packed)
+        # decoder projection of the (old) codebook, then the gather: the reference quantizes with the weights it had
+        # before this step's EMA update (:218-222 come before :225-237)
+        table, _ = ops.proj_forward(weight, wd, bd, vq.num_embeddings, 1, False)
+        tokens = ops.gather_rows_cf(table, idx, n_lines, frames).view((n_lines, Cd) + tuple(feats.shape[2:]))
+        if need_grad:
+            # the decoder projection's input as the reference's autograd sees it: x + (e[idx] - x)
+            q_st = ops.vq_gather_st(x_rows, idx, weight, n_lines, frames, False) if N > 0 else x_rows
+            ctx.save_for_backward(x, q_st, we, wd)
+        if update and (N > 0 or vq._dp_group is not None):
+            vq._ema_update(x_rows, idx, cb)
+            vq._codebook_tag = vq._weight_tag()
+        ctx.shapes = (feats.shape, w_enc.shape, w_dec.shape, feats.dtype, b_enc is not None, b_dec is not None)
+        ctx.mark_non_differentiable(idx)
+        return tokens, idx
+
+    @staticmethod
+    def backward(ctx, g_tokens, _g_idx):
+        x, q_st, we, wd = ctx.saved_tensors
+        f_shape, we_shape, wd_shape, f_dtype, has_be, has_bd = ctx.shapes
+        n_lines, C = f_shape[0], f_shape[1]
+        Cd, D = wd.shape
+        g = g_tokens.detach().float().reshape(n_lines, Cd, -1).permute(0, 2, 1).reshape(-1, Cd)        # rows [N, Cd]
+        xr = x.reshape(n_lines, C, -1).permute(0, 2, 1).reshape(-1, C)                                 # rows [N, C]
+        d_wd = (g.t() @ q_st).view(wd_shape) if ctx.needs_input_grad[3] else None
+        d_bd = g.sum(0) if (has_bd and ctx.needs_input_grad[4]) else None
+        dq = g @ wd                                             # straight-through: also the projected features' gradient
+        d_we = (dq.t() @ xr).view(we_shape) if ctx.needs_input_grad[1] else None
+        d_be = dq.sum(0) if (has_be and ctx.needs_input_grad[2]) else None
+        d_x = None
+        if ctx.needs_input_grad[0]:
+            d_x = (dq @ we).view(n_lines, -1, C).permute(0, 2, 1).reshape(f_shape)
+            if d_x.dtype != f_dtype:
+                d_x = d_x.to(f_dtype)
+        return d_x, d_we, d_be, d_wd, d_bd, None
+
+
 class _WeightedMse(torch.autograd.Function):
     """w * mse(tokens, features) with gradient to `features` only (w_features) and/or `tokens` (w_tokens)."""
 
@@ -138,22 +207,32 @@ class VectorQuantizer(torch.nn.Module):
         idx, _, x_rows = ops.vq_assign(x, cb, n_lines, frames, channels_first=True, want_rows=True)
         out = ops.vq_gather_st(x_rows, idx, weight, n_lines, frames, channels_first=True)
         if update:
-            # Every rank enters the exchange, also one whose shard of the batch is empty (it contributes zeros): the
-            # peers are waiting for it inside their exchange kernel.
-            if self._peer_range is not None:      # [K, D+1] SUM over ranks, in place in the peer-mapped range
-                if idx.numel() > 0:
-                    sums_counts = ops.vq_ema_accumulate(x_rows, idx, self.num_embeddings, out=self._peer_range.tensor)
-                else:
-                    sums_counts = self._peer_range.tensor.zero_()
-                self._peer_range.all_reduce_sum_()
-            else:
-                if idx.numel() > 0:
-                    sums_counts = ops.vq_ema_accumulate(x_rows, idx, self.num_embeddings)
-                else:
-                    sums_counts = torch.zeros(self.num_embeddings * (self.embeddings_dim + 1), dtype=torch.float32, device=x.device)
-                torch.distributed.all_reduce(sums_counts, group=self._dp_group)
-            ops.vq_ema_apply(sums_counts, self.ema_w.data, self.ema_cluster_size, weight, self.decay, self.epsilon, cb)
+            self._ema_update(x_rows, idx, cb)
         return out, idx
+
+    def _ema_update(self, x_rows, idx, cb):
+        """EMA codebook update (autoencoders.py:225-237) from the fp32 frame rows and their indices; data parallel: the
+        sums|counts are exchanged between accumulate and apply."""
+        weight = self.embedding.weight.data
+        if self._dp_group is None:
+            if idx.numel() == 0:
+                return
+            sums_counts = ops.vq_ema_accumulate(x_rows, idx, self.num_embeddings)
+        # Every rank enters the exchange, also one whose shard of the batch is empty (it contributes zeros): the
+        # peers are waiting for it inside their exchange kernel.
+        elif self._peer_range is not None:      # [K, D+1] SUM over ranks, in place in the peer-mapped range
+            if idx.numel() > 0:
+                sums_counts = ops.vq_ema_accumulate(x_rows, idx, self.num_embeddings, out=self._peer_range.tensor)
+            else:
+                sums_counts = self._peer_range.tensor.zero_()
+            self._peer_range.all_reduce_sum_()
+        else:
+            if idx.numel() > 0:
+                sums_counts = ops.vq_ema_accumulate(x_rows, idx, self.num_embeddings)
+            else:
+                sums_counts = torch.zeros(self.num_embeddings * (self.embeddings_dim + 1), dtype=torch.float32, device=x_rows.device)
+            torch.distributed.all_reduce(sums_counts, group=self._dp_group)
+        ops.vq_ema_apply(sums_counts, self.ema_w.data, self.ema_cluster_size, weight, self.decay, self.epsilon, cb)
 
     def _graphed_forward(self, x, cb, update, n_lines, frames):
         weight = self.embedding.weight.data
@@ -269,10 +348,17 @@ class VQVAE(torch.nn.Module):
     def decode(self, x):
         return self.decoder(x)
 
+    fuse_projections = True
+
     def quantize(self, x):
-        x = self.encoder_projection_layer(x)
+        """autoencoders.py:142-147.  With `fuse_projections` (default) the two 1x1 projections run inside libpero_b200
+        around the distance GEMM (see _ProjectedQuantize); False keeps them as torch.nn.Conv2d calls around self.vq."""
+        enc, dec = self.encoder_projection_layer, self.decoder_projection_layer
+        if self.fuse_projections and x.is_cuda and x.dim() == 4:
+            return _ProjectedQuantize.apply(x, enc.weight, enc.bias, dec.weight, dec.bias, self.vq)
+        x = enc(x)
         tokens, labels = self.vq(x)
-        return self.decoder_projection_layer(tokens), labels
+        return dec(tokens), labels
 
     def forward(self, images):
         features = self.encode(images)

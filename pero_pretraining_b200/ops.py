@@ -128,6 +128,48 @@ def vq_unpack(packed, want_dmin=False):
     return idx, dmin
 
 
+def vq_assign_bf16(x_bf16, codebook, packed, index_offset=0):
+    """The distance GEMM + arg-min on frames that already exist as bf16 rows [N, Dp] (pero_vq_assign_bf16): min-merges
+    the packed (distance, index) winners into `packed` (pre-set to "empty")."""
+    N = x_bf16.shape[0]
+    check(_lib.lib().pero_vq_assign_bf16(x_bf16.data_ptr(), int(N), codebook.K, codebook.D, codebook.blob.data_ptr(),
+                                         int(index_offset), packed.data_ptr(), _stream()), "pero_vq_assign_bf16")
+    return packed
+
+
+def proj_forward(x, weight, bias, n_lines, frames_per_line, channels_first, want_rows=True, want_bf16=False, packed=None):
+    """1x1 projection y[n, :] = weight x[n, :] + bias over the N = n_lines * frames_per_line frames (pero_proj_forward).
+    x: [n_lines, C, frames] fp32 (channels_first) or rows [N, C]; weight [D, C]; bias [D] or None.
+    Returns (rows fp32 [N, D] or None, bf16 rows [N, Dp] or None: the distance GEMM's operand); `packed` (int64 [N]) is
+    reset to "empty" on the way."""
+    L = _lib.lib()
+    x = _f32c(x, "x")
+    w = _f32c(weight, "weight")
+    b = None if bias is None else _f32c(bias, "bias")
+    D, C = int(w.shape[0]), int(w.shape[1])
+    N = int(n_lines) * int(frames_per_line)
+    dev = x.device
+    rows = torch.empty(N, D, dtype=torch.float32, device=dev) if want_rows else None
+    xb = torch.empty(N, (D + 63) // 64 * 64, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    if N == 0:
+        return rows, xb
+    wsb = L.pero_proj_workspace_bytes(N, C, D)
+    ws = _ws(wsb, dev)
+    check(L.pero_proj_forward(x.data_ptr(), int(n_lines), int(frames_per_line), 1 if channels_first else 0, C, w.data_ptr(), _p(b), D,
+                              _p(rows), _p(xb), _p(packed), ws.data_ptr(), wsb, _stream()), "pero_proj_forward")
+    return rows, xb
+
+
+def gather_rows_cf(table, idx, n_lines, frames_per_line):
+    """out[l, c, t] = table[idx[l * frames + t], c] as a channels-first tensor [n_lines, C, frames] (pero_gather_rows_cf)."""
+    t = _f32c(table, "table")
+    K, C = int(t.shape[0]), int(t.shape[1])
+    out = torch.empty(int(n_lines), C, int(frames_per_line), dtype=torch.float32, device=t.device)
+    check(_lib.lib().pero_gather_rows_cf(t.data_ptr(), idx.data_ptr(), int(n_lines), int(frames_per_line), K, C, out.data_ptr(),
+                                         _stream()), "pero_gather_rows_cf")
+    return out
+
+
 def vq_gather_st(x_rows, idx, weight, n_lines, frames_per_line, channels_first):
     """out = x + (weight[idx] - x), channels-first [n_lines, D, frames] or rows [N, D]."""
     w = _f32c(weight, "weight")
