@@ -19,6 +19,11 @@ and head gradients|loss reduced in place inside the step by the library's peer-m
 import argparse
 import json
 import os
+
+# The step is captured as a CUDA graph with up to nine parallel branches (three compute chains, operand preparation, the
+# loss read-out and, data parallel, three exchange chains): with the default of 8 hardware queues two branches can share
+# one and serialise.  Set before CUDA is initialised; an explicit setting of the caller wins.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading

@@ -34,6 +34,11 @@
 #pragma once
 #include "ptx.cuh"
 
+// 1: one elected lane of the MMA warp walks the whole issue loop; 0: the warp walks it and elects a lane per k-block
+#ifndef PERO_MMA_SINGLE_LANE
+#define PERO_MMA_SINGLE_LANE 0
+#endif
+
 namespace pero {
 
 constexpr int kBlockM = 128;        // accumulator rows per CTA (TMEM lanes)
@@ -343,7 +348,8 @@ __device__ __forceinline__ void gemm_tn_body(const CUtensorMap& tmap_a, const CU
         // (Measured, round 2: handing alternate units to a second issuing warp that has already passed the waits of
         // the next unit does not shorten a unit -- the 16 MMAs of a 256 x 256 x 256 unit take ~2700 cycles back to
         // back either way -- so the single issuer stays.)
-        if (leader && u0 < u1) {
+        constexpr bool single = PERO_MMA_SINGLE_LANE != 0;
+        if (leader && u0 < u1 && (single ? elect_one_sync() : 1u)) {
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCtaGroup, kBlockN, kAMn, kBMn);
             int stage = 0; uint32_t phase = 0;
             int prev_rb = -1, rbi = -1, it = 0;
@@ -357,15 +363,15 @@ __device__ __forceinline__ void gemm_tn_body(const CUtensorMap& tmap_a, const CU
                 const int buf = it & 1;
                 const int aset = (kASets == 2) ? (rbi & 1) : 0;
                 const int ause = (kASets == 2) ? (rbi >> 1) : rbi;
-                stamp(sh, tl && lane == 0, it, 0);
+                stamp(sh, tl && (single || lane == 0), it, 0);
                 mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
-                stamp(sh, tl && lane == 0, it, 1);
+                stamp(sh, tl && (single || lane == 0), it, 1);
                 const uint32_t tmem_d = tmem_base + buf * kBlockN;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (kAResident && new_rb) mbar_wait(afull_bar(aset * sh.num_kb + kb), ause & 1);
                     if (!ready) mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    if (kb == kb0) stamp(sh, tl && lane == 0, it, 2);
+                    if (kb == kb0) stamp(sh, tl && (single || lane == 0), it, 2);
                     int nstage = stage + 1; uint32_t nphase = phase;
                     if (nstage == stages) { nstage = 0; nphase ^= 1; }
                     // probe only if another k-block follows: a probe of a phase that never completes would stall
@@ -378,7 +384,7 @@ __device__ __forceinline__ void gemm_tn_body(const CUtensorMap& tmap_a, const CU
                     // address-field step per UMMA_K (16 contraction elements): K-major +32 B inside the 128-byte
                     // swizzle row (+2 in the >>4 field); MN-major +16 k-rows = two 1024-byte atoms (+128)
                     constexpr uint64_t kAStep = kAMn ? (2048u >> 4) : 2u, kBStep = kBMn ? (2048u >> 4) : 2u;
-                    if (elect_one_sync()) {
+                    if (single || elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                             umma_bf16<kCtaGroup>(tmem_d, adesc + kAStep * k, bdesc + kBStep * k, idesc,
@@ -388,7 +394,7 @@ __device__ __forceinline__ void gemm_tn_body(const CUtensorMap& tmap_a, const CU
                         if (kAResident && last_of_rb) umma_commit<kCtaGroup>(aempty_bar(aset * sh.num_kb + kb));
                         if (kb + 1 == kb1) { umma_commit<kCtaGroup>(tfull_bar(buf)); stamp(sh, tl, it, 3); }
                     }
-                    __syncwarp();
+                    if (!single) __syncwarp();
                     stage = nstage; phase = nphase;
                 }
             }

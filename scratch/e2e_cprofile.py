@@ -10,7 +10,9 @@ with torch.no_grad():
     vq.embedding.weight.copy_(batch["weight"]); vq.ema_w.copy_(batch["weight"]); vq.ema_cluster_size.fill_(1.0)
     head.linear.weight.copy_(batch["W"]); head.linear.bias.copy_(batch["b"])
 gq = batch["gq"].to(dev); mask = batch["mask"]
-xd, hd = batch["x"].to(dev), batch["h"].to(dev)
+xd, hd = batch["x"].to(dev), batch["h"].to(dev).bfloat16()
+vq.enable_cuda_graph()
+torch.autograd.set_multithreading_enabled(False)
 def step():
     x = xd.detach().requires_grad_(True); h = hd.detach().requires_grad_(True)
     q, idx = vq(x)
