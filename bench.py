@@ -740,6 +740,42 @@ class CeChain:
         return self.out
 
 
+def vqvae_quantize_leg(dev, flush, steps, lines=64, frames=128, C=256, K=8192, D=256):
+    import copy
+    from pero_pretraining_b200 import VQVAE
+
+    class _Pass(torch.nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.out_channels = self.base_channels = c
+
+        def forward(self, x):
+            return x
+
+    torch.manual_seed(1240)
+    fused = VQVAE(_Pass(C), _Pass(C), K, D, 0.25, 0.99).to(dev).eval()
+    plain = copy.deepcopy(fused)
+    fused.fuse_projections, plain.fuse_projections = True, False
+    feats = torch.randn(lines, C, 1, frames, device=dev)
+    res = {}
+    for name, m in (("fused", fused), ("conv2d", plain)):
+        def step(m=m):
+            with torch.no_grad():
+                return m.quantize(feats)
+        ms, ms_min, launch, graph = timed_loop(step, steps, 3, flush, False)
+        res[name] = {"ms_per_step": ms, "ms_min": ms_min, "launch": launch, "frames_per_s": lines * frames / (ms * 1e-3)}
+        graph = None
+    with torch.no_grad():
+        la, lb = fused.quantize(feats)[1], plain.quantize(feats)[1]
+    N = lines * frames
+    fl = 2.0 * N * (C * D + K * D)                                 # encoder projection + assign
+    return {"workload": f"VQVAE.quantize, eval (label production: the decoder-projected codebook is computed once per codebook version): {lines} lines x {frames} frames, {C}->{D} projection, {K}x{D} codebook, {D}->{C} projection",
+            "fused": res["fused"], "conv2d_projections": res["conv2d"],
+            "speedup": res["conv2d"]["ms_per_step"] / res["fused"]["ms_per_step"],
+            "labels_equal_fraction": float((la == lb).float().mean()),
+            "fused_tflops_algorithmic": fl / (res["fused"]["ms_per_step"] * 1e-3) / 1e12}
+
+
 def configs_legs(dev, dp, rank, world, flush, steps):
     """BASELINE configs[2..4] measured with the same timing method as the headline workload:
       c3  masked CE over 4096 labels, Dh 512, 32 lines x 128 frames PER GPU, bf16 hidden states, data parallel (weak)
@@ -813,6 +849,12 @@ def configs_legs(dev, dp, rank, world, flush, steps):
                  "api": "ShardedCodebook.assign (frame preparation fp32 -> bf16 inside the timed region)"}
     graph = None
     del sc, X
+    torch.cuda.empty_cache()
+    # ---- VQVAE.quantize with its two 1x1 projections (models/autoencoders.py:142-147), label production
+    # (eval, no grad) at the configs[1] quantizer behind 256-channel projections: fused in libpero_b200 against the same
+    # module with torch.nn.Conv2d (cuDNN) projections around the VectorQuantizer.  Single GPU only.
+    if not dp:
+        out["vqvae_quantize"] = vqvae_quantize_leg(dev, flush, steps)
     torch.cuda.empty_cache()
     return out
 

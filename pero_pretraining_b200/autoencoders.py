@@ -57,7 +57,7 @@ class _ProjectedQuantize(torch.autograd.Function):
     back to back, d_tokens -> W_d -> W_e -> d_features; those are plain matrix products (torch.matmul, fp32)."""
 
     @staticmethod
-    def forward(ctx, feats, w_enc, b_enc, w_dec, b_dec, vq):
+    def forward(ctx, feats, w_enc, b_enc, w_dec, b_dec, vq, owner=None):
         n_lines, C = feats.shape[0], feats.shape[1]
         frames = 1
         for s in feats.shape[2:]:
@@ -76,14 +76,19 @@ class _ProjectedQuantize(torch.autograd.Function):
         weight = vq.embedding.weight.data
         update = vq.decay > 0.0 and vq.training
         packed = torch.empty(N, dtype=torch.int64, device=x.device)
-        need_grad = any(ctx.needs_input_grad[:5])
+        # (needs_input_grad reports requires_grad of the parameters also under torch.no_grad(): ask the owner's flag)
+        need_grad = any(ctx.needs_input_grad[:5]) and (owner is None or owner._grad_enabled)
         x_rows, xb = ops.proj_forward(x, we, be, n_lines, frames, True, want_rows=update or need_grad, want_bf16=True, packed=packed)
         if N > 0:
             ops.vq_assign_bf16(xb, cb, packed)
         idx, _ = ops.vq_unpack(packed)
         # decoder projection of the (old) codebook, then the gather: the reference quantizes with the weights it had
         # before this step's EMA update (:218-222 come before :225-237)
-        table, _ = ops.proj_forward(weight, wd, bd, vq.num_embeddings, 1, False)
+        table = owner._projected_codebook(weight, w_dec, b_dec) if owner is not None else None
+        if table is None:
+            table, _ = ops.proj_forward(weight, wd, bd, vq.num_embeddings, 1, False)
+            if owner is not None:
+                owner._store_projected_codebook(table, weight, w_dec, b_dec)
         tokens = ops.gather_rows_cf(table, idx, n_lines, frames).view((n_lines, Cd) + tuple(feats.shape[2:]))
         if need_grad:
             # the decoder projection's input as the reference's autograd sees it: x + (e[idx] - x)
@@ -114,7 +119,7 @@ class _ProjectedQuantize(torch.autograd.Function):
             d_x = (dq @ we).view(n_lines, -1, C).permute(0, 2, 1).reshape(f_shape)
             if d_x.dtype != f_dtype:
                 d_x = d_x.to(f_dtype)
-        return d_x, d_we, d_be, d_wd, d_bd, None
+        return d_x, d_we, d_be, d_wd, d_bd, None, None
 
 
 class _WeightedMse(torch.autograd.Function):
@@ -348,14 +353,46 @@ class VQVAE(torch.nn.Module):
     def decode(self, x):
         return self.decoder(x)
 
-    fuse_projections = True
+    # 'auto' (default): the fused path where it is the faster one -- label production / evaluation (no gradient: the
+    # decoder-projected codebook is computed once per codebook version, the projected NCHW tensor never exists) -- and the
+    # torch.nn.Conv2d projections around self.vq in training, where cuDNN's TF32 convolutions beat the fp32-grade
+    # three-product GEMM (measured).  True / False force one path.
+    fuse_projections = 'auto'
+    _grad_enabled = True
+    _table = None
+    _table_tag = None
+
+    def _table_key(self, weight, w_dec, b_dec):
+        return (weight.data_ptr(), weight._version, self.vq._codebook_tag, w_dec.data_ptr(), w_dec._version,
+                None if b_dec is None else (b_dec.data_ptr(), b_dec._version))
+
+    def _projected_codebook(self, weight, w_dec, b_dec):
+        """decoder_projection_layer applied to the K codewords ([K, Cd] fp32), kept while neither the codebook nor the
+        projection has changed (a label-production loop projects the codebook once).  invalidate_projections() after a
+        write through `.data`."""
+        if self._table is not None and self._table_tag == self._table_key(self.vq.embedding.weight, w_dec, b_dec):
+            return self._table
+        return None
+
+    def _store_projected_codebook(self, table, weight, w_dec, b_dec):
+        if self.training:            # the EMA update behind this forward changes the codebook: nothing to keep
+            self._table = self._table_tag = None
+            return
+        self._table, self._table_tag = table, self._table_key(self.vq.embedding.weight, w_dec, b_dec)
+
+    def invalidate_projections(self):
+        self._table = self._table_tag = None
+        self.vq.invalidate_codebook()
 
     def quantize(self, x):
-        """autoencoders.py:142-147.  With `fuse_projections` (default) the two 1x1 projections run inside libpero_b200
-        around the distance GEMM (see _ProjectedQuantize); False keeps them as torch.nn.Conv2d calls around self.vq."""
+        """autoencoders.py:142-147.  Fused: the two 1x1 projections run inside libpero_b200 around the distance GEMM (see
+        _ProjectedQuantize); otherwise they are torch.nn.Conv2d calls around self.vq."""
         enc, dec = self.encoder_projection_layer, self.decoder_projection_layer
-        if self.fuse_projections and x.is_cuda and x.dim() == 4:
-            return _ProjectedQuantize.apply(x, enc.weight, enc.bias, dec.weight, dec.bias, self.vq)
+        grad = torch.is_grad_enabled() and (x.requires_grad or enc.weight.requires_grad or dec.weight.requires_grad)
+        fuse = (not grad) if self.fuse_projections == 'auto' else bool(self.fuse_projections)
+        if fuse and x.is_cuda and x.dim() == 4:
+            self._grad_enabled = grad
+            return _ProjectedQuantize.apply(x, enc.weight, enc.bias, dec.weight, dec.bias, self.vq, self)
         x = enc(x)
         tokens, labels = self.vq(x)
         return dec(tokens), labels

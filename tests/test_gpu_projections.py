@@ -107,8 +107,7 @@ def test_fused_quantize_matches_conv_modules(cuda_dev, n_lines, H, W, C, K, D, d
         rows = (target - a.encoder_projection_layer.bias.double()) @ torch.linalg.pinv(we).t()
         feats = rows.float().view(n_lines, H, W, C).permute(0, 3, 1, 2).contiguous()
     b = copy.deepcopy(a)
-    b.fuse_projections = False
-    assert a.fuse_projections
+    a.fuse_projections, b.fuse_projections = True, False
     g_out = torch.randn(n_lines, C, H, W, device=cuda_dev)
     prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
@@ -146,13 +145,38 @@ def test_fused_quantize_matches_conv_modules(cuda_dev, n_lines, H, W, C, K, D, d
         # (a cold-start EMA step divides by cluster sizes near epsilon: codewords reach 1e2, hence the absolute term)
         wa, wb = a.vq.embedding.weight.detach(), b.vq.embedding.weight.detach()
         assert float((wa - wb).abs().max()) <= 1e-4 * float(wb.abs().max()), "codebook after the EMA update"
-    # eval: labels only (label production), no EMA update
-    a.eval()
+    # eval ('auto' takes the fused path when no gradient is wanted): labels only (label production), no EMA update, and the
+    # decoder-projected codebook is computed once and kept until the codebook or the projection changes
+    a.fuse_projections = 'auto'
+    a.eval(); b.eval()
+    b.load_state_dict(a.state_dict())
     w0 = a.vq.embedding.weight.detach().clone()
     with torch.no_grad():
         t2, l2 = a.quantize(feats)
+        table = a._table
+        assert table is not None and tuple(table.shape) == (K, C)
+        t3, l3 = a.quantize(feats)
+        assert a._table is table and torch.equal(t3, t2) and torch.equal(l3, l2)
+        torch.backends.cudnn.allow_tf32 = False                # the comparison path's convolutions in fp32
+        try:
+            tb2, lb2 = b.quantize(feats)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev[0]
+        a.decoder_projection_layer.bias.add_(1.0)             # in-place update bumps the version: the table is rebuilt
+        t4, _ = a.quantize(feats)
+        assert a._table is not table
     assert torch.equal(a.vq.embedding.weight.detach(), w0)
     assert l2.shape == la.shape and t2.shape == ta.shape
+    same = (l2 == lb2)
+    assert float(same.float().mean()) >= 0.998
+    sel = same.view(n_lines, 1, H, W).expand_as(t2)
+    assert float((t2 - tb2)[sel].abs().max()) <= 1e-4 * float(tb2.abs().max())
+    assert float((t4 - t2 - 1.0).abs().max()) <= 1e-5 * (1.0 + float(t2.abs().max()))
+    # with gradients wanted, 'auto' keeps the torch.nn.Conv2d projections (cuDNN) around the quantizer
+    a.train()
+    f = feats.clone().requires_grad_(True)
+    tok, _ = a.quantize(f)
+    assert tok.grad_fn is not None and "ProjectedQuantize" not in type(tok.grad_fn).__name__
 
 
 def test_proj_entry_points_stay_inside_their_buffers(cuda_dev):

@@ -130,9 +130,11 @@ def test_calculate_loss_golden(cuda_dev):
         np.testing.assert_allclose(gt, g[f"{tag}_g_tokens"], rtol=1e-5, atol=1e-8)
 
 
-def test_vqvae_forward_golden(cuda_dev):
+@pytest.mark.parametrize("fuse", ["auto", True])
+def test_vqvae_forward_golden(cuda_dev, fuse):
     """VQVAE.forward with stand-in conv encoder/decoder: dict keys, the projection/loss wiring
-    (calculate_loss(tokens, features) across the 1x1 convs) and counts."""
+    (calculate_loss(tokens, features) across the 1x1 convs) and counts; fuse=True: the 1x1 projections inside
+    libpero_b200, 'auto': torch.nn.Conv2d in training."""
     import sys, os
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
     from pero_pretraining_b200 import VQVAE
@@ -161,6 +163,7 @@ def test_vqvae_forward_golden(cuda_dev):
     m = VQVAE(Enc(), Dec(), num_embeddings=32, embeddings_dim=8)
     m.load_state_dict({k[len("state_"):]: T(v) for k, v in g.items() if k.startswith("state_")})
     m = m.to(cuda_dev).train()
+    m.fuse_projections = fuse
     prev = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
