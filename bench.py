@@ -435,7 +435,7 @@ def dump_timeline(run, path):
             f.write(f"{e.time_range.start - t0:10.1f} {e.time_range.end - e.time_range.start:8.1f} {e.name[:110]}\n")
 
 
-def e2e_leg(batch, dev, dp, steps, warm, repeats=3, loss_read="pipelined", single_thread_autograd=True):
+def e2e_leg(batch, dev, dp, steps, warm, repeats=5, loss_read="pipelined", single_thread_autograd=True):
     """Public module API, host inputs: per step H2D of x (fp32) / h (bf16: what --bfloat16 training hands the head,
     masked_pretraining/trainer.py:57-59) / mask rows from pinned memory, D2H of the loss.  `repeats` timed loops of
     `steps` steps each; returns (median s/step, min s/step, all, h2d bytes, d2h bytes, last loss).
@@ -486,6 +486,7 @@ def e2e_leg(batch, dev, dp, steps, warm, repeats=3, loss_read="pipelined", singl
     stage(0)
     labels_shape = (c["lines"], c["frames"])
     pipelined = loss_read == "pipelined"
+    one = torch.ones((), dtype=torch.float32, device=dev)
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -498,10 +499,14 @@ def e2e_leg(batch, dev, dp, steps, warm, repeats=3, loss_read="pipelined", singl
         x = bufs[i & 1][0].detach().requires_grad_(True)
         h = bufs[i & 1][1].detach().requires_grad_(True)
         q, idx = vq(x)
-        loss = vq.calculate_loss(q, x) + head.masked_loss(h, idx.view(labels_shape), mask, None, group)
+        loss_q = vq.calculate_loss(q, x)
+        loss_h = head.masked_loss(h, idx.view(labels_shape), mask, None, group)
         head.linear.weight.grad = None
         head.linear.bias.grad = None
-        torch.autograd.backward([loss, q], [None, gq])
+        # d(loss_q + loss_h): the two losses are differentiated as two roots with a preallocated unit gradient (no
+        # AddBackward node, no ones_like per step); their sum, the step's result, is formed on the detached values
+        torch.autograd.backward([loss_q, loss_h, q], [one, one, gq])
+        loss = loss_q.detach() + loss_h.detach()
         consumed[i & 1].record(main)
         if not pipelined:
             return float(loss.item())                  # D2H read of the step's result
@@ -520,7 +525,7 @@ def e2e_leg(batch, dev, dp, steps, warm, repeats=3, loss_read="pipelined", singl
     prev_mt = torch.autograd.is_multithreading_enabled()
     if single_thread_autograd:
         torch.autograd.set_multithreading_enabled(False)
-    for _ in range(warm):
+    for _ in range(max(warm, 10)):            # allocator pools, pinned staging ring and graph caches settle in the first steps
         step()
     times = []
     for _ in range(repeats):

@@ -22,6 +22,7 @@ class _RowStager:
     def __init__(self, device, ring=8, capacity=8192):
         self.device = device
         self.host = [torch.empty(capacity, dtype=torch.int32).pin_memory() for _ in range(ring)]
+        self.views = [h.numpy() for h in self.host]          # numpy views of the pinned buffers, made once
         self.events = [torch.cuda.Event() for _ in range(ring)]
         self.used = [False] * ring
         self.next = 0
@@ -35,10 +36,11 @@ class _RowStager:
         if self.host[i].numel() < n:
             cap = int(n * 1.5) + 16
             self.host[i] = torch.empty(cap, dtype=torch.int32).pin_memory()
-        self.host[i].numpy()[:n] = rows
+            self.views[i] = self.host[i].numpy()
+        self.views[i][:n] = rows
         # the device copy is a fresh tensor (it is saved for backward and must not be recycled with the ring)
         out = torch.empty(n, dtype=torch.int32, device=self.device)
-        out.copy_(self.host[i][:n], non_blocking=True)
+        out.copy_(self.host[i].narrow(0, 0, n), non_blocking=True)
         self.events[i].record(torch.cuda.current_stream(self.device))
         self.used[i] = True
         return out

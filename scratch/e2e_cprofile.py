@@ -29,4 +29,4 @@ print("us/step without profiler:", (time.perf_counter() - t0) / 50 * 1e6)
 pr = cProfile.Profile(); pr.enable()
 for _ in range(50): step()
 pr.disable()
-st = pstats.Stats(pr); st.sort_stats("tottime").print_stats(45)
+st = pstats.Stats(pr); st.sort_stats("cumulative").print_stats(70)
