@@ -397,6 +397,27 @@ class VQVAE(torch.nn.Module):
         tokens, labels = self.vq(x)
         return dec(tokens), labels
 
+    def labels(self, x):
+        """Labels only (what scripts/produce_vqvae_labels.py:37 keeps of quantize()): encoder projection -> nearest
+        codeword, [n*h*w] int64.  No quantized output, no decoder projection, no EMA update, no gradient."""
+        enc = self.encoder_projection_layer
+        if not (x.is_cuda and x.dim() == 4):
+            return self.quantize(x)[1]
+        with torch.no_grad():
+            n_lines, C = x.shape[0], x.shape[1]
+            frames = x.shape[2] * x.shape[3]
+            N = n_lines * frames
+            xf = x.detach()
+            if xf.dtype != torch.float32:
+                xf = xf.float()
+            packed = torch.empty(N, dtype=torch.int64, device=x.device)
+            _, xb = ops.proj_forward(xf.contiguous(), enc.weight.detach().reshape(self.embeddings_dim, C),
+                                     None if enc.bias is None else enc.bias.detach(), n_lines, frames, True, want_rows=False,
+                                     want_bf16=True, packed=packed)
+            if N > 0:
+                ops.vq_assign_bf16(xb, self.vq._prepared_codebook(), packed)
+            return ops.vq_unpack(packed)[0]
+
     def forward(self, images):
         features = self.encode(images)
         tokens, labels = self.quantize(features)

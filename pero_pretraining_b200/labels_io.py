@@ -122,8 +122,15 @@ def compute_labels(model, batches):
     data = {}
     with torch.no_grad():
         for batch in batches:
-            tokens, labels = model.quantize(model.encode(batch["images"]))
-            N, _, _, T = tokens.shape
+            feats = model.encode(batch["images"])
+            if hasattr(model, "labels"):          # labels only: no quantized output, no decoder projection
+                labels = model.labels(feats)
+                N, T = feats.shape[0], feats.shape[3]              # (the encoders of the reference emit height 1)
+                if labels.numel() != N * T:
+                    T = labels.numel() // N
+            else:
+                tokens, labels = model.quantize(feats)
+                N, _, _, T = tokens.shape
             labels = labels.reshape(N, T).cpu().numpy()
             for line_id, line_image_mask, line_labels in zip(batch["ids"], batch["image_masks"], labels):
                 data[line_id] = line_labels[np.asarray(line_image_mask) == 1].tolist()

@@ -204,3 +204,28 @@ def test_proj_entry_points_stay_inside_their_buffers(cuda_dev):
         g.check(f"projection entry points {n_lines}x{frames} C={C} D={D}")
         assert L.pero_proj_forward(x.data_ptr(), n_lines, frames, cf, C, w.data_ptr(), b.data_ptr(), D, rows.data_ptr(),
                                    xb.data_ptr(), packed.data_ptr(), ws.data_ptr(), wsb - 1, _s()) == -3      # PERO_ERR_WORKSPACE
+
+
+def test_label_production_matches_quantize(cuda_dev):
+    """compute_labels (scripts/produce_vqvae_labels.py:25-44) through VQVAE.labels -- encoder projection + assignment only --
+    gives the labels VQVAE.quantize gives, filtered by the image masks."""
+    from pero_pretraining_b200 import VQVAE, compute_labels
+    torch.manual_seed(3)
+    m = VQVAE(_Enc(24), _Dec(24), 64, 16, 0.25, 0.99).to(cuda_dev).eval()
+    batches = []
+    for b in range(3):
+        images = torch.randn(4, 24, 1, 37, device=cuda_dev)
+        masks = [(np.arange(37) < 30 + i).astype(int) for i in range(4)]
+        batches.append({"images": images, "ids": [f"line{b}_{i}" for i in range(4)], "image_masks": masks})
+    data = compute_labels(m, batches)
+    assert len(data) == 12
+    with torch.no_grad():
+        for batch in batches:
+            _, ref = m.quantize(batch["images"])
+            ref = ref.reshape(4, 37).cpu().numpy()
+            for i, line_id in enumerate(batch["ids"]):
+                assert data[line_id] == ref[i][batch["image_masks"][i] == 1].tolist()
+    w0 = m.vq.embedding.weight.detach().clone()
+    m.train()
+    lab = m.labels(batches[0]["images"])                        # never updates the EMA state, also in training mode
+    assert torch.equal(m.vq.embedding.weight.detach(), w0) and lab.dtype == torch.int64 and lab.shape == (4 * 37,)
