@@ -251,7 +251,8 @@ class DeviceStep:
         # offers, so that its pending CTAs are placed ahead of the EMA / commitment kernels whenever SM slots free up
         self.s_ce = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PERO_CE_PRIO", "-5")))
         self.s_prep = torch.cuda.Stream(device=dev, priority=0)
-        self.s_comm = torch.cuda.Stream(device=dev, priority=-1)
+        # the gradient exchange is the data-parallel tail: its CTAs must not queue behind pending GEMM CTAs of the CE chain
+        self.s_comm = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PERO_COMM_PRIO", "-5")))
         # Data-parallel exchange ranges (EMA sums|counts and d_W|d_b|loss_sum) live in a peer-mapped buffer and
         # are reduced in place by the library's own NVLink/NVSwitch kernel.
         self.peer = self.ema_x = self.grad_x = None
