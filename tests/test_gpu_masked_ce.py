@@ -65,6 +65,8 @@ def test_fused_head_ce_golden(cuda_dev):
     (5, 37, 96, 1000, 0.5, torch.float32),         # ragged: V, Dh, M not multiples of any tile
     (2, 9, 64, 300, 1.0, torch.float32),           # every frame masked
     (3, 50, 512, 257, 0.02, torch.float32),        # a handful of masked frames
+    (4, 64, 768, 1000, 0.3, torch.float32),        # model_dim 768: both operands stream through the ring (no resident A)
+    (2, 64, 1024, 520, 0.5, torch.bfloat16),       # model_dim 1024
 ])
 def test_fused_head_ce_vs_oracle(cuda_dev, Nl, T_, Dh, V, p, dtype):
     rng = np.random.default_rng(Nl * 1000 + V)
