@@ -1022,20 +1022,27 @@ def our_arm(args):
     if not args.skip_e2e:
         st_autograd = os.environ.get("PERO_E2E_ST", "1") != "0"
         loss_read = os.environ.get("PERO_E2E_LOSS", "pipelined")
-        # the same loop with a blocking `loss.item()` per step, reported beside the headline for comparison
-        sync_s, sync_min, _, _, _, sync_loss = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup), loss_read="sync",
-                                                       single_thread_autograd=st_autograd)
-        s_per_step, s_min, s_all, h2d, d2h, e2e_loss = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup),
-                                                               loss_read=loss_read, single_thread_autograd=st_autograd)
+        # Two loops that differ only in how the step's loss reaches the host (both read EVERY step's loss inside the timed
+        # region): a blocking `loss.item()` per step, and an asynchronous D2H into pinned memory that the host reads one
+        # step later.  Which is faster depends on the host (on a loaded box the blocking loop wins); both medians are
+        # reported and the headline is the faster of the two (all values are maxima over the ranks, so every rank picks
+        # the same one).
+        legs = {}
+        for mode in ("sync", "pipelined") if loss_read == "pipelined" else (loss_read,):
+            legs[mode] = e2e_leg(batch, dev, dp, args.steps, max(3, args.warmup), loss_read=mode, single_thread_autograd=st_autograd)
+        best = min(legs, key=lambda m: legs[m][0])
+        s_per_step, s_min, s_all, h2d, d2h, e2e_loss = legs[best]
+        describe = {"pipelined": ("every step's loss copied D2H into pinned memory asynchronously and read by the host one step "
+                                  "later, the last one before the closing synchronize"),
+                    "sync": "blocking loss.item() at the end of every step"}
         e2e = {"value": m_total / s_per_step, "unit": "masked frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": s_per_step * 1e3, "ms_per_step_min": s_min * 1e3, "ms_per_step_all": [t * 1e3 for t in s_all],
-               "statistic": f"median of {len(s_all)} timed loops of {args.steps} steps",
-               "loss_read": ("every step's loss copied D2H into pinned memory asynchronously and read by the host one step "
-                             "later, the last one before the closing synchronize" if loss_read == "pipelined" else
-                             "blocking loss.item() at the end of every step"),
-               "ms_per_step_blocking_loss_read": sync_s * 1e3, "ms_per_step_blocking_loss_read_min": sync_min * 1e3,
+               "statistic": f"median of {len(s_all)} timed loops of {args.steps} steps; the faster of the loss read-back modes measured",
+               "loss_read": describe[best],
+               "loss_read_modes": {m: {"how": describe[m], "ms_per_step": v[0] * 1e3, "ms_per_step_min": v[1] * 1e3,
+                                       "ms_per_step_all": [t * 1e3 for t in v[2]], "last_loss": v[5]} for m, v in legs.items()},
                "autograd": "single-threaded (torch.autograd.set_multithreading_enabled(False))" if st_autograd else "default",
-               "last_loss": e2e_loss, "last_loss_blocking": sync_loss,
+               "last_loss": e2e_loss,
                "inputs": "x fp32 [64,256,1,128] + hidden states bf16 [64,128,512] + masked-row list, pinned host memory",
                "api": ("VectorQuantizer.forward (enable_cuda_graph" + (", data parallel" if dp else "") +
                        ") / calculate_loss + LinearHead.masked_loss + backward")}
