@@ -15,6 +15,15 @@ One "step" = one pass of the hot path over one synthetic batch (BASELINE.json co
 `cpu_baseline`: the oracle port of the reference path on this box's host cores (rank 0, N=1 only).
 Multi-GPU: weak scaling, batch-sharded (every rank owns 64 lines), codebook/head replicated, EMA sums|counts
 and head gradients|loss reduced in place inside the step by the library's peer-memory kernel (NVSwitch multimem).
+
+A/B knobs of THIS script (environment variables; the defaults are the measured optimum, profiles/r2_notes.md; the
+library itself reads no environment variable in its production build):
+  PERO_CE_PRIO (-5) / PERO_EMA_PRIO (-2) / PERO_COMMIT_PRIO (0) / PERO_COMM_PRIO (-5)   stream priorities of the masked-CE
+      chain, the EMA chain, the quantize + commitment chain and the gradient-exchange stream
+  PERO_STEP_GATHER_SIDE (1), PERO_STEP_COMMIT_SIDE (1), PERO_STEP_PREP_LOW (1), PERO_STEP_SPLIT_EMA (1 on one GPU)
+      which chain of the step runs on which stream
+  PERO_DP_CHUNKS (1)   label ranges of the data-parallel head backward;  PERO_PEER_BLOCKS (24), PERO_PEER_MULTICAST (auto)
+  PERO_E2E_LOSS (pipelined | sync), PERO_E2E_ST (1: single-threaded autograd), PERO_E2E_GRAPH (1), PERO_E2E_BF16 (1)
 """
 import argparse
 import json
