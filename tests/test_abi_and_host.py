@@ -87,6 +87,25 @@ def test_python_mirror_fails_loudly_without_gpu():
         LinearHead(4, 8).masked_loss(torch.randn(1, 3, 4), torch.zeros(1, 3, dtype=torch.long), np.ones((1, 3), dtype=int))
     with pytest.raises(PeroError):
         MaskedCrossEntropyLoss()(torch.randn(1, 3, 8), torch.zeros(1, 3, dtype=torch.long), torch.ones(1, 3, dtype=torch.long))
+    # VQVAE.quantize / labels: whichever path 'auto' takes, there is no CPU quantizer behind it
+    from pero_pretraining_b200 import VQVAE, ops
+
+    class _Pass(torch.nn.Module):
+        out_channels = base_channels = 6
+
+        def forward(self, x):
+            return x
+
+    m = VQVAE(_Pass(), _Pass(), 8, 4)
+    assert m.fuse_projections == 'auto'
+    for fuse in ('auto', True, False):
+        m.fuse_projections = fuse
+        with pytest.raises(PeroError):
+            m.quantize(torch.randn(1, 6, 1, 3))
+        with pytest.raises(PeroError), torch.no_grad():
+            m.labels(torch.randn(1, 6, 1, 3))
+    with pytest.raises((PeroError, TypeError)):
+        ops.proj_forward(torch.randn(3, 6), torch.randn(4, 6), None, 3, 1, False)
 
 
 def test_product_package_never_imports_the_oracle():
