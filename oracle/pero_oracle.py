@@ -94,6 +94,24 @@ def vq_calculate_loss_grads(tokens, features, commitment_cost, decay, grad_out=1
     return g_tokens, g_features
 
 
+def conv1x1(x, weight, bias):
+    """torch.nn.Conv2d(C_in, C_out, 1) as the per-frame affine map it is: x [Nl, C, H, W], weight [C_out, C_in(, 1, 1)],
+    bias [C_out] -> [Nl, C_out, H, W].  models/autoencoders.py:114-115."""
+    w = weight.reshape(weight.shape[0], -1)
+    y = torch.matmul(x.permute(0, 2, 3, 1), w.t())
+    if bias is not None:
+        y = y + bias
+    return y.permute(0, 3, 1, 2).contiguous()
+
+
+def vqvae_quantize(features, enc_w, enc_b, dec_w, dec_b, weight, indices_override=None):
+    """VQVAE.quantize in eval mode, models/autoencoders.py:142-147: encoder projection -> VectorQuantizer.forward (no EMA
+    update) -> decoder projection.  Returns (projected tokens [Nl, Cd, H, W], labels [N])."""
+    x = conv1x1(features, enc_w, enc_b)
+    out = vq_forward(x, weight, training=False, indices_override=indices_override)
+    return conv1x1(out["quantized"], dec_w, dec_b), out["indices"]
+
+
 def bincount(labels, K):
     """VQVAE.forward 'counts'.  models/autoencoders.py:165."""
     return torch.bincount(labels, minlength=K)

@@ -225,7 +225,43 @@ def gen_pixel_mask(name, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
 
 
+class _Pass(torch.nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.out_channels = self.base_channels = c
+
+    def forward(self, x):
+        return x
+
+
+def gen_vqvae_quantize(name, seed, C=40, D=24, K=96, nl=3, H=2, W=21):
+    """VQVAE.quantize in eval mode (label production, scripts/produce_vqvae_labels.py:37): the reference's two 1x1
+    convolutions around its quantizer on features whose projection lies near a codeword (so that the labels have clear
+    fp64 gaps); also the fp64 top-2 gap of every frame for the near-tie rule."""
+    torch.manual_seed(seed)
+    m = VQVAE(_Pass(C), _Pass(C), num_embeddings=K, embeddings_dim=D)
+    m.eval()
+    with torch.no_grad():
+        we = m.encoder_projection_layer.weight.view(D, C).double()
+        N = nl * H * W
+        target = m.vq.embedding.weight[torch.randint(0, K, (N,))].double() + 0.3 * torch.randn(N, D).double()
+        rows = (target - m.encoder_projection_layer.bias.double()) @ torch.linalg.pinv(we).t()
+        feats = rows.float().view(nl, H, W, C).permute(0, 3, 1, 2).contiguous()
+        tokens, labels = m.quantize(feats)
+        xp = m.encoder_projection_layer(feats).permute(0, 2, 3, 1).reshape(-1, D).double()
+        d = torch.cdist(xp, m.vq.embedding.weight.double()) ** 2
+        top2 = torch.topk(d, 2, dim=1, largest=False).values
+        gap = (top2[:, 1] - top2[:, 0]) / top2[:, 1].clamp_min(1e-30)
+    rec = {"state_" + k: t2n(v) for k, v in m.state_dict().items()}
+    rec.update(features=t2n(feats), out_tokens=t2n(tokens), out_labels=t2n(labels), gap=t2n(gap),
+               dims=np.array([C, D, K, nl, H, W]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "vqvae_quantize":
+        gen_vqvae_quantize("vqvae_quantize_eval", seed=81)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "kmeans_minibatch":       # only the scikit-learn fixture
         gen_kmeans_minibatch("kmeans_minibatch", seed=61)
         sys.exit(0)
@@ -242,6 +278,7 @@ if __name__ == "__main__":
     gen_masked_ce("masked_ce", seed=51)
     gen_kmeans_minibatch("kmeans_minibatch", seed=61)
     gen_pixel_mask("pixel_mask", seed=71)
+    gen_vqvae_quantize("vqvae_quantize_eval", seed=81)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):

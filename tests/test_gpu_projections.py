@@ -229,3 +229,31 @@ def test_label_production_matches_quantize(cuda_dev):
     m.train()
     lab = m.labels(batches[0]["images"])                        # never updates the EMA state, also in training mode
     assert torch.equal(m.vq.embedding.weight.detach(), w0) and lab.dtype == torch.int64 and lab.shape == (4 * 37,)
+
+
+@pytest.mark.parametrize("fuse", [True, "auto", False])
+def test_vqvae_quantize_eval_golden(cuda_dev, fuse):
+    """The reference's own VQVAE.quantize outputs (eval mode; tests/golden/vqvae_quantize_eval.npz, generated by importing
+    the reference) against the drop-in module: labels exactly (every frame of the fixture has a clear fp64 gap), projected
+    tokens to 1e-4 of their range -- through the fused projections (True / 'auto') and through the Conv2d path (False)."""
+    from pero_pretraining_b200 import VQVAE
+    g = load_golden("vqvae_quantize_eval")
+    C, D, K, nl, H, W = [int(v) for v in g["dims"]]
+    m = VQVAE(_Enc(C), _Dec(C), K, D)
+    m.load_state_dict({k[len("state_"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state_")})
+    m = m.to(cuda_dev).eval()
+    m.fuse_projections = fuse
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            tokens, labels = m.quantize(torch.from_numpy(g["features"]).to(cuda_dev))
+            only_labels = m.labels(torch.from_numpy(g["features"]).to(cuda_dev))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert float(g["gap"].min()) > EPS_TIE
+    assert np.array_equal(labels.cpu().numpy(), g["out_labels"])
+    assert np.array_equal(only_labels.cpu().numpy(), g["out_labels"])
+    ref = g["out_tokens"]
+    assert tokens.shape == ref.shape
+    assert float(np.abs(tokens.cpu().numpy() - ref).max()) <= 1e-4 * float(np.abs(ref).max())

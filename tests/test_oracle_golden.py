@@ -160,3 +160,17 @@ def test_pixel_mask_and_predictions_match_reference():
     np.testing.assert_array_equal(O.mask_pixels(g["x"], g["mask"], g["tile"]), g["masked"])
     np.testing.assert_array_equal(O.predict_labels(g["logits"]), g["argmax"])
     assert g["argmax"][0, 0] == 7          # the exact tie resolves to the first index
+
+
+def test_vqvae_quantize_eval_matches_reference():
+    """oracle.vqvae_quantize (1x1 projections as per-frame affine maps around the quantizer) against the reference's
+    VQVAE.quantize in eval mode (tests/golden/make_golden.py::gen_vqvae_quantize); the fixture's labels have clear
+    fp64 gaps."""
+    g = load_golden("vqvae_quantize_eval")
+    st = {k[len("state_"):]: T(v) for k, v in g.items() if k.startswith("state_")}
+    tokens, labels = O.vqvae_quantize(T(g["features"]), st["encoder_projection_layer.weight"], st["encoder_projection_layer.bias"],
+                                      st["decoder_projection_layer.weight"], st["decoder_projection_layer.bias"],
+                                      st["vq.embedding.weight"])
+    assert np.array_equal(labels.numpy(), g["out_labels"])
+    np.testing.assert_allclose(tokens.numpy(), g["out_tokens"], rtol=1e-5, atol=1e-6)
+    assert float(g["gap"].min()) > 0.05
