@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-configs", action="store_true", help="skip the BASELINE configs[2..4] legs (c3, c4, c5)")
     ap.add_argument("--skip-gpu-baseline", action="store_true", help="skip the torch-on-B200 reference leg")
+    ap.add_argument("--skip-dp-check", action="store_true", help="N > 1: skip the data-parallel == single-process check")
     ap.add_argument("--cpu-time-cap", type=float, default=150.0, help="reference arm: stop after this many seconds of CPU steps")
     ap.add_argument("--timeline", default=None, help="write the kernel timeline (CUPTI) of 2 step replays to this file")
     return ap.parse_args()
@@ -230,8 +231,9 @@ class DeviceStep:
     def __init__(self, batch, dev, dp):
         from pero_pretraining_b200 import ops
         self.ops, self.dp, c = ops, dp, CFG
-        self.x = batch["x"].to(dev).view(c["lines"], c["D"], c["frames"])
-        self.gq = batch["gq"].to(dev).view(c["lines"], c["D"], c["frames"])
+        self.lines = int(batch["x"].shape[0])          # CFG["lines"], or all ranks' lines in the equivalence check
+        self.x = batch["x"].to(dev).view(self.lines, c["D"], c["frames"])
+        self.gq = batch["gq"].to(dev).view(self.lines, c["D"], c["frames"])
         self.h = batch["h"].to(dev).view(-1, c["Dh"])
         self.W, self.b = batch["W"].to(dev), batch["b"].to(dev)
         self.weight = batch["weight"].to(dev)
@@ -241,7 +243,7 @@ class DeviceStep:
         self.M = int(rows.size)
         self.rows = torch.from_numpy(rows).to(dev)
         self.cb = ops.PreparedCodebook(c["K"], c["D"], dev).prepare(self.weight)
-        self.packed = torch.empty(c["lines"] * c["frames"], dtype=torch.int64, device=dev)
+        self.packed = torch.empty(self.lines * c["frames"], dtype=torch.int64, device=dev)
         self.head = ops.PreparedHead(c["V"], c["Dh"], dev)
         self.m_global = float(self.M)
         if dp:
@@ -299,7 +301,7 @@ class DeviceStep:
                               labels from its packed (distance, index) winners -- logits GEMM + LSE, dlogits, d_W | d_h,
                               scatter; the loss sum is read out of the partials at the end, off the GEMM chain."""
         ops, c = self.ops, CFG
-        N = c["lines"] * c["frames"]
+        N = self.lines * c["frames"]
         main = torch.cuda.current_stream()
         s_ema, s_ce = self.s_ema, self.s_ce
         s_ema.wait_stream(main)
@@ -312,7 +314,7 @@ class DeviceStep:
         with torch.cuda.stream(s_prep):
             ce_ws = ops.masked_ce_gather(self.h, self.rows, c["V"])
             self.head.prepare(self.W, self.b)        # head weights change every optimizer step in training
-        _, _, x_rows = ops.vq_assign(self.x, self.cb, c["lines"], c["frames"], True, want_rows=True, packed=packed,
+        _, _, x_rows = ops.vq_assign(self.x, self.cb, self.lines, c["frames"], True, want_rows=True, packed=packed,
                                      init_packed=True)
         s_ce.wait_stream(s_prep)
         assigned = torch.cuda.Event()
@@ -345,7 +347,7 @@ class DeviceStep:
         if gather_side:
             s_q.wait_stream(main)
         with torch.cuda.stream(s_q if gather_side else main):
-            q, loss_c = ops.vq_gather_st_mse(x_rows, idx, self.weight, c["lines"], c["frames"], True, 0.0, c["commitment_cost"])
+            q, loss_c = ops.vq_gather_st_mse(x_rows, idx, self.weight, self.lines, c["frames"], True, 0.0, c["commitment_cost"])
             gathered = torch.cuda.Event()
             gathered.record(torch.cuda.current_stream())
         if s_q is not main and not gather_side:
@@ -409,6 +411,58 @@ class DeviceStep:
         self.out = dict(idx=idx, x_rows=x_rows, q=q, loss_c=loss_c, g_x=g_x, sums=sums, loss_sum=loss_sum, lse=lse, ws=ws,
                         d_h=d_h, d_W=d_W, d_b=d_b, flat=flat)
         return self.out
+
+
+def dp_equivalence_check(dev, rank, world):
+    """Data-parallel step == single-process step on the concatenated batch, checked inside the multi-GPU bench
+    run so that the driver's own N > 1 runs carry the evidence (the -m gpu suite's multi-GPU test is skipped on a 1-GPU
+    box).  Every rank runs ONE data-parallel step from the bench's initial state; rank 0 also runs the single-GPU step on
+    all ranks' lines (regenerated from their seeds) and compares: indices exactly, the EMA-updated codebook, d_W, d_b and
+    the loss sum within fp32 re-association / bf16-operand tolerance; replicas must hold identical bits."""
+    try:
+        c = CFG
+        ds = DeviceStep(make_batch(rank), dev, True)
+        out = ds()
+        torch.cuda.synchronize()
+        V, Dh = c["V"], c["Dh"]
+        mine = dict(idx=out["idx"], weight=ds.weight, d_W=out["d_W"].reshape(-1), d_b=out["d_b"], loss=out["loss_sum"].reshape(1))
+        # replicas: the exchanged quantities and the updated codebook carry the same bits on every rank
+        sums = torch.stack([mine[k].contiguous().view(torch.int32).to(torch.int64).sum() for k in ("weight", "d_W", "d_b", "loss")])
+        gathered = [torch.empty_like(sums) for _ in range(world)]
+        torch.distributed.all_gather(gathered, sums)
+        replicas_identical = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+        all_idx = [torch.empty_like(mine["idx"]) for _ in range(world)]
+        torch.distributed.all_gather(all_idx, mine["idx"])
+        res = None
+        if rank == 0:
+            parts = [make_batch(r) for r in range(world)]
+            cat = dict(weight=parts[0]["weight"], W=parts[0]["W"], b=parts[0]["b"],
+                       x=torch.cat([p["x"] for p in parts]), gq=torch.cat([p["gq"] for p in parts]),
+                       h=torch.cat([p["h"] for p in parts]), mask=np.concatenate([p["mask"] for p in parts], axis=0))
+            single = DeviceStep(cat, dev, False)
+            ref = single()
+            torch.cuda.synchronize()
+
+            def rel(a, b):
+                return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+            res = {"world": world, "frames": int(single.lines * c["frames"]), "masked_frames": int(single.M),
+                   "replicas_bit_identical": replicas_identical,
+                   "indices_equal": bool(torch.equal(torch.cat(all_idx), ref["idx"])),
+                   "codebook_after_ema_max_rel_err": rel(mine["weight"], single.weight),
+                   "d_W_max_err_over_max": rel(mine["d_W"], ref["d_W"].reshape(-1)),
+                   "d_b_max_err_over_max": rel(mine["d_b"], ref["d_b"]),
+                   "loss_sum_rel_err": rel(mine["loss"], ref["loss_sum"].reshape(1))}
+            res["ok"] = bool(res["replicas_bit_identical"] and res["indices_equal"] and res["codebook_after_ema_max_rel_err"] < 1e-4
+                             and res["d_W_max_err_over_max"] < 2e-2 and res["d_b_max_err_over_max"] < 2e-2
+                             and res["loss_sum_rel_err"] < 1e-3)
+            del single, ref, cat, parts
+        del ds, out, mine
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:      # noqa: BLE001  (the check must never take the measurement down)
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def count_kernels(fn, align=None):
@@ -1070,6 +1124,8 @@ def our_arm(args):
         gpu_base["ours_over_fp32"] = value / gpu_base["fp32"]["value"]
         gpu_base["ours_over_bf16_autocast_head"] = value / gpu_base["bf16_autocast_head"]["value"]
     _log("gpu baseline leg done")
+    dp_check = dp_equivalence_check(dev, rank, world) if (dp and not args.skip_dp_check) else None
+    _log("data-parallel equivalence check done")
     configs = None
     if not args.skip_configs:
         configs = configs_legs(dev, dp, rank, world, flush, max(5, min(args.steps, 20)))
@@ -1092,6 +1148,7 @@ def our_arm(args):
                            "l2": "flushed (256 MiB write) between timed steps", "launch": launch_mode,
                            "host_affinity": (f"{len(bound_cpus)} CPUs local to the GPU (NVML)" if bound_cpus else "unchanged")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_baseline": gpu_base, "configs": configs,
+                "dp_check": dp_check,
                 "gpu_launches": (n_ours if n_ours > 0 else n_kernels) * args.steps, "kernels_per_step": n_kernels, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if dp:
