@@ -56,6 +56,12 @@ z = torch.randn(2, 30, 100, generator=g).to(dev).requires_grad_(True)
 MaskedCrossEntropyLoss(0.3)(z, torch.randint(0, 100, (2, 30), generator=g).to(dev),
                             (torch.rand(2, 30, generator=g) < 0.4).long().to(dev)).backward()
 PixelMasker().to(dev)(torch.rand(2, 3, 40, 100, generator=g).to(dev), (np.random.default_rng(1).random((2, 13)) < 0.5).astype(int))
+# 1x1 projections around the quantizer: split-bf16 projection GEMM (channels-first and rows), projected-codebook gather
+rows_p, xb_p = ops.proj_forward(torch.randn(3, 24, 37, generator=g).to(dev), torch.randn(16, 24, generator=g).to(dev),
+                                torch.randn(16, generator=g).to(dev), 3, 37, True, want_rows=True, want_bf16=True,
+                                packed=torch.empty(111, dtype=torch.int64, device=dev))
+table_p, _ = ops.proj_forward(torch.randn(50, 70, generator=g).to(dev), torch.randn(300, 70, generator=g).to(dev), None, 50, 1, False)
+ops.gather_rows_cf(table_p, torch.randint(0, 50, (111,), generator=g).to(dev), 3, 37)
 # peer exchange protocol, 4 emulated ranks in one cooperative launch
 bufs = [torch.zeros(16384 + 4096, dtype=torch.uint8, device=dev) for _ in range(4)]
 for b in bufs:
